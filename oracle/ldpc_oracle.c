@@ -1,0 +1,491 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE.  See ldpc_oracle.h for the role of this file.
+ * Plain-C restatement of the reference decode path; citations are /root/reference paths. */
+#define _GNU_SOURCE
+#include "ldpc_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------ */
+/* loader — src/core/ldpc.cpp:40-101 (header scan, bit_pos, max degree) and
+ *          src/core/sparse.h:91-153 (edge list in file order, rowN/colN in file order)        */
+/* ------------------------------------------------------------------------------------------ */
+
+static void parse_int_list(const char *s, int **list, int *n)
+{
+    /* "while (record >> index) push_back(index)" — ldpc.cpp:60-69 */
+    int cap = 16;
+    *list = (int *)malloc(sizeof(int) * cap);
+    *n = 0;
+    for (;;)
+    {
+        char *end;
+        long v = strtol(s, &end, 10);
+        if (end == s) break;
+        if (*n == cap) { cap *= 2; *list = (int *)realloc(*list, sizeof(int) * cap); }
+        (*list)[(*n)++] = (int)v;
+        s = end;
+    }
+}
+
+static int contains(const int *l, int n, int v)
+{
+    for (int i = 0; i < n; ++i) if (l[i] == v) return 1;
+    return 0;
+}
+
+static orc_code *load_impl(const char *path, int scan_header, int skip_lines)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) return NULL;
+    orc_code *c = (orc_code *)calloc(1, sizeof(orc_code));
+    char *line = NULL; size_t cap = 0; ssize_t len;
+    int ecap = 1024;
+    c->e_row = (int *)malloc(sizeof(int) * ecap);
+    c->e_col = (int *)malloc(sizeof(int) * ecap);
+    c->punct = (int *)malloc(sizeof(int)); c->shorten = (int *)malloc(sizeof(int));
+    int in_header = scan_header;
+    int maxr = 0, maxc = 0; /* numCols/numRows start at 0, sparse.h:103-104 */
+    while ((len = getline(&line, &cap, f)) >= 0)
+    {
+        if (skip_lines > 0) { --skip_lines; continue; }
+        if (in_header)
+        {
+            char *colon = strchr(line, ':');
+            if (colon)
+            { /* legacy "key: value" header lines; only puncture/shorten are interpreted, ldpc.cpp:53-72 */
+                *colon = 0;
+                if (strstr(line, "puncture")) { free(c->punct); parse_int_list(colon + 1, &c->punct, &c->n_punct); }
+                else if (strstr(line, "shorten")) { free(c->shorten); parse_int_list(colon + 1, &c->shorten, &c->n_short); }
+                continue;
+            }
+            in_header = 0; /* first line without ':' ends the header, ldpc.cpp:73-76 */
+        }
+        int r, cc, v;
+        int got = sscanf(line, "%d %d %d", &r, &cc, &v);
+        if (got < 2) continue; /* blank/garbage line: the reference pushes uninitialised ints (UB); ignored here */
+        if (c->nnz == ecap)
+        {
+            ecap *= 2;
+            c->e_row = (int *)realloc(c->e_row, sizeof(int) * ecap);
+            c->e_col = (int *)realloc(c->e_col, sizeof(int) * ecap);
+        }
+        /* every listed entry is a 1 over GF(2) (missing/zero value -> 1, sparse.h:124-128) */
+        c->e_row[c->nnz] = r; c->e_col[c->nnz] = cc; c->nnz++;
+        if (cc > maxc) maxc = cc;
+        if (r > maxr) maxr = r;
+    }
+    free(line);
+    fclose(f);
+    c->nc = maxc + 1; c->mc = maxr + 1; /* sparse.h:136-143 */
+
+    /* rowN / colN: per node the edge ids in file order (sparse.h:132-133) */
+    c->row_ptr = (int *)calloc(c->mc + 1, sizeof(int));
+    c->col_ptr = (int *)calloc(c->nc + 1, sizeof(int));
+    for (int e = 0; e < c->nnz; ++e) { c->row_ptr[c->e_row[e] + 1]++; c->col_ptr[c->e_col[e] + 1]++; }
+    for (int i = 0; i < c->mc; ++i) c->row_ptr[i + 1] += c->row_ptr[i];
+    for (int i = 0; i < c->nc; ++i) c->col_ptr[i + 1] += c->col_ptr[i];
+    c->row_edge = (int *)malloc(sizeof(int) * (c->nnz + 1));
+    c->col_edge = (int *)malloc(sizeof(int) * (c->nnz + 1));
+    int *rfill = (int *)calloc(c->mc, sizeof(int)), *cfill = (int *)calloc(c->nc, sizeof(int));
+    for (int e = 0; e < c->nnz; ++e)
+    {
+        int r = c->e_row[e], cc = c->e_col[e];
+        c->row_edge[c->row_ptr[r] + rfill[r]++] = e;
+        c->col_edge[c->col_ptr[cc] + cfill[cc]++] = e;
+    }
+    free(rfill); free(cfill);
+
+    c->max_degree = 0; /* ldpc.cpp:83-87 */
+    for (int i = 0; i < c->mc; ++i) { int d = c->row_ptr[i + 1] - c->row_ptr[i]; if (d > c->max_degree) c->max_degree = d; }
+    for (int i = 0; i < c->nc; ++i) { int d = c->col_ptr[i + 1] - c->col_ptr[i]; if (d > c->max_degree) c->max_degree = d; }
+
+    /* derived sizes, ldpc.h:47-59; note the list *sizes* are used, duplicates included */
+    c->kc = c->nc - c->mc;
+    c->nct = c->nc - c->n_punct - c->n_short;
+    c->mct = c->mc - c->n_punct;
+    c->kct = c->nct - c->mct;
+    /* bit_pos: ascending indices neither shortened nor punctured, ldpc.cpp:90-100 */
+    c->bit_pos = (int *)malloc(sizeof(int) * (c->nc + 1));
+    int nb = 0;
+    for (int i = 0; i < c->nc; ++i)
+    {
+        if (contains(c->shorten, c->n_short, i)) continue;
+        if (contains(c->punct, c->n_punct, i)) continue;
+        c->bit_pos[nb++] = i;
+    }
+    /* with duplicate-free in-range lists nb == nct; otherwise the reference would index out of range */
+    if (nb < c->nct) c->nct = nb;
+    return c;
+}
+
+orc_code *orc_load(const char *path) { return load_impl(path, 1, 0); }
+orc_code *orc_load_matrix(const char *path, int skip_lines) { return load_impl(path, 0, skip_lines); }
+
+void orc_free(orc_code *c)
+{
+    if (!c) return;
+    free(c->punct); free(c->shorten); free(c->bit_pos); free(c->e_row); free(c->e_col);
+    free(c->row_ptr); free(c->row_edge); free(c->col_ptr); free(c->col_edge); free(c);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* decoder — src/decoding/decoder.h:7-20 (sign, jacobian, minsum), decoder.cpp:11-78 (decode) */
+/* ------------------------------------------------------------------------------------------ */
+
+static inline int sgn(double x) { return 1 - 2 * (signbit(x) ? 1 : 0); } /* decoder.h:7-10: -0.0 is negative */
+static inline double dmin(double a, double b) { return (b < a) ? b : a; }  /* std::min */
+
+static double f_minsum(double x, double y) /* decoder.h:17-20 */
+{
+    return sgn(x) * sgn(y) * dmin(fabs(x), fabs(y));
+}
+
+static double f_jacobian(double x, double y) /* decoder.h:12-15 */
+{
+    return sgn(x) * sgn(y) * dmin(fabs(x), fabs(y)) + log((1 + exp(-fabs(x + y))) / (1 + exp(-fabs(x - y))));
+}
+
+int orc_is_codeword(const orc_code *c, const uint8_t *co) /* decoder.h:47-64 */
+{
+    for (int i = 0; i < c->mc; ++i)
+    {
+        uint8_t s = 0;
+        for (int k = c->row_ptr[i]; k < c->row_ptr[i + 1]; ++k) s ^= co[c->e_col[c->row_edge[k]]];
+        if (s) return 0;
+    }
+    return 1;
+}
+
+int orc_decode(const orc_code *c, const double *llr_in, int iterations, int early_term, int minsum,
+               double *llr_out, uint8_t *co)
+{
+    double (*f)(double, double) = minsum ? f_minsum : f_jacobian;
+    double *v2c = (double *)malloc(sizeof(double) * (c->nnz + 1));
+    double *c2v = (double *)calloc(c->nnz + 1, sizeof(double));
+    double *F = (double *)calloc(c->max_degree + 2, sizeof(double));
+    double *B = (double *)calloc(c->max_degree + 2, sizeof(double));
+    for (int i = 0; i < c->nc; ++i) { llr_out[i] = 0.0; co[i] = 0; } /* vectors are value-initialised, decoder.h:35-39 */
+
+    for (int e = 0; e < c->nnz; ++e) v2c[e] = llr_in[c->e_col[e]]; /* decoder.cpp:16-19 */
+
+    int I = 0;
+    while (I < iterations) /* decoder.cpp:22 */
+    {
+        for (int i = 0; i < c->mc; ++i) /* CN processing, decoder.cpp:25-45 */
+        {
+            const int *cn = c->row_edge + c->row_ptr[i];
+            int cw = c->row_ptr[i + 1] - c->row_ptr[i];
+            if (cw < 2) continue; /* degree 0/1 checks index out of range in the reference (UB); skipped */
+            F[0] = v2c[cn[0]];
+            B[cw - 1] = v2c[cn[cw - 1]];
+            for (int j = 1; j < cw; ++j)
+            {
+                F[j] = f(F[j - 1], v2c[cn[j]]);
+                B[cw - 1 - j] = f(B[cw - j], v2c[cn[cw - j - 1]]);
+            }
+            c2v[cn[0]] = B[1];
+            c2v[cn[cw - 1]] = F[cw - 2];
+            for (int j = 1; j < cw - 1; ++j) c2v[cn[j]] = f(F[j - 1], B[j + 1]);
+        }
+        for (int i = 0; i < c->nc; ++i) /* VN processing and app calc, decoder.cpp:48-64 */
+        {
+            double out = llr_in[i];
+            for (int k = c->col_ptr[i]; k < c->col_ptr[i + 1]; ++k) out += c2v[c->col_edge[k]];
+            llr_out[i] = out;
+            co[i] = (out <= 0);
+            for (int k = c->col_ptr[i]; k < c->col_ptr[i + 1]; ++k) v2c[c->col_edge[k]] = out - c2v[c->col_edge[k]];
+        }
+        if (early_term && orc_is_codeword(c, co)) break; /* decoder.cpp:66-72: break BEFORE ++I */
+        ++I;
+    }
+    free(v2c); free(c2v); free(F); free(B);
+    return I;
+}
+
+/* BEC decoder — decoder.h:145-155 (vn_update, cn_update), decoder.cpp:91-192 */
+static inline uint8_t bec_cn(uint8_t l, uint8_t r)
+{
+    return (l == ORC_ERASURE || r == ORC_ERASURE) ? ORC_ERASURE : (uint8_t)((l != 0) ^ (r != 0));
+}
+static inline uint8_t bec_vn(uint8_t l, uint8_t r, uint8_t xi)
+{
+    return (xi == l || xi == r) ? xi : ORC_ERASURE;
+}
+
+int orc_decode_bec(const orc_code *c, const uint8_t *llr_in, const uint8_t *cw_true, int iterations,
+                   int early_term, int deg1_compat, uint8_t *llr_out, uint8_t *co)
+{
+    uint8_t *v2c = (uint8_t *)malloc(c->nnz + 1), *c2v = (uint8_t *)calloc(c->nnz + 1, 1);
+    uint8_t *F = (uint8_t *)calloc(c->max_degree + 2, 1), *B = (uint8_t *)calloc(c->max_degree + 2, 1);
+    for (int i = 0; i < c->nc; ++i) { llr_out[i] = 0; co[i] = 0; }
+    for (int e = 0; e < c->nnz; ++e) v2c[e] = llr_in[c->e_col[e]]; /* decoder.cpp:96-99 */
+    int I = 0;
+    while (I < iterations)
+    {
+        for (int i = 0; i < c->mc; ++i) /* decoder.cpp:105-123 */
+        {
+            const int *cn = c->row_edge + c->row_ptr[i];
+            int cw = c->row_ptr[i + 1] - c->row_ptr[i];
+            if (cw < 2) continue;
+            F[0] = v2c[cn[0]];
+            B[cw - 1] = v2c[cn[cw - 1]];
+            for (int j = 1; j < cw; ++j)
+            {
+                F[j] = bec_cn(F[j - 1], v2c[cn[j]]);
+                B[cw - 1 - j] = bec_cn(B[cw - j], v2c[cn[cw - j - 1]]);
+            }
+            c2v[cn[0]] = B[1];
+            c2v[cn[cw - 1]] = F[cw - 2];
+            for (int j = 1; j < cw - 1; ++j) c2v[cn[j]] = bec_cn(F[j - 1], B[j + 1]);
+        }
+        for (int i = 0; i < c->nc; ++i) /* decoder.cpp:126-167 */
+        {
+            const int *vn = c->col_edge + c->col_ptr[i];
+            int vw = c->col_ptr[i + 1] - c->col_ptr[i];
+            uint8_t xi = cw_true[i];
+            if (llr_in[i] != ORC_ERASURE)
+            {
+                for (int k = 0; k < vw; ++k) v2c[vn[k]] = xi;
+                llr_out[i] = xi;
+                co[i] = xi;
+            }
+            else if (vw == 0)
+            {
+                llr_out[i] = ORC_ERASURE; co[i] = 1; /* isolated erased bit (reference: UB) */
+            }
+            else if (vw == 1)
+            {
+                /* reference reads mExMsgF[-1] (decoder.cpp:155-156, UB).  Observed value: 0. */
+                v2c[vn[0]] = deg1_compat ? 0 : ORC_ERASURE;
+                llr_out[i] = c2v[vn[0]];
+                co[i] = (llr_out[i] == ORC_ERASURE) ? 1 : xi;
+            }
+            else
+            {
+                F[0] = c2v[vn[0]];
+                B[vw - 1] = c2v[vn[vw - 1]];
+                for (int j = 1; j < vw; ++j)
+                {
+                    F[j] = bec_vn(F[j - 1], c2v[vn[j]], xi);
+                    B[vw - 1 - j] = bec_vn(B[vw - j], c2v[vn[vw - j - 1]], xi);
+                }
+                v2c[vn[0]] = B[1];
+                v2c[vn[vw - 1]] = F[vw - 2];
+                for (int j = 1; j < vw - 1; ++j) v2c[vn[j]] = bec_vn(F[j - 1], B[j + 1], xi);
+                llr_out[i] = F[vw - 1];
+                /* "-channelInput[i]" is gf2(~v) == 1 for both v (gf2.cpp:5-8) */
+                co[i] = (llr_out[i] == ORC_ERASURE) ? 1 : xi;
+            }
+        }
+        if (early_term) /* decoder.cpp:169-186: stop when no output is erased */
+        {
+            int found = 0;
+            for (int i = 0; i < c->nc; ++i) if (llr_out[i] == ORC_ERASURE) { found = 1; break; }
+            if (!found) break;
+        }
+        ++I;
+    }
+    free(v2c); free(c2v); free(F); free(B);
+    return I;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* channel LLR rules — src/sim/channel.cpp                                                    */
+/* ------------------------------------------------------------------------------------------ */
+
+void orc_llr_awgn(const orc_code *c, const double *y, double sigma2, double *llr) /* channel.cpp:70-93 */
+{
+    for (int i = 0; i < c->n_punct; ++i) llr[c->punct[i]] = 0.0;
+    for (int i = 0; i < c->n_short; ++i) llr[c->shorten[i]] = 99999.9;
+    for (int i = 0; i < c->nct; ++i) llr[c->bit_pos[i]] = 2 * y[i] / sigma2;
+}
+
+void orc_llr_bsc(const orc_code *c, const uint8_t *y, double eps, double *llr) /* channel.cpp:137-162 */
+{
+    const double delta = log((1 - eps) / eps);
+    for (int i = 0; i < c->n_punct; ++i) llr[c->punct[i]] = 0.0;
+    for (int i = 0; i < c->n_short; ++i) llr[c->shorten[i]] = delta;
+    for (int i = 0; i < c->nct; ++i) llr[c->bit_pos[i]] = delta * (1 - 2 * (int)y[i]);
+}
+
+void orc_llr_bec(const orc_code *c, const uint8_t *y, const uint8_t *cw, uint8_t *llr) /* channel.cpp:207-229 */
+{
+    for (int i = 0; i < c->n_punct; ++i) llr[c->punct[i]] = ORC_ERASURE;
+    /* reference indexes mX (length nct) with the code index s (latent bug, channel.cpp:221); the true bit is meant */
+    for (int i = 0; i < c->n_short; ++i) llr[c->shorten[i]] = cw[c->shorten[i]];
+    for (int i = 0; i < c->nct; ++i) llr[c->bit_pos[i]] = y[i];
+}
+
+int orc_count_bit_errors(const orc_code *c, const uint8_t *co, const uint8_t *cw) /* ldpcsim.cpp:184-188 */
+{
+    int n = 0;
+    for (int i = 0; i < c->nct; ++i) n += (co[c->bit_pos[i]] != cw[c->bit_pos[i]]);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* GF(2) helpers — src/core/sparse.h                                                          */
+/* ------------------------------------------------------------------------------------------ */
+
+void orc_multiply_left(const orc_code *g, const uint8_t *left, uint8_t *result) /* sparse.h:162-172: result += left*G */
+{
+    for (int j = 0; j < g->nc; ++j)
+        for (int k = g->col_ptr[j]; k < g->col_ptr[j + 1]; ++k) result[j] ^= (left[g->e_row[g->col_edge[k]]] & 1);
+}
+
+void orc_multiply_right(const orc_code *h, const uint8_t *right, uint8_t *result) /* sparse.h:196-206 */
+{
+    for (int i = 0; i < h->mc; ++i)
+        for (int k = h->row_ptr[i]; k < h->row_ptr[i + 1]; ++k) result[i] ^= (right[h->e_col[h->row_edge[k]]] & 1);
+}
+
+int orc_rank(const orc_code *h) /* value of sparse.h:227-294 (rank is algorithm independent): dense bit-packed elimination */
+{
+    int words = (h->nc + 63) / 64;
+    uint64_t *m = (uint64_t *)calloc((size_t)h->mc * words, sizeof(uint64_t));
+    for (int e = 0; e < h->nnz; ++e) m[(size_t)h->e_row[e] * words + h->e_col[e] / 64] ^= 1ull << (h->e_col[e] % 64);
+    int rank = 0;
+    for (int col = 0; col < h->nc && rank < h->mc; ++col)
+    {
+        int w = col / 64; uint64_t bit = 1ull << (col % 64);
+        int piv = -1;
+        for (int r = rank; r < h->mc; ++r) if (m[(size_t)r * words + w] & bit) { piv = r; break; }
+        if (piv < 0) continue;
+        if (piv != rank)
+            for (int k = 0; k < words; ++k) { uint64_t t = m[(size_t)piv * words + k]; m[(size_t)piv * words + k] = m[(size_t)rank * words + k]; m[(size_t)rank * words + k] = t; }
+        for (int r = rank + 1; r < h->mc; ++r)
+            if (m[(size_t)r * words + w] & bit)
+                for (int k = w; k < words; ++k) m[(size_t)r * words + k] ^= m[(size_t)rank * words + k];
+        ++rank;
+    }
+    free(m);
+    return rank;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* specification of the counter-based channel (new; replaces mt19937_64 of channel.cpp:10-11)  */
+/* ------------------------------------------------------------------------------------------ */
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r)
+    {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static void philox_block(uint64_t seed, uint32_t point, uint32_t stream, uint64_t frame, uint32_t j, uint32_t out[4])
+{
+    uint32_t ctr[4] = {j, (uint32_t)frame, (uint32_t)(frame >> 32), (point & 0xFFFFFFu) | (stream << 24)};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    orc_philox4x32_10(ctr, key, out);
+}
+
+void orc_normal_pair(uint64_t seed, uint32_t point, uint64_t frame, uint32_t j, double z[2])
+{
+    uint32_t x[4];
+    philox_block(seed, point, 0, frame, j, x);
+    const double two_m53 = 1.0 / 9007199254740992.0;
+    double u1 = ((double)((((uint64_t)x[1] << 32) | x[0]) >> 11) + 1.0) * two_m53; /* (0,1] */
+    double u2 = (double)((((uint64_t)x[3] << 32) | x[2]) >> 11) * two_m53;         /* [0,1) */
+    double r = sqrt(-2.0 * log(u1));
+    double a = 6.283185307179586 * u2;
+    z[0] = r * cos(a);
+    z[1] = r * sin(a);
+}
+
+static uint32_t prob_threshold(double p)
+{
+    double t = floor(p * 4294967296.0);
+    if (t <= 0) return 0;
+    if (t >= 4294967295.0) return 4294967295u;
+    return (uint32_t)t;
+}
+
+void orc_channel_frame(const orc_code *c, const orc_code *g, int kind, double x, uint64_t seed,
+                       uint32_t point, uint64_t frame, uint8_t *cw, double *llr_f64, uint8_t *llr_u8)
+{
+    memset(cw, 0, c->nc);
+    if (g)
+    { /* fresh random information word per frame (stream 1), cw = u*G (channel.cpp:44-52 without the
+         accumulate-into-previous-codeword quirk of sparse.h:169) */
+        uint8_t *u = (uint8_t *)malloc(g->mc);
+        for (int k = 0; k < g->mc; ++k)
+        {
+            uint32_t w[4];
+            philox_block(seed, point, 1, frame, (uint32_t)k >> 7, w);
+            u[k] = (w[(k >> 5) & 3] >> (k & 31)) & 1;
+        }
+        orc_multiply_left(g, u, cw);
+        free(u);
+    }
+    if (kind == ORC_AWGN)
+    {
+        double sigma2 = pow(10, -x / 10), sigma = sqrt(sigma2); /* channel.cpp:39-41 */
+        double *y = (double *)malloc(sizeof(double) * (c->nct + 1));
+        for (int t = 0; t < c->nct; t += 2)
+        {
+            double z[2];
+            orc_normal_pair(seed, point, frame, (uint32_t)t >> 1, z);
+            for (int k = 0; k < 2 && t + k < c->nct; ++k)
+            {
+                double xs = 1 - 2 * (int)cw[c->bit_pos[t + k]]; /* channel.cpp:58 */
+                y[t + k] = z[k] * sigma + xs;                    /* channel.cpp:66: normal(0,sigma)() + x */
+            }
+        }
+        orc_llr_awgn(c, y, sigma2, llr_f64);
+        free(y);
+    }
+    else
+    {
+        uint32_t thr = prob_threshold(x);
+        uint8_t *y = (uint8_t *)malloc(c->nct + 1);
+        for (int t = 0; t < c->nct; ++t)
+        {
+            uint32_t w[4];
+            philox_block(seed, point, 0, frame, (uint32_t)t >> 2, w);
+            int hit = w[t & 3] < thr;
+            uint8_t b = cw[c->bit_pos[t]];
+            if (kind == ORC_BSC) y[t] = b ^ (uint8_t)hit;            /* channel.cpp:131 */
+            else y[t] = hit ? ORC_ERASURE : b;                       /* channel.cpp:201 */
+        }
+        if (kind == ORC_BSC) orc_llr_bsc(c, y, x, llr_f64);
+        else orc_llr_bec(c, y, cw, llr_u8);
+        free(y);
+    }
+}
+
+void orc_sim_point(const orc_code *c, const orc_code *g, int kind, int minsum, int iterations, int early_term,
+                   int bec_deg1_compat, double x, uint64_t seed, uint32_t point, uint64_t frame0,
+                   uint64_t nframes, int threads, uint64_t counters[4])
+{
+    uint64_t fec = 0, bec = 0, iters = 0;
+    if (threads < 1) threads = 1;
+#pragma omp parallel num_threads(threads) reduction(+ : fec, bec, iters)
+    {
+        uint8_t *cw = (uint8_t *)malloc(c->nc), *co = (uint8_t *)malloc(c->nc);
+        uint8_t *lu = (uint8_t *)malloc(c->nc), *lou = (uint8_t *)malloc(c->nc);
+        double *lf = (double *)malloc(sizeof(double) * c->nc), *lo = (double *)malloc(sizeof(double) * c->nc);
+#pragma omp for schedule(dynamic, 4)
+        for (uint64_t t = 0; t < nframes; ++t)
+        { /* frame loop body, ldpcsim.cpp:160-190 */
+            orc_channel_frame(c, g, kind, x, seed, point, frame0 + t, cw, lf, lu);
+            int it = (kind == ORC_BEC) ? orc_decode_bec(c, lu, cw, iterations, early_term, bec_deg1_compat, lou, co)
+                                       : orc_decode(c, lf, iterations, early_term, minsum, lo, co);
+            iters += (uint64_t)it;
+            int be = orc_count_bit_errors(c, co, cw);
+            if (be > 0) { bec += (uint64_t)be; ++fec; }
+        }
+        free(cw); free(co); free(lu); free(lou); free(lf); free(lo);
+    }
+    counters[0] = fec; counters[1] = bec; counters[2] = nframes; counters[3] = iters;
+}
