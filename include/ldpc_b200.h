@@ -1,0 +1,200 @@
+/* libldpc_b200 — C ABI of the B200-native LDPC decode path.
+ *
+ * Part 1 is the drop-in boundary: the six symbols and four POD structs that the reference's
+ * libldpc.so exports (reference: src/shared.cpp:9-78, src/core/functions.h:107-127,
+ * src/sim/ldpcsim.h:23-31) and that pyLDPC/ldpc.py binds through ctypes (pyLDPC/ldpc.py:8-50,
+ * 102,130,160-166,200,216).  Same names, same argument meaning, same struct layouts (LP64),
+ * structs passed BY VALUE exactly as the reference does.
+ *
+ * Part 2 is the handle-based API the tests, bench.py, the ldpcsim CLI and the multi-GPU host use.
+ * Plain pointers and sizes only; no C++/torch types.  Every int-returning function returns 0 on
+ * success and a negative value on failure with the text available from ldpc_b200_last_error().
+ * There is no CPU fallback: anything that decodes or simulates needs a CUDA device and fails
+ * loudly without one.  Loader / GF(2) helpers are host-side (they are one-off O(nnz) utilities in
+ * the reference as well) and work without a GPU.
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 1 — reference-compatible boundary                                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+/* reference: src/core/functions.h:107-112 (16 bytes: bool @0, u32 @4, char* @8) */
+typedef struct
+{
+    bool earlyTerm;
+    uint32_t iterations;
+    const char *type; /* "BP_MS" = min-sum; anything else = BP (src/decoding/decoder.h:76) */
+} decoder_param;
+
+/* reference: src/core/functions.h:114-119 (40 bytes) */
+typedef struct
+{
+    uint64_t seed;
+    double xRange[3]; /* MIN MAX STEP, half-open sweep (src/sim/ldpcsim.cpp:104-110) */
+    const char *type; /* "AWGN" | "BSC" | "BEC" */
+} channel_param;
+
+/* reference: src/core/functions.h:121-127 (32 bytes) */
+typedef struct
+{
+    uint32_t threads; /* accepted for compatibility; the GPU path ignores it */
+    uint64_t maxFrames;
+    uint64_t fec;
+    const char *resultFile;
+} simulation_param;
+
+/* reference: src/sim/ldpcsim.h:23-31 (48 bytes); caller-allocated arrays indexed by point in
+ * execution order (reversed for BSC/BEC, src/sim/ldpcsim.cpp:114-122) */
+typedef struct
+{
+    double *fer;
+    double *ber;
+    double *avg_iter;
+    double *time;
+    uint64_t *fec;
+    uint64_t *frames;
+} sim_results_t;
+
+/* replaces src/shared.cpp:11-24 — loads the code (and optional generator) into the process-global
+ * context; prints "Error: ..." and exit(EXIT_FAILURE)s on file errors like src/core/ldpc.cpp:16-20 */
+void ldpc_setup(const char *pcFile, const char *genFile, int *n, int *m, int *nct, int *mct);
+/* replaces src/shared.cpp:26-30 — blocking Monte-Carlo sweep; fills results[] per point; polls *stopFlag */
+void simulate(decoder_param decoderParams, channel_param channelParam, simulation_param simParam,
+              sim_results_t *results, bool *stopFlag);
+/* replaces src/shared.cpp:32-35 */
+int calculate_rank(void);
+/* replaces src/shared.cpp:37-45 — infoWord[kct] -> codeWord[nct] (transmitted positions of u*G) */
+void encode(uint8_t *infoWord, uint8_t *codeWord);
+/* replaces src/shared.cpp:47-65 — llr[nct] in, llrOut[nct] out, returns the 0-based iteration count
+ * (src/decoding/decoder.cpp:66-77).  Punctured and shortened inputs are 0.0 (shared.cpp:50).
+ * Unlike the reference there is no sticky min-sum state between calls (reference quirk: decoder.h:73-80). */
+int decode(decoder_param decoderParams, double *llr, double *llrOut);
+/* replaces src/shared.cpp:67-77 — word[nc] -> syndrome[mc] */
+void syndrome(uint8_t *word, uint8_t *syndrome);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 2 — handle-based B200 API                                                             */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct ldpc_b200_ctx ldpc_b200_ctx;
+
+enum { LDPC_B200_F64 = 0, LDPC_B200_F32 = 1 };          /* arithmetic / message type of the decoder */
+enum { LDPC_B200_AUTO = 0, LDPC_B200_SMEM = 1, LDPC_B200_GLOBAL = 2 }; /* message residency */
+
+typedef struct
+{
+    int nc, mc, nnz, kc;     /* src/core/ldpc.h:47-53 */
+    int nct, mct, kct;       /* src/core/ldpc.h:55-59 */
+    int n_punct, n_short;
+    int max_degree;          /* src/core/ldpc.cpp:83-87 */
+    int max_check_degree, max_var_degree;
+    int has_generator, g_rows, g_cols, g_nnz;
+} ldpc_b200_code_info;
+
+typedef struct
+{
+    int precision;        /* LDPC_B200_F64 (bit-exact parity mode, default) | LDPC_B200_F32 */
+    int residency;        /* LDPC_B200_AUTO | _SMEM | _GLOBAL */
+    int frames_per_cta;   /* 0 = auto (power of two, 1..32) */
+    int threads_per_cta;  /* 0 = auto */
+    int ctas;             /* 0 = auto (148 x resident CTAs) */
+    int bec_deg1_compat;  /* 1 (default) = erased degree-1 variable nodes send 0 like the reference's UB outcome */
+} ldpc_b200_tuning;
+
+const char *ldpc_b200_last_error(void);
+const char *ldpc_b200_version(void);
+/* number of CUDA devices visible (0 when there is no GPU / driver) */
+int ldpc_b200_device_count(void);
+
+/* Loads pcFile (+ genFile, may be NULL/"") on the host.  device >= 0 binds the context to that CUDA
+ * device (tables are uploaded lazily on first use); device = -1 keeps it host-only.  NULL on failure. */
+ldpc_b200_ctx *ldpc_b200_open(const char *pcFile, const char *genFile, int device);
+void ldpc_b200_close(ldpc_b200_ctx *ctx);
+int ldpc_b200_info(const ldpc_b200_ctx *ctx, ldpc_b200_code_info *info);
+int ldpc_b200_set_tuning(ldpc_b200_ctx *ctx, const ldpc_b200_tuning *t);
+int ldpc_b200_get_tuning(const ldpc_b200_ctx *ctx, ldpc_b200_tuning *t);
+
+/* host-side views of the loaded code (file order; sizes from ldpc_b200_info) */
+int ldpc_b200_get_edges(const ldpc_b200_ctx *ctx, int *rows /*[nnz]*/, int *cols /*[nnz]*/);
+int ldpc_b200_get_bit_pos(const ldpc_b200_ctx *ctx, int *bit_pos /*[nct]*/);
+int ldpc_b200_get_puncture(const ldpc_b200_ctx *ctx, int *punct /*[n_punct]*/, int *shorten /*[n_short]*/);
+/* device schedule for the current tuning (for tests): for every edge e (file order) the check-major
+ * message slot it lives in; n_slots = padded slot count */
+int ldpc_b200_get_layout(ldpc_b200_ctx *ctx, int *edge_slot /*[nnz]*/, int *n_slots, int *frames_per_cta,
+                         int *threads_per_cta, int *residency);
+
+/* GF(2) helpers on the host (reference: src/core/sparse.h:162-218,227-294) */
+int ldpc_b200_rank(const ldpc_b200_ctx *ctx);
+int ldpc_b200_encode(const ldpc_b200_ctx *ctx, const uint8_t *info /*[g_rows]*/, uint8_t *cw_full /*[nc]*/);
+int ldpc_b200_syndrome(const ldpc_b200_ctx *ctx, const uint8_t *word /*[nc]*/, uint8_t *synd /*[mc]*/);
+
+/* Batched flooding decode on the GPU, HOST buffers (copies are part of the call).
+ *   llr      [n_frames][nc]  full-length LLRs (punctured/shortened positions included)
+ *   llr_out  [n_frames][nc]  posterior LLRs after the last executed iteration (may be NULL)
+ *   hard     [n_frames][nc]  decisions (LLR <= 0 -> 1, src/decoding/decoder.cpp:58)   (may be NULL)
+ *   iters    [n_frames]      reference iteration count (0-based on success)              (may be NULL)
+ * Decoder type/iterations/early termination come from decoder_param (reference semantics). */
+int ldpc_b200_decode_batch(ldpc_b200_ctx *ctx, decoder_param dp, const double *llr, int64_t n_frames,
+                           double *llr_out, uint8_t *hard, int32_t *iters);
+/* Same with DEVICE buffers (already resident in HBM), asynchronous on `stream` (cudaStream_t). */
+int ldpc_b200_decode_batch_device(ldpc_b200_ctx *ctx, decoder_param dp, const double *d_llr, int64_t n_frames,
+                                  double *d_llr_out, uint8_t *d_hard, int32_t *d_iters, void *stream);
+
+/* BEC decode, HOST buffers: in[n][nc] in {0,1,'E'}, cw[n][nc] true bits (genie check of the
+ * reference's vn_update, src/decoding/decoder.h:145-149). */
+int ldpc_b200_decode_bec_batch(ldpc_b200_ctx *ctx, decoder_param dp, const uint8_t *in, const uint8_t *cw,
+                               int64_t n_frames, uint8_t *out, uint8_t *hard, int32_t *iters);
+
+/* Philox channel only: writes the decoder inputs the simulator would generate for global frames
+ * [frame0, frame0+n) of sweep point `point`: cw[n][nc] (may be NULL), and llr[n][nc] doubles
+ * (AWGN/BSC) or llr_u8[n][nc] (BEC).  HOST buffers. */
+int ldpc_b200_channel(ldpc_b200_ctx *ctx, const char *channel, double x, uint64_t seed, uint32_t point,
+                      uint64_t frame0, int64_t n_frames, uint8_t *cw, double *llr, uint8_t *llr_u8);
+
+/* One Monte-Carlo round of one sweep point, fully on the GPU (channel -> decode -> accounting):
+ * global frames [frame0, frame0+n_frames).  counters[4] += {frame errors, bit errors, frames,
+ * sum of reference iteration counts} (src/sim/ldpcsim.cpp:175-190).  Blocking; counters on the host.
+ * device_ms (may be NULL) receives the CUDA-event time of the kernel(s). */
+int ldpc_b200_sim_point(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
+                        uint32_t point, uint64_t frame0, uint64_t n_frames, uint64_t counters[4], float *device_ms);
+/* Asynchronous variant: d_counters is a DEVICE array of 5 uint64 that the kernel accumulates into
+ * ({frame errors, bit errors, frames, sum of reference iteration counts, sum of executed iterations}). */
+int ldpc_b200_sim_point_async(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
+                              uint32_t point, uint64_t frame0, uint64_t n_frames, uint64_t *d_counters, void *stream);
+
+/* Whole sweep with the reference's semantics (x list, reversed order for BSC/BEC, stop rule, results
+ * file layout — src/sim/ldpcsim.cpp:97-263).  rank/world shard the frames of every round across
+ * processes; `allreduce` (may be NULL when world == 1) is called once per round with a small host
+ * array of uint64 counters to be summed over ranks (the caller wires it to NCCL/gloo).  quiet != 0 suppresses the console table. */
+typedef void (*ldpc_b200_allreduce_fn)(uint64_t *values, int n, void *user); /* in-place sum over ranks */
+int ldpc_b200_simulate(ldpc_b200_ctx *ctx, decoder_param dp, channel_param cp, simulation_param sp,
+                       sim_results_t *results, bool *stopFlag, int rank, int world,
+                       ldpc_b200_allreduce_fn allreduce, void *user, int quiet);
+
+/* execution statistics of the last simulate/sim_point/decode_batch call on this context */
+typedef struct
+{
+    double device_ms;        /* CUDA-event time summed over kernel launches */
+    uint64_t launches;       /* kernel launches */
+    uint64_t frames;         /* frames decoded */
+    uint64_t edge_iterations;/* sum over frames of executed iterations x nnz */
+    int frames_per_cta, threads_per_cta, ctas, residency, precision;
+    size_t smem_bytes;
+} ldpc_b200_stats;
+int ldpc_b200_get_stats(const ldpc_b200_ctx *ctx, ldpc_b200_stats *s);
+int ldpc_b200_reset_stats(ldpc_b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H */

@@ -1,0 +1,259 @@
+#include "code.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <queue>
+#include <stdexcept>
+
+namespace b200
+{
+    namespace
+    {
+        // whitespace separated integers until the first token that is not one ("record >> index" loop)
+        std::vector<int> leading_ints(const char *s)
+        {
+            std::vector<int> v;
+            for (;;)
+            {
+                char *end = nullptr;
+                long x = std::strtol(s, &end, 10);
+                if (end == s) break;
+                v.push_back(static_cast<int>(x));
+                s = end;
+            }
+            return v;
+        }
+    } // namespace
+
+    // Semantics follow src/core/ldpc.cpp:40-101 and src/core/sparse.h:91-153:
+    //  * leading lines containing ':' form the header; only keys containing "puncture"/"shorten" matter
+    //  * every following line is "row col [value]"; any listed entry is a one; dimensions = max index + 1
+    //  * edge ids are file positions; per-node adjacency keeps file order
+    // Lines that do not start with two integers (blank/trailing lines) are ignored; the reference pushes
+    // uninitialised indices for those (undefined behaviour), so there is nothing to be compatible with.
+    void HostCode::load(const std::string &path, bool parse_header)
+    {
+        std::ifstream in(path);
+        if (!in.good()) throw std::runtime_error("can not open file for reading");
+        *this = HostCode();
+        std::string line;
+        bool header = parse_header;
+        int max_r = 0, max_c = 0;
+        while (std::getline(in, line))
+        {
+            if (header)
+            {
+                const auto colon = line.find(':');
+                if (colon != std::string::npos)
+                {
+                    const std::string key = line.substr(0, colon);
+                    if (key.find("puncture") != std::string::npos)
+                    {
+                        auto v = leading_ints(line.c_str() + colon + 1);
+                        puncture.insert(puncture.end(), v.begin(), v.end());
+                    }
+                    else if (key.find("shorten") != std::string::npos)
+                    {
+                        auto v = leading_ints(line.c_str() + colon + 1);
+                        shorten.insert(shorten.end(), v.begin(), v.end());
+                    }
+                    continue;
+                }
+                header = false;
+            }
+            auto v = leading_ints(line.c_str());
+            if (v.size() < 2) continue;
+            if (v[0] < 0 || v[1] < 0) throw std::runtime_error("negative index in code file");
+            e_row.push_back(v[0]);
+            e_col.push_back(v[1]);
+            max_r = std::max(max_r, v[0]);
+            max_c = std::max(max_c, v[1]);
+        }
+        nnz = static_cast<int>(e_row.size());
+        mc = max_r + 1;
+        nc = max_c + 1;
+
+        row_ptr.assign(mc + 1, 0);
+        col_ptr.assign(nc + 1, 0);
+        for (int e = 0; e < nnz; ++e) { ++row_ptr[e_row[e] + 1]; ++col_ptr[e_col[e] + 1]; }
+        std::partial_sum(row_ptr.begin(), row_ptr.end(), row_ptr.begin());
+        std::partial_sum(col_ptr.begin(), col_ptr.end(), col_ptr.begin());
+        row_edge.assign(nnz, 0);
+        col_edge.assign(nnz, 0);
+        {
+            std::vector<int> rf(row_ptr.begin(), row_ptr.end() - 1), cf(col_ptr.begin(), col_ptr.end() - 1);
+            for (int e = 0; e < nnz; ++e) { row_edge[rf[e_row[e]]++] = e; col_edge[cf[e_col[e]]++] = e; }
+        }
+        max_cn_degree = max_vn_degree = 0;
+        min_cn_degree = nnz;
+        for (int i = 0; i < mc; ++i)
+        {
+            max_cn_degree = std::max(max_cn_degree, row_ptr[i + 1] - row_ptr[i]);
+            min_cn_degree = std::min(min_cn_degree, row_ptr[i + 1] - row_ptr[i]);
+        }
+        for (int i = 0; i < nc; ++i) max_vn_degree = std::max(max_vn_degree, col_ptr[i + 1] - col_ptr[i]);
+        max_degree = std::max(max_cn_degree, max_vn_degree);
+
+        std::vector<char> removed(nc, 0);
+        for (int p : puncture) if (p >= 0 && p < nc) removed[p] = 1;
+        for (int s : shorten) if (s >= 0 && s < nc) removed[s] = 1;
+        for (int i = 0; i < nc; ++i) if (!removed[i]) bit_pos.push_back(i);
+    }
+
+    void HostCode::multiply_left(const uint8_t *left, uint8_t *result) const
+    {
+        for (int e = 0; e < nnz; ++e) result[e_col[e]] ^= (left[e_row[e]] & 1);
+    }
+
+    void HostCode::multiply_right(const uint8_t *right, uint8_t *result) const
+    {
+        for (int e = 0; e < nnz; ++e) result[e_row[e]] ^= (right[e_col[e]] & 1);
+    }
+
+    // GF(2) rank by bit-packed Gauss elimination over 64-bit words (same value as the list-based
+    // elimination of sparse.h:227-294).
+    int HostCode::rank() const
+    {
+        const size_t words = (static_cast<size_t>(nc) + 63) / 64;
+        std::vector<uint64_t> m(static_cast<size_t>(mc) * words, 0);
+        for (int e = 0; e < nnz; ++e) m[e_row[e] * words + (e_col[e] >> 6)] ^= 1ull << (e_col[e] & 63);
+        int r = 0;
+        for (int c = 0; c < nc && r < mc; ++c)
+        {
+            const size_t w = c >> 6;
+            const uint64_t bit = 1ull << (c & 63);
+            int piv = -1;
+            for (int i = r; i < mc; ++i) if (m[i * words + w] & bit) { piv = i; break; }
+            if (piv < 0) continue;
+            if (piv != r) std::swap_ranges(m.begin() + piv * words, m.begin() + (piv + 1) * words, m.begin() + r * words);
+            const uint64_t *src = &m[r * words];
+            for (int i = r + 1; i < mc; ++i)
+            {
+                uint64_t *dst = &m[i * words];
+                if (dst[w] & bit) for (size_t k = w; k < words; ++k) dst[k] ^= src[k];
+            }
+            ++r;
+        }
+        return r;
+    }
+
+    namespace
+    {
+        struct Group
+        {
+            int degree;
+            std::vector<int> nodes; // <= npw node ids
+        };
+
+        // Same-degree nodes are packed npw at a time (one warp executes one group per round with all its
+        // node threads on equal trip counts); groups are then spread over warps longest-first.
+        std::vector<std::vector<Group>> schedule(const std::vector<int> &degree, int npw, int warps)
+        {
+            std::vector<int> order(degree.size());
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return degree[a] > degree[b]; });
+            std::vector<Group> groups;
+            for (size_t i = 0; i < order.size();)
+            {
+                Group g;
+                g.degree = degree[order[i]];
+                while (i < order.size() && degree[order[i]] == g.degree && (int)g.nodes.size() < npw) g.nodes.push_back(order[i++]);
+                groups.push_back(std::move(g));
+            }
+            using Load = std::pair<long, int>; // (load, warp)
+            std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+            for (int w = 0; w < warps; ++w) heap.push({0, w});
+            std::vector<std::vector<Group>> per_warp(warps);
+            for (auto &g : groups)
+            {
+                auto [load, w] = heap.top();
+                heap.pop();
+                per_warp[w].push_back(g);
+                heap.push({load + g.degree + 3, w});
+            }
+            return per_warp;
+        }
+    } // namespace
+
+    void TileLayout::build(const HostCode &code, int fpc_, int threads_)
+    {
+        if (fpc_ < 1 || fpc_ > 32 || (fpc_ & (fpc_ - 1))) throw std::runtime_error("frames_per_cta must be a power of two <= 32");
+        if (threads_ < 32 || threads_ > 1024 || threads_ % 32) throw std::runtime_error("threads_per_cta must be a multiple of 32 <= 1024");
+        if (code.nnz >= (1 << 22)) throw std::runtime_error("code too large (nnz >= 2^22)");
+        if (code.max_cn_degree > 64) throw std::runtime_error("check degree > 64 not supported");
+        if (code.max_vn_degree > 255) throw std::runtime_error("variable degree > 255 not supported");
+        if (code.min_cn_degree < 2) throw std::runtime_error("check nodes of degree < 2 are not supported (undefined in the reference)");
+        fpc = fpc_;
+        threads = threads_;
+        npw = 32 / fpc;
+        nt = threads / fpc;
+        const int warps = threads / 32;
+
+        std::vector<int> cdeg(code.mc), vdeg(code.nc);
+        for (int i = 0; i < code.mc; ++i) cdeg[i] = code.row_ptr[i + 1] - code.row_ptr[i];
+        for (int i = 0; i < code.nc; ++i) vdeg[i] = code.col_ptr[i + 1] - code.col_ptr[i];
+        std::vector<char> tx(code.nc, 0);
+        for (int p : code.bit_pos) tx[p] = 1;
+
+        // ---- check side -------------------------------------------------------------------
+        auto cs = schedule(cdeg, npw, warps);
+        cn_rounds = 0;
+        for (auto &l : cs) cn_rounds = std::max<int>(cn_rounds, (int)l.size());
+        cn_desc.assign((size_t)cn_rounds * nt, IDLE_NODE);
+        edge_slot.assign(code.nnz, -1);
+        cn_col.clear();
+        int base = 0;
+        for (int r = 0; r < cn_rounds; ++r)
+            for (int w = 0; w < warps; ++w)
+            {
+                if (r >= (int)cs[w].size()) continue;
+                const Group &g = cs[w][r];
+                cn_col.resize(base + (size_t)npw * g.degree, 0);
+                for (int j = 0; j < (int)g.nodes.size(); ++j)
+                {
+                    const int row = g.nodes[j];
+                    cn_desc[(size_t)r * nt + w * npw + j] = (uint32_t)(base + j) | ((uint32_t)g.degree << 24);
+                    for (int k = 0; k < g.degree; ++k)
+                    {
+                        const int e = code.row_edge[code.row_ptr[row] + k];
+                        const int slot = base + k * npw + j;
+                        edge_slot[e] = slot;
+                        cn_col[slot] = (uint32_t)code.e_col[e];
+                    }
+                }
+                base += npw * g.degree;
+            }
+        n_slots = base;
+
+        // ---- variable side ----------------------------------------------------------------
+        auto vs = schedule(vdeg, npw, warps);
+        vn_rounds = 0;
+        for (auto &l : vs) vn_rounds = std::max<int>(vn_rounds, (int)l.size());
+        vn_desc.assign((size_t)vn_rounds * nt, IDLE_NODE);
+        vn_id.assign((size_t)vn_rounds * nt, 0);
+        vn_slot.clear();
+        int qbase = 0;
+        for (int r = 0; r < vn_rounds; ++r)
+            for (int w = 0; w < warps; ++w)
+            {
+                if (r >= (int)vs[w].size()) continue;
+                const Group &g = vs[w][r];
+                vn_slot.resize(qbase + (size_t)npw * g.degree, 0);
+                for (int j = 0; j < (int)g.nodes.size(); ++j)
+                {
+                    const int col = g.nodes[j];
+                    const size_t k0 = (size_t)r * nt + w * npw + j;
+                    vn_id[k0] = (uint32_t)col;
+                    vn_desc[k0] = (uint32_t)(qbase + j) | ((uint32_t)g.degree << 23) | (tx[col] ? 0x80000000u : 0u);
+                    for (int k = 0; k < g.degree; ++k)
+                        vn_slot[qbase + k * npw + j] = (uint32_t)edge_slot[code.col_edge[code.col_ptr[col] + k]];
+                }
+                qbase += npw * g.degree;
+            }
+        n_vslots = qbase;
+        if (n_slots >= (1 << 23) || n_vslots >= (1 << 23)) throw std::runtime_error("layout too large");
+    }
+} // namespace b200

@@ -1,0 +1,66 @@
+// Host-side code model and device-layout builder.
+//
+// HostCode   : what the reference's ldpc_code + sparse_csr hold (src/core/ldpc.cpp:40-101,
+//              src/core/sparse.h:91-153): edge list in FILE ORDER, per-row / per-column edge lists in
+//              file order (they fix the box-plus recursion order and the variable-node summation
+//              order), puncture/shorten lists, bit_pos, max degree.
+// TileLayout : the B200 mapping of one code onto a CTA tile: frames in the fast dimension,
+//              degree-sorted node groups balanced over warps, edge-slot-major message slots so that
+//              every sequential access is bank-conflict free / coalesced.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace b200
+{
+    struct HostCode
+    {
+        int nc = 0, mc = 0, nnz = 0;
+        std::vector<int> e_row, e_col;         // [nnz] file order
+        std::vector<int> row_ptr, row_edge;    // rowN (edge ids, file order within the row)
+        std::vector<int> col_ptr, col_edge;    // colN (edge ids, file order within the column)
+        std::vector<int> puncture, shorten;    // header lists, as given
+        std::vector<int> bit_pos;              // transmitted positions, ascending
+        int max_degree = 0, max_cn_degree = 0, max_vn_degree = 0, min_cn_degree = 0;
+        int kc() const { return nc - mc; }
+        int nct() const { return (int)bit_pos.size(); }
+        int mct() const { return mc - (int)puncture.size(); }
+        int kct() const { return nct() - mct(); }
+        bool empty() const { return nnz == 0; }
+
+        // Parses a code file.  parse_header=true applies the leading "key: value" header rule
+        // (ldpc.cpp:49-76); false reads every line as an edge (generator matrix, ldpc.cpp:103-106).
+        // Throws std::runtime_error("can not open file for reading") like sparse.h:99.
+        void load(const std::string &path, bool parse_header);
+
+        // GF(2) helpers (sparse.h:162-218, 227-294)
+        void multiply_left(const uint8_t *left, uint8_t *result_accum) const;  // result[col] ^= left[row]
+        void multiply_right(const uint8_t *right, uint8_t *result_accum) const; // result[row] ^= right[col]
+        int rank() const;
+    };
+
+    // One scheduled node entry: first slot, slot stride, degree.
+    constexpr uint32_t IDLE_NODE = 0xFFFFFFFFu;
+
+    struct TileLayout
+    {
+        int fpc = 0;       // frames per CTA (power of two <= 32)
+        int threads = 0;   // threads per CTA
+        int nt = 0;        // node threads = threads / fpc
+        int npw = 0;       // node threads per warp = 32 / fpc
+        int n_slots = 0;   // padded number of message slots
+        int cn_rounds = 0, vn_rounds = 0;
+        // check side: entry k = round * nt + node_thread
+        std::vector<uint32_t> cn_desc;  // first slot (bits 0-23) | degree (bits 24-31); IDLE_NODE = none
+        std::vector<uint32_t> cn_col;   // [n_slots] variable id gathered by each slot (0 for padding)
+        // variable side
+        std::vector<uint32_t> vn_desc;  // first index into vn_slot (bits 0-22) | degree (23-30) | transmitted (31); IDLE_NODE = none
+        std::vector<uint32_t> vn_id;    // variable id (0 for idle entries)
+        std::vector<uint32_t> vn_slot;  // [n_vslots] message slot of the k-th edge (file order) at q0 + k*npw
+        int n_vslots = 0;
+        std::vector<int> edge_slot;     // [nnz] file-order edge -> message slot (for tests / debugging)
+
+        void build(const HostCode &code, int fpc, int threads);
+    };
+} // namespace b200

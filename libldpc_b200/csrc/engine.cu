@@ -1,0 +1,579 @@
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <tuple>
+
+#include "kernels.cuh"
+#include "bec_kernel.cuh"
+
+namespace b200
+{
+#define CUDA_OK(call)                                                                                              \
+    do                                                                                                             \
+    {                                                                                                              \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess)                                                                                     \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call);        \
+    } while (0)
+
+    struct DeviceLayout
+    {
+        uint32_t *cn_desc = nullptr, *vn_desc = nullptr;
+        void *cn_col = nullptr, *vn_slot = nullptr, *vn_id = nullptr;
+        const TileLayout *host = nullptr;
+        ~DeviceLayout()
+        {
+            cudaFree(cn_desc); cudaFree(vn_desc); cudaFree(cn_col); cudaFree(vn_slot); cudaFree(vn_id);
+        }
+    };
+
+    namespace
+    {
+        template <typename IdxT>
+        void *upload_idx(const std::vector<uint32_t> &v)
+        {
+            std::vector<IdxT> tmp(v.size() ? v.size() : 1);
+            for (size_t i = 0; i < v.size(); ++i) tmp[i] = static_cast<IdxT>(v[i]);
+            void *d = nullptr;
+            CUDA_OK(cudaMalloc(&d, tmp.size() * sizeof(IdxT)));
+            CUDA_OK(cudaMemcpy(d, tmp.data(), tmp.size() * sizeof(IdxT), cudaMemcpyHostToDevice));
+            return d;
+        }
+
+        template <typename V>
+        V *upload(const std::vector<V> &v)
+        {
+            V *d = nullptr;
+            CUDA_OK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(V)));
+            if (!v.empty()) CUDA_OK(cudaMemcpy(d, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice));
+            return d;
+        }
+
+        size_t tile_smem_bytes(const TileLayout &l, size_t sizeof_t, int nc, bool idx16)
+        {
+            const size_t idx = idx16 ? 2 : 4;
+            size_t b = sizeof_t * ((size_t)l.n_slots + 2 * (size_t)nc) * l.fpc;
+            b += 4 * ((size_t)l.cn_rounds + l.vn_rounds) * l.nt;
+            b += idx * ((size_t)l.n_slots + l.n_vslots + (size_t)l.vn_rounds * l.nt);
+            return b + 16;
+        }
+
+        template <typename T, typename IdxT, int ALG, bool SMEM>
+        void launch_tile(const KParams &kp, int ctas, int threads, size_t smem, cudaStream_t s)
+        {
+            static bool attr_set = false;
+            if (SMEM && !attr_set)
+            {
+                CUDA_OK(cudaFuncSetAttribute(tile_kernel<T, IdxT, ALG, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048));
+                attr_set = true;
+            }
+            tile_kernel<T, IdxT, ALG, SMEM><<<ctas, threads, SMEM ? smem : 0, s>>>(kp);
+            CUDA_OK(cudaGetLastError());
+        }
+
+        template <typename T, int ALG>
+        void dispatch2(const KParams &kp, bool smem, bool idx16, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
+        {
+            if (smem)
+            {
+                if (!idx16) throw std::runtime_error("internal: shared-memory residency needs 16-bit indices");
+                launch_tile<T, uint16_t, ALG, true>(kp, ctas, threads, smem_bytes, s);
+            }
+            else if (idx16) launch_tile<T, uint16_t, ALG, false>(kp, ctas, threads, 0, s);
+            else launch_tile<T, uint32_t, ALG, false>(kp, ctas, threads, 0, s);
+        }
+    } // namespace
+
+    // ------------------------------------------------------------------------------------------
+
+    Engine::Engine(const std::string &pc_file, const std::string &gen_file, int dev) : device(dev)
+    {
+        H.load(pc_file, true);
+        if (!gen_file.empty())
+        {
+            G.load(gen_file, false);
+            has_gen = true;
+        }
+        tuning.precision = LDPC_B200_F64;
+        tuning.residency = LDPC_B200_AUTO;
+        tuning.bec_deg1_compat = 1;
+    }
+
+    Engine::~Engine()
+    {
+        if (!cuda_ready_) return;
+        cudaSetDevice(device);
+        dev_layouts_.clear();
+        cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
+        if (ev0_) cudaEventDestroy((cudaEvent_t)ev0_);
+        if (ev1_) cudaEventDestroy((cudaEvent_t)ev1_);
+        if (stream_) cudaStreamDestroy((cudaStream_t)stream_);
+    }
+
+    void Engine::ensure_cuda()
+    {
+        if (cuda_ready_)
+        {
+            CUDA_OK(cudaSetDevice(device));
+            return;
+        }
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw std::runtime_error("no CUDA device available: libldpc_b200 has no CPU fallback for decoding/simulation");
+        if (device < 0) device = 0;
+        if (device >= n) throw std::runtime_error("CUDA device index out of range");
+        CUDA_OK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw std::runtime_error(std::string("libldpc_b200 is built for sm_100a only; found ") + prop.name);
+        sm_count_ = prop.multiProcessorCount;
+        smem_optin_ = prop.sharedMemPerBlockOptin;
+        cudaStream_t s;
+        CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        stream_ = s;
+        cudaEvent_t a, b;
+        CUDA_OK(cudaEventCreate(&a));
+        CUDA_OK(cudaEventCreate(&b));
+        ev0_ = a; ev1_ = b;
+        std::vector<int32_t> bp(H.bit_pos.begin(), H.bit_pos.end()), pu(H.puncture.begin(), H.puncture.end()), sh(H.shorten.begin(), H.shorten.end());
+        d_bit_pos_ = upload(bp);
+        d_punct_ = upload(pu);
+        d_short_ = upload(sh);
+        CUDA_OK(cudaMalloc(&d_counters_, 8 * sizeof(unsigned long long)));
+        CUDA_OK(cudaMemset(d_counters_, 0, 8 * sizeof(unsigned long long)));
+        cuda_ready_ = true;
+    }
+
+    const TileLayout &Engine::get_layout(int fpc, int threads)
+    {
+        auto key = std::make_pair(fpc, threads);
+        auto it = layouts_.find(key);
+        if (it == layouts_.end())
+        {
+            auto l = std::make_unique<TileLayout>();
+            l->build(H, fpc, threads);
+            it = layouts_.emplace(key, std::move(l)).first;
+        }
+        return *it->second;
+    }
+
+    const TileLayout &Engine::layout_for(int precision, int alg, int *residency, size_t *smem_bytes)
+    {
+        const size_t st = precision == LDPC_B200_F32 ? 4 : 8;
+        const int threads = tuning.threads_per_cta > 0 ? tuning.threads_per_cta : (alg == ALG_MS ? 1024 : 512);
+        auto get = [&](int fpc) -> const TileLayout & { return get_layout(fpc, threads); };
+        const size_t limit = smem_optin_ - 2048; // static shared memory of the kernel + slack
+        if (tuning.residency != LDPC_B200_GLOBAL)
+        {
+            for (int fpc = 32; fpc >= 1; fpc >>= 1)
+            {
+                if (tuning.frames_per_cta > 0 && fpc != tuning.frames_per_cta) continue;
+                if (threads / fpc < 1) continue;
+                const TileLayout &l = get(fpc);
+                const bool idx16 = std::max({l.n_slots, l.n_vslots, H.nc}) <= 65535;
+                if (!idx16) continue;
+                const size_t need = tile_smem_bytes(l, st, H.nc, true);
+                if (need <= limit)
+                {
+                    *residency = LDPC_B200_SMEM;
+                    *smem_bytes = need;
+                    return l;
+                }
+            }
+            if (tuning.residency == LDPC_B200_SMEM) throw std::runtime_error("code does not fit shared-memory residency with this tuning");
+        }
+        const int fpc = tuning.frames_per_cta > 0 ? tuning.frames_per_cta : (int)(128 / st);
+        *residency = LDPC_B200_GLOBAL;
+        *smem_bytes = 0;
+        return get(fpc);
+    }
+
+    Engine::Config Engine::choose(int precision, int alg, uint64_t n_frames)
+    {
+        Config c{};
+        c.precision = precision;
+        c.alg = alg;
+        const TileLayout &l = layout_for(precision, alg, &c.residency, &c.smem_bytes);
+        c.fpc = l.fpc;
+        c.threads = l.threads;
+        c.idx16 = std::max({l.n_slots, l.n_vslots, H.nc}) <= 65535;
+        int ctas = tuning.ctas > 0 ? tuning.ctas : sm_count_;
+        const uint64_t need = (n_frames + c.fpc - 1) / c.fpc;
+        if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
+        c.ctas = ctas;
+        return c;
+    }
+
+    DeviceLayout &Engine::device_layout(int fpc, int threads, bool idx16)
+    {
+        auto key = std::make_tuple(fpc, threads, idx16);
+        auto it = dev_layouts_.find(key);
+        if (it != dev_layouts_.end()) return *it->second;
+        const TileLayout &l = *layouts_.at(std::make_pair(fpc, threads));
+        auto d = std::make_unique<DeviceLayout>();
+        d->host = &l;
+        d->cn_desc = upload(l.cn_desc);
+        d->vn_desc = upload(l.vn_desc);
+        if (idx16)
+        {
+            d->cn_col = upload_idx<uint16_t>(l.cn_col);
+            d->vn_slot = upload_idx<uint16_t>(l.vn_slot);
+            d->vn_id = upload_idx<uint16_t>(l.vn_id);
+        }
+        else
+        {
+            d->cn_col = upload_idx<uint32_t>(l.cn_col);
+            d->vn_slot = upload_idx<uint32_t>(l.vn_slot);
+            d->vn_id = upload_idx<uint32_t>(l.vn_id);
+        }
+        return *dev_layouts_.emplace(key, std::move(d)).first->second;
+    }
+
+    void Engine::ensure_state(size_t bytes)
+    {
+        if (bytes <= state_bytes_) return;
+        CUDA_OK(cudaDeviceSynchronize());
+        cudaFree(d_state_);
+        d_state_ = nullptr;
+        state_bytes_ = 0;
+        CUDA_OK(cudaMalloc(&d_state_, bytes));
+        state_bytes_ = bytes;
+    }
+
+    int Engine::channel_kind(const std::string &name)
+    {
+        if (name == "AWGN") return SRC_AWGN;
+        if (name == "BSC") return SRC_BSC;
+        if (name == "BEC") return SRC_BEC;
+        throw std::runtime_error("No channel selected."); // message of src/sim/ldpcsim.cpp:72
+    }
+
+    void Engine::launch(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream)
+    {
+        if (n_frames == 0) return;
+        ensure_cuda();
+        cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)stream_;
+        const bool minsum = dp.type && std::string(dp.type) == "BP_MS"; // src/decoding/decoder.h:76
+        if (dp.iterations == 0) throw std::runtime_error("iterations must be >= 1");
+
+        if (src.kind == SRC_BEC || src.d_bec_in)
+        {
+            launch_bec(dp, src, sink, n_frames, s);
+            return;
+        }
+
+        const int alg = minsum ? ALG_MS : ALG_BP;
+        const Config c = choose(tuning.precision, alg, n_frames);
+        DeviceLayout &dl = device_layout(c.fpc, c.threads, c.idx16);
+        const TileLayout &l = *dl.host;
+
+        KParams kp{};
+        kp.cn_desc = dl.cn_desc; kp.vn_desc = dl.vn_desc;
+        kp.cn_col = dl.cn_col; kp.vn_slot = dl.vn_slot; kp.vn_id = dl.vn_id;
+        kp.bit_pos = d_bit_pos_; kp.punct = d_punct_; kp.shorten = d_short_;
+        kp.cn_rounds = l.cn_rounds; kp.vn_rounds = l.vn_rounds; kp.n_slots = l.n_slots; kp.n_vslots = l.n_vslots;
+        kp.nc = H.nc; kp.nct = H.nct(); kp.n_punct = (int)H.puncture.size(); kp.n_short = (int)H.shorten.size();
+        kp.fpc = c.fpc;
+        kp.fshift = 0;
+        while ((1 << kp.fshift) < c.fpc) ++kp.fshift;
+        kp.max_iter = (int)dp.iterations;
+        kp.early_term = dp.earlyTerm ? 1 : 0;
+        kp.kind = src.kind;
+        kp.llr_in = src.d_llr;
+        if (src.kind == SRC_AWGN)
+        {
+            kp.sigma2 = std::pow(10.0, -src.x / 10.0); // src/sim/channel.cpp:39-40
+            kp.sigma = std::sqrt(kp.sigma2);
+        }
+        else if (src.kind == SRC_BSC)
+        {
+            kp.delta = std::log((1 - src.x) / src.x); // src/sim/channel.cpp:139
+            double t = std::floor(src.x * 4294967296.0);
+            kp.thr = t <= 0 ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+        }
+        kp.seed = src.seed; kp.point = src.point; kp.frame0 = src.frame0; kp.n_frames = n_frames;
+        kp.llr_out = sink.d_llr_out; kp.hard_out = sink.d_hard; kp.iters_out = sink.d_iters;
+        kp.counters = sink.d_counters ? sink.d_counters : d_counters_;
+        if (c.residency == LDPC_B200_GLOBAL)
+        {
+            const size_t st = c.precision == LDPC_B200_F32 ? 4 : 8;
+            kp.state_stride = ((st * ((size_t)l.n_slots + 2 * (size_t)H.nc) * c.fpc) + 255) & ~(size_t)255;
+            ensure_state(kp.state_stride * c.ctas);
+            kp.state = d_state_;
+        }
+        const bool smem = c.residency == LDPC_B200_SMEM;
+        if (c.precision == LDPC_B200_F32)
+        {
+            if (alg == ALG_MS) dispatch2<float, ALG_MS>(kp, smem, c.idx16, c.ctas, c.threads, c.smem_bytes, s);
+            else dispatch2<float, ALG_BP>(kp, smem, c.idx16, c.ctas, c.threads, c.smem_bytes, s);
+        }
+        else
+        {
+            if (alg == ALG_MS) dispatch2<double, ALG_MS>(kp, smem, c.idx16, c.ctas, c.threads, c.smem_bytes, s);
+            else dispatch2<double, ALG_BP>(kp, smem, c.idx16, c.ctas, c.threads, c.smem_bytes, s);
+        }
+        stats.launches += 1;
+        stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;
+        stats.residency = c.residency; stats.precision = c.precision; stats.smem_bytes = c.smem_bytes;
+    }
+
+    void Engine::launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream)
+    {
+        cudaStream_t s = (cudaStream_t)stream;
+        const int threads = 1024;
+        const TileLayout &l = get_layout(32, threads);
+        const bool idx16 = std::max({l.n_slots, l.n_vslots, H.nc}) <= 65535;
+        DeviceLayout &dl = device_layout(32, threads, idx16);
+        BecParams bp{};
+        bp.cn_desc = dl.cn_desc; bp.vn_desc = dl.vn_desc; bp.cn_col = dl.cn_col; bp.vn_slot = dl.vn_slot; bp.vn_id = dl.vn_id;
+        bp.bit_pos = d_bit_pos_; bp.punct = d_punct_; bp.shorten = d_short_;
+        bp.cn_rounds = l.cn_rounds; bp.vn_rounds = l.vn_rounds; bp.n_slots = l.n_slots;
+        bp.nc = H.nc; bp.nct = H.nct(); bp.n_punct = (int)H.puncture.size(); bp.n_short = (int)H.shorten.size();
+        bp.max_iter = (int)dp.iterations; bp.early_term = dp.earlyTerm ? 1 : 0; bp.deg1_compat = tuning.bec_deg1_compat;
+        bp.kind = src.d_bec_in ? SRC_LLR : SRC_BEC;
+        bp.in = src.d_bec_in; bp.cw = src.d_bec_cw;
+        {
+            double t = std::floor(src.x * 4294967296.0);
+            bp.thr = t <= 0 ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+        }
+        bp.seed = src.seed; bp.point = src.point; bp.frame0 = src.frame0; bp.n_frames = n_frames;
+        bp.out = sink.d_bec_out; bp.hard = sink.d_hard; bp.iters_out = sink.d_iters;
+        bp.counters = sink.d_counters ? sink.d_counters : d_counters_;
+        int ctas = tuning.ctas > 0 ? tuning.ctas : sm_count_;
+        const uint64_t need = (n_frames + 31) / 32;
+        if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
+        bp.state_stride = (((2 * (size_t)l.n_slots + 3 * (size_t)H.nc) * 32) + 255) & ~(size_t)255;
+        ensure_state(bp.state_stride * ctas);
+        bp.state = d_state_;
+        if (idx16) bec_kernel<uint16_t><<<ctas, threads, 0, s>>>(bp);
+        else bec_kernel<uint32_t><<<ctas, threads, 0, s>>>(bp);
+        CUDA_OK(cudaGetLastError());
+        stats.launches += 1;
+        stats.frames_per_cta = 32; stats.threads_per_cta = threads; stats.ctas = ctas;
+        stats.residency = LDPC_B200_GLOBAL; stats.precision = -1; stats.smem_bytes = 0;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // blocking helpers
+    // ------------------------------------------------------------------------------------------
+
+    void Engine::sim_point_async(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
+                                 uint64_t frame0, uint64_t n_frames, unsigned long long *d_counters, void *stream)
+    {
+        FrameSource src;
+        src.kind = channel_kind(channel);
+        src.x = x; src.seed = seed; src.point = point; src.frame0 = frame0;
+        FrameSink sink;
+        sink.d_counters = d_counters;
+        launch(dp, src, sink, n_frames, stream);
+    }
+
+    void Engine::sim_point(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
+                           uint64_t frame0, uint64_t n_frames, uint64_t counters[5], float *device_ms)
+    {
+        ensure_cuda();
+        cudaStream_t s = (cudaStream_t)stream_;
+        CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), s));
+        CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
+        sim_point_async(dp, channel, x, seed, point, frame0, n_frames, d_counters_, s);
+        CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));
+        unsigned long long h[5];
+        CUDA_OK(cudaMemcpyAsync(h, d_counters_, sizeof(h), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
+        if (device_ms) *device_ms = ms;
+        for (int i = 0; i < 5; ++i) counters[i] = h[i];
+        stats.device_ms += ms;
+        stats.frames += h[2];
+        stats.edge_iterations += h[4] * (uint64_t)H.nnz;
+    }
+
+    void Engine::decode_batch_host(const decoder_param &dp, const double *llr, int64_t n, double *llr_out, uint8_t *hard, int32_t *iters)
+    {
+        if (n <= 0) return;
+        ensure_cuda();
+        cudaStream_t s = (cudaStream_t)stream_;
+        const size_t nc = H.nc;
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((512ull << 20) / (nc * sizeof(double)))));
+        double *d_in = nullptr, *d_out = nullptr;
+        uint8_t *d_hard = nullptr;
+        int32_t *d_it = nullptr;
+        CUDA_OK(cudaMalloc(&d_in, chunk * nc * sizeof(double)));
+        if (llr_out) CUDA_OK(cudaMalloc(&d_out, chunk * nc * sizeof(double)));
+        if (hard) CUDA_OK(cudaMalloc(&d_hard, chunk * nc));
+        if (iters) CUDA_OK(cudaMalloc(&d_it, chunk * sizeof(int32_t)));
+        try
+        {
+            for (int64_t o = 0; o < n; o += chunk)
+            {
+                const int64_t m = std::min(chunk, n - o);
+                CUDA_OK(cudaMemcpyAsync(d_in, llr + o * nc, m * nc * sizeof(double), cudaMemcpyHostToDevice, s));
+                CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), s));
+                FrameSource src;
+                src.kind = SRC_LLR;
+                src.d_llr = d_in;
+                FrameSink sink;
+                sink.d_llr_out = d_out; sink.d_hard = d_hard; sink.d_iters = d_it;
+                CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
+                launch(dp, src, sink, (uint64_t)m, s);
+                CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));
+                if (llr_out) CUDA_OK(cudaMemcpyAsync(llr_out + o * nc, d_out, m * nc * sizeof(double), cudaMemcpyDeviceToHost, s));
+                if (hard) CUDA_OK(cudaMemcpyAsync(hard + o * nc, d_hard, m * nc, cudaMemcpyDeviceToHost, s));
+                if (iters) CUDA_OK(cudaMemcpyAsync(iters + o, d_it, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+                unsigned long long h[5];
+                CUDA_OK(cudaMemcpyAsync(h, d_counters_, sizeof(h), cudaMemcpyDeviceToHost, s));
+                CUDA_OK(cudaStreamSynchronize(s));
+                float ms = 0;
+                CUDA_OK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
+                stats.device_ms += ms;
+                stats.frames += h[2];
+                stats.edge_iterations += h[4] * (uint64_t)H.nnz;
+            }
+        }
+        catch (...)
+        {
+            cudaFree(d_in); cudaFree(d_out); cudaFree(d_hard); cudaFree(d_it);
+            throw;
+        }
+        cudaFree(d_in); cudaFree(d_out); cudaFree(d_hard); cudaFree(d_it);
+    }
+
+    void Engine::decode_bec_host(const decoder_param &dp, const uint8_t *in, const uint8_t *cw, int64_t n, uint8_t *out, uint8_t *hard, int32_t *iters)
+    {
+        if (n <= 0) return;
+        ensure_cuda();
+        cudaStream_t s = (cudaStream_t)stream_;
+        const size_t nc = H.nc;
+        uint8_t *d_in = nullptr, *d_cw = nullptr, *d_out = nullptr, *d_hard = nullptr;
+        int32_t *d_it = nullptr;
+        CUDA_OK(cudaMalloc(&d_in, n * nc));
+        CUDA_OK(cudaMalloc(&d_cw, n * nc));
+        CUDA_OK(cudaMalloc(&d_out, n * nc));
+        CUDA_OK(cudaMalloc(&d_hard, n * nc));
+        CUDA_OK(cudaMalloc(&d_it, n * sizeof(int32_t)));
+        try
+        {
+            CUDA_OK(cudaMemcpyAsync(d_in, in, n * nc, cudaMemcpyHostToDevice, s));
+            CUDA_OK(cudaMemcpyAsync(d_cw, cw, n * nc, cudaMemcpyHostToDevice, s));
+            CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), s));
+            FrameSource src;
+            src.kind = SRC_LLR;
+            src.d_bec_in = d_in; src.d_bec_cw = d_cw;
+            FrameSink sink;
+            sink.d_bec_out = d_out; sink.d_hard = d_hard; sink.d_iters = d_it;
+            launch(dp, src, sink, (uint64_t)n, s);
+            if (out) CUDA_OK(cudaMemcpyAsync(out, d_out, n * nc, cudaMemcpyDeviceToHost, s));
+            if (hard) CUDA_OK(cudaMemcpyAsync(hard, d_hard, n * nc, cudaMemcpyDeviceToHost, s));
+            if (iters) CUDA_OK(cudaMemcpyAsync(iters, d_it, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaStreamSynchronize(s));
+        }
+        catch (...)
+        {
+            cudaFree(d_in); cudaFree(d_cw); cudaFree(d_out); cudaFree(d_hard); cudaFree(d_it);
+            throw;
+        }
+        cudaFree(d_in); cudaFree(d_cw); cudaFree(d_out); cudaFree(d_hard); cudaFree(d_it);
+    }
+
+    // Stand-alone channel kernel: the same generator code as the fused path, one thread per Philox block.
+    __global__ void channel_kernel(int kind, int nc, int nct, const int32_t *__restrict__ bit_pos, const int32_t *__restrict__ punct, int n_punct,
+                                   const int32_t *__restrict__ shorten, int n_short, double sigma, double sigma2, double delta, uint32_t thr,
+                                   uint64_t seed, uint32_t point, uint64_t frame0, int64_t n_frames, uint8_t *cw, double *llr, uint8_t *llr_u8)
+    {
+        const int per = (kind == SRC_AWGN) ? 2 : 4;
+        const int nblk = (nct + per - 1) / per;
+        const int64_t total = n_frames * (int64_t)nblk;
+        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x)
+        {
+            const int64_t fr = g / nblk;
+            const int j = (int)(g % nblk);
+            const u32x4 r = channel_block(seed, point, 0, frame0 + fr, (uint32_t)j);
+            const size_t base = (size_t)fr * nc;
+            if (kind == SRC_AWGN)
+            {
+                const double u1 = ((double)((((uint64_t)r.y << 32) | r.x) >> 11) + 1.0) * 0x1p-53;
+                const double u2 = (double)((((uint64_t)r.w << 32) | r.z) >> 11) * 0x1p-53;
+                const double rad = sqrt(-2.0 * log(u1));
+                double sn, cs;
+                sincos(6.283185307179586 * u2, &sn, &cs);
+                const double y0 = __dadd_rn(__dmul_rn(rad * cs, sigma), 1.0);
+                const double y1 = __dadd_rn(__dmul_rn(rad * sn, sigma), 1.0);
+                const int t = 2 * j;
+                llr[base + bit_pos[t]] = __dmul_rn(2.0, y0) / sigma2;
+                if (t + 1 < nct) llr[base + bit_pos[t + 1]] = __dmul_rn(2.0, y1) / sigma2;
+            }
+            else
+            {
+                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+                for (int q = 0; q < 4; ++q)
+                {
+                    const int t = 4 * j + q;
+                    if (t >= nct) break;
+                    const bool hit = w[q] < thr;
+                    if (kind == SRC_BSC) llr[base + bit_pos[t]] = hit ? -delta : delta;
+                    else llr_u8[base + bit_pos[t]] = hit ? (uint8_t)'E' : (uint8_t)0;
+                }
+            }
+            if (j == 0)
+            {
+                for (int i = 0; i < n_punct; ++i)
+                {
+                    if (kind == SRC_BEC) llr_u8[base + punct[i]] = (uint8_t)'E';
+                    else llr[base + punct[i]] = 0.0;
+                }
+                for (int i = 0; i < n_short; ++i)
+                {
+                    if (kind == SRC_BEC) llr_u8[base + shorten[i]] = 0;
+                    else llr[base + shorten[i]] = (kind == SRC_AWGN) ? 99999.9 : delta;
+                }
+                if (cw) for (int i = 0; i < nc; ++i) cw[base + i] = 0;
+            }
+        }
+    }
+
+    void Engine::channel_host(const std::string &channel, double x, uint64_t seed, uint32_t point, uint64_t frame0, int64_t n,
+                              uint8_t *cw, double *llr, uint8_t *llr_u8)
+    {
+        if (n <= 0) return;
+        ensure_cuda();
+        const int kind = channel_kind(channel);
+        cudaStream_t s = (cudaStream_t)stream_;
+        const size_t nc = H.nc;
+        double *d_llr = nullptr;
+        uint8_t *d_u8 = nullptr, *d_cw = nullptr;
+        if (kind == SRC_BEC) { if (!llr_u8) throw std::runtime_error("llr_u8 buffer required for BEC"); CUDA_OK(cudaMalloc(&d_u8, n * nc)); }
+        else { if (!llr) throw std::runtime_error("llr buffer required"); CUDA_OK(cudaMalloc(&d_llr, n * nc * sizeof(double))); }
+        if (cw) CUDA_OK(cudaMalloc(&d_cw, n * nc));
+        double sigma2 = 1, sigma = 1, delta = 0;
+        uint32_t thr = 0;
+        if (kind == SRC_AWGN) { sigma2 = std::pow(10.0, -x / 10.0); sigma = std::sqrt(sigma2); }
+        else
+        {
+            delta = std::log((1 - x) / x);
+            double t = std::floor(x * 4294967296.0);
+            thr = t <= 0 ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+        }
+        channel_kernel<<<sm_count_ * 4, 256, 0, s>>>(kind, (int)nc, H.nct(), d_bit_pos_, d_punct_, (int)H.puncture.size(), d_short_,
+                                                     (int)H.shorten.size(), sigma, sigma2, delta, thr, seed, point, frame0, n, d_cw, d_llr, d_u8);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess && d_llr) e = cudaMemcpyAsync(llr, d_llr, n * nc * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && d_u8) e = cudaMemcpyAsync(llr_u8, d_u8, n * nc, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && d_cw) e = cudaMemcpyAsync(cw, d_cw, n * nc, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d_llr); cudaFree(d_u8); cudaFree(d_cw);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
+    }
+} // namespace b200
+
+extern "C" int ldpc_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}

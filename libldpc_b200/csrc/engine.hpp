@@ -1,0 +1,100 @@
+// Host engine: owns the loaded code, the device copies of its tile layouts and the workspaces,
+// and launches the persistent tile kernel (kernels.cuh).  C++17 host code; the CUDA runtime is only
+// touched lazily so that loader / GF(2) helpers work on machines without a GPU.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ldpc_b200.h"
+#include "code.hpp"
+
+namespace b200
+{
+    struct DeviceLayout; // device-resident TileLayout (engine.cu)
+
+    struct FrameSource
+    {
+        int kind = 0;                // SRC_* of kernels.cuh
+        const double *d_llr = nullptr; // SRC_LLR: device [n][nc]
+        const uint8_t *d_bec_in = nullptr, *d_bec_cw = nullptr; // BEC decode mode
+        double x = 0;                // channel parameter (snr dB or epsilon)
+        uint64_t seed = 0;
+        uint32_t point = 0;
+        uint64_t frame0 = 0;
+    };
+
+    struct FrameSink
+    {
+        double *d_llr_out = nullptr;
+        uint8_t *d_hard = nullptr;
+        uint8_t *d_bec_out = nullptr;
+        int32_t *d_iters = nullptr;
+        unsigned long long *d_counters = nullptr; // [5]; null -> engine scratch
+    };
+
+    class Engine
+    {
+    public:
+        Engine(const std::string &pc_file, const std::string &gen_file, int device);
+        ~Engine();
+
+        HostCode H, G;
+        bool has_gen = false;
+        int device = -1;
+        ldpc_b200_tuning tuning{};
+        ldpc_b200_stats stats{};
+
+        // Chooses / builds the layout for (precision, algorithm) under the current tuning (host only).
+        const TileLayout &layout_for(int precision, int alg, int *residency, size_t *smem_bytes);
+
+        // Launches the tile kernel over n_frames frames on `stream` (0 = engine stream). Asynchronous.
+        void launch(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
+
+        // Blocking helpers used by the C ABI
+        void decode_batch_host(const decoder_param &dp, const double *llr, int64_t n, double *llr_out, uint8_t *hard, int32_t *iters);
+        void decode_bec_host(const decoder_param &dp, const uint8_t *in, const uint8_t *cw, int64_t n, uint8_t *out, uint8_t *hard, int32_t *iters);
+        void channel_host(const std::string &channel, double x, uint64_t seed, uint32_t point, uint64_t frame0, int64_t n,
+                          uint8_t *cw, double *llr, uint8_t *llr_u8);
+        void sim_point(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
+                       uint64_t frame0, uint64_t n_frames, uint64_t counters[5], float *device_ms);
+        void sim_point_async(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
+                             uint64_t frame0, uint64_t n_frames, unsigned long long *d_counters, void *stream);
+
+        void ensure_cuda();
+        void *engine_stream() const { return stream_; }
+
+    private:
+        struct Config
+        {
+            int precision, alg, residency, fpc, threads, ctas;
+            size_t smem_bytes;
+            bool idx16;
+        };
+        Config choose(int precision, int alg, uint64_t n_frames);
+        const TileLayout &get_layout(int fpc, int threads);
+        void launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
+        DeviceLayout &device_layout(int fpc, int threads, bool idx16);
+        void ensure_state(size_t bytes);
+        static int channel_kind(const std::string &name);
+
+        bool cuda_ready_ = false;
+        int sm_count_ = 148;
+        size_t smem_optin_ = 227 * 1024;
+        void *stream_ = nullptr;
+        void *ev0_ = nullptr, *ev1_ = nullptr;
+        std::map<std::pair<int, int>, std::unique_ptr<TileLayout>> layouts_;
+        std::map<std::tuple<int, int, bool>, std::unique_ptr<DeviceLayout>> dev_layouts_;
+        int32_t *d_bit_pos_ = nullptr, *d_punct_ = nullptr, *d_short_ = nullptr;
+        unsigned long long *d_counters_ = nullptr;
+        unsigned char *d_state_ = nullptr;
+        size_t state_bytes_ = 0;
+    };
+
+    // reference-semantics sweep driver (sim_driver.cpp)
+    int run_sweep(Engine &eng, const decoder_param &dp, const channel_param &cp, const simulation_param &sp,
+                  sim_results_t *results, bool *stop_flag, int rank, int world, ldpc_b200_allreduce_fn allreduce,
+                  void *user, bool quiet, bool write_file);
+} // namespace b200

@@ -1,0 +1,234 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+(a) the committed golden vectors produced by the unmodified reference and (b) the C oracle on the
+same seeded inputs.  Bars: min-sum — bit-exact posteriors, decisions and iteration counts;
+BP — posteriors within 1e-4 relative (north_star), >= 99.99 % identical decisions; integer paths
+(BSC/BEC channel, BEC decoder, counters) — bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import G_FILE, H_FILE
+
+pytestmark = pytest.mark.gpu
+
+BP_RTOL = 1e-4  # tolerance stated by BASELINE.json north_star for BP posterior LLRs
+
+
+def _cfg(case):
+    it, et, seed, n, useg = [int(v) for v in case["cfg"]]
+    ch, dec = [str(v) for v in case["names"]]
+    return it, bool(et), seed, n, useg, ch, dec, float(case["x"][0])
+
+
+def _rel_err(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-9)
+
+
+@pytest.mark.parametrize("precision_mode", ["smem", "global"])
+def test_minsum_golden_bit_exact(gpu_ctx, golden_cases, precision_mode):
+    from libldpc_b200 import api
+    gpu_ctx.set_tuning(precision=api.F64, residency=api.SMEM if precision_mode == "smem" else api.GLOBAL, frames_per_cta=0)
+    n_checked = 0
+    for name, case in golden_cases.items():
+        it, et, seed, n, useg, ch, dec, x = _cfg(case)
+        if ch == "BEC" or dec != "BP_MS":
+            continue
+        out, hard, its = gpu_ctx.decode_batch(case["llr_in"], "BP_MS", it, et)
+        assert np.array_equal(its, case["iters"]), name
+        assert np.array_equal(hard, case["co"]), name
+        assert np.array_equal(out.view(np.uint64), case["llr_out"].view(np.uint64)), name  # bit pattern, incl. -0.0
+        n_checked += 1
+    assert n_checked >= 8
+    gpu_ctx.set_tuning(residency=api.AUTO)
+
+
+def test_bp_golden_within_tolerance(gpu_ctx, golden_cases):
+    from libldpc_b200 import api
+    gpu_ctx.set_tuning(precision=api.F64, residency=api.AUTO, frames_per_cta=0)
+    tot = same = 0
+    for name, case in golden_cases.items():
+        it, et, seed, n, useg, ch, dec, x = _cfg(case)
+        if ch == "BEC" or dec != "BP":
+            continue
+        out, hard, its = gpu_ctx.decode_batch(case["llr_in"], "BP", it, et)
+        assert np.array_equal(its, case["iters"]), name
+        tot += hard.size
+        same += int((hard == case["co"]).sum())
+        assert _rel_err(out, case["llr_out"]).max() < BP_RTOL, name
+    assert tot > 0 and same / tot >= 0.9999
+
+
+def test_bec_golden_bit_exact(gpu_ctx, golden_cases):
+    n_checked = 0
+    for name, case in golden_cases.items():
+        it, et, seed, n, useg, ch, dec, x = _cfg(case)
+        if ch != "BEC":
+            continue
+        out, hard, its = gpu_ctx.decode_bec_batch(case["llr_in"], case["cw"], it, et)
+        assert np.array_equal(its, case["iters"]), name
+        assert np.array_equal(out, case["llr_out"]), name
+        assert np.array_equal(hard, case["co"]), name
+        n_checked += 1
+    assert n_checked >= 3
+
+
+@pytest.mark.parametrize("decoding,et,iters", [("BP_MS", True, 50), ("BP_MS", False, 7), ("BP_MS", True, 1), ("BP", True, 50), ("BP", False, 3)])
+def test_decode_vs_oracle_seeded(gpu_ctx, oracle_code, decoding, et, iters):
+    """Same seeded LLRs (incl. exact zeros, ties, huge values, -0.0) through the oracle and the GPU."""
+    rng = np.random.default_rng(1234)
+    n = 96
+    llr = rng.normal(1.0, 1.6, size=(n, oracle_code.nc))
+    llr[:, oracle_code.puncture] = 0.0
+    llr[3, :] = np.round(llr[3, :])            # exact ties and zeros
+    llr[4, ::7] = -0.0
+    llr[5, :] = np.where(rng.random(oracle_code.nc) < 0.2, -1.5, 1.5)  # BSC-like two-valued input
+    llr[6, :200] = 99999.9
+    ro, rc, ri = oracle_code.decode(llr, iters, et, decoding == "BP_MS")
+    out, hard, its = gpu_ctx.decode_batch(llr, decoding, iters, et)
+    assert np.array_equal(its, ri)
+    if decoding == "BP_MS":
+        assert np.array_equal(hard, rc)
+        assert np.array_equal(out.view(np.uint64), ro.view(np.uint64))
+    else:
+        assert (hard == rc).mean() >= 0.9999
+        assert _rel_err(out, ro).max() < BP_RTOL
+
+
+def test_ragged_batches_and_refill(gpu_ctx, oracle_code):
+    """Batch sizes around the tile size (1, fpc-1, fpc+1, many) give per-frame identical results."""
+    rng = np.random.default_rng(7)
+    llr = rng.normal(0.6, 1.3, size=(700, oracle_code.nc))
+    llr[:, oracle_code.puncture] = 0.0
+    full = gpu_ctx.decode_batch(llr, "BP_MS", 20, True)
+    for n in (1, 3, 5, 33, 149 * 4 + 1):
+        part = gpu_ctx.decode_batch(llr[:n], "BP_MS", 20, True)
+        for a, b in zip(part, full):
+            assert np.array_equal(a, b[:n])
+    ro, rc, ri = oracle_code.decode(llr[:40], 20, True, True)
+    assert np.array_equal(full[2][:40], ri) and np.array_equal(full[1][:40], rc)
+
+
+def test_channel_kernel_vs_spec(gpu_ctx, oracle_code):
+    """Philox channel: BSC/BEC inputs bit-exact with the CPU specification, AWGN within 1e-12."""
+    for ch, x in (("BSC", 0.11), ("BEC", 0.45)):
+        cw, llr = gpu_ctx.channel(ch, x, seed=9, point=3, frame0=1 << 33, n=17)
+        ocw, ollr = oracle_code.channel_frames(ch, x, 9, 3, 1 << 33, 17)
+        assert np.array_equal(cw, ocw)
+        assert np.array_equal(llr, ollr)
+    cw, llr = gpu_ctx.channel("AWGN", -4.5, seed=2, point=1, frame0=5, n=64)
+    ocw, ollr = oracle_code.channel_frames("AWGN", -4.5, 2, 1, 5, 64)
+    assert np.allclose(llr, ollr, rtol=1e-12, atol=1e-12)
+    tx = oracle_code.bit_pos
+    z = (llr[:, tx] * 10 ** (4.5 / 10) / 2 - 1) / np.sqrt(10 ** (4.5 / 10))  # back to standard normal
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+    assert np.all(llr[:, oracle_code.puncture] == 0.0)
+
+
+@pytest.mark.parametrize("ch,x,dec", [("BSC", 0.21, "BP_MS"), ("BSC", 0.16, "BP_MS"), ("BEC", 0.9, "BP"), ("BEC", 0.6, "BP")])
+def test_sim_counters_bit_exact_integer_channels(gpu_ctx, oracle_code, ch, x, dec):
+    """Whole pipeline (channel -> decode -> accounting) on the GPU equals the oracle's frame loop."""
+    n = 600
+    g = gpu_ctx.sim_point(ch, x, seed=5, point=2, frame0=100, nframes=n, decoding=dec, iterations=30, early_term=True)
+    o = oracle_code.sim_point(ch, x, seed=5, point=2, frame0=100, nframes=n, decoding=dec, iterations=30, early_term=True, threads=8)
+    assert {k: g[k] for k in ("fec", "bec", "frames", "iters")} == o
+
+
+def test_sim_awgn_minsum_matches_oracle_on_dumped_llrs(gpu_ctx, oracle_code):
+    """AWGN: LLRs the GPU channel generates, decoded by the oracle, reproduce the fused kernel's counters."""
+    n, x = 400, -4.5
+    g = gpu_ctx.sim_point("AWGN", x, seed=1, point=0, frame0=0, nframes=n, decoding="BP_MS", iterations=50, early_term=True)
+    cw, llr = gpu_ctx.channel("AWGN", x, seed=1, point=0, frame0=0, n=n)
+    out, co, its = oracle_code.decode(llr, 50, True, True)
+    errs = (co[:, oracle_code.bit_pos] != 0).sum(1)
+    assert g["frames"] == n
+    assert g["iters"] == int(its.sum())
+    assert g["fec"] == int((errs > 0).sum())
+    assert g["bec"] == int(errs.sum())
+
+
+def test_counters_independent_of_partition(gpu_ctx):
+    """Totals depend only on (seed, point, frame range): split launches / CTA counts give the same sums."""
+    kw = dict(seed=3, point=1, decoding="BP_MS", iterations=25, early_term=True)
+    whole = gpu_ctx.sim_point("AWGN", -4.8, frame0=0, nframes=3000, **kw)
+    parts = [gpu_ctx.sim_point("AWGN", -4.8, frame0=f0, nframes=nf, **kw) for f0, nf in ((0, 1000), (1000, 1), (1001, 1999))]
+    gpu_ctx.set_tuning(ctas=7)
+    few = gpu_ctx.sim_point("AWGN", -4.8, frame0=0, nframes=3000, **kw)
+    gpu_ctx.set_tuning(ctas=0)
+    for k in ("fec", "bec", "frames", "iters"):
+        assert whole[k] == sum(p[k] for p in parts) == few[k]
+
+
+def test_f32_mode_is_statistically_consistent(gpu_ctx):
+    from libldpc_b200 import api
+    kw = dict(seed=11, point=0, frame0=0, nframes=20000, decoding="BP_MS", iterations=50, early_term=True)
+    a = gpu_ctx.sim_point("AWGN", -4.5, **kw)
+    gpu_ctx.set_tuning(precision=api.F32)
+    b = gpu_ctx.sim_point("AWGN", -4.5, **kw)
+    gpu_ctx.set_tuning(precision=api.F64)
+    assert abs(a["fec"] - b["fec"]) <= 0.02 * a["fec"] + 5   # same noise, rounding-level differences only
+    assert abs(a["iters"] - b["iters"]) <= 0.01 * a["iters"]
+
+
+def test_fer_curve_within_binomial_ci(gpu_ctx):
+    """FER/BER points agree with the reference CLI's curve (tests/golden/curves.json) within 95 % CIs."""
+    import json, os
+    from conftest import GOLDEN
+    curves = json.load(open(os.path.join(GOLDEN, "curves.json")))
+    for name, dec, ch in (("awgn_ms", "BP_MS", "AWGN"), ("awgn_bp", "BP", "AWGN"), ("bsc_ms", "BP_MS", "BSC")):
+        for pt in curves[name]["points"]:
+            if pt["fer"] < 4e-3 or pt["fec"] < 30:
+                continue
+            n = int(min(max(400 / pt["fer"], 4000), 120000))
+            g = gpu_ctx.sim_point(ch, pt["x"], seed=77, point=0, frame0=0, nframes=n, decoding=dec, iterations=50, early_term=True)
+            p_ref, n_ref = pt["fer"], pt["frames"]
+            p_gpu = g["fec"] / g["frames"]
+            p = (pt["fec"] + g["fec"]) / (n_ref + g["frames"])
+            sigma = np.sqrt(p * (1 - p) * (1 / n_ref + 1 / g["frames"]))
+            assert abs(p_gpu - p_ref) <= 1.96 * 1.5 * sigma + 1e-12, (name, pt["x"], p_gpu, p_ref, sigma)
+
+
+def test_reference_abi_and_python_wrapper(built_lib, oracle_code, tmp_path):
+    """The six reference symbols via the pyLDPC-compatible wrapper: decode/encode/syndrome/rank/simulate."""
+    import time
+    from libldpc_b200 import ldpc
+    code = ldpc.LDPC(H_FILE, G_FILE)
+    assert (code.n, code.m, code.nct, code.mct, code.kct) == (1152, 1024, 1024, 896, 128)
+    rng = np.random.default_rng(5)
+    llr = rng.normal(1.0, 1.5, size=code.nct)
+    full = np.zeros(code.n); full[oracle_code.bit_pos] = llr
+    for dec in ("BP_MS", "BP", "BP_MS"):   # no sticky min-sum state between calls
+        out, it = code.decode(llr, True, 50, dec)
+        ro, rc, ri = oracle_code.decode(full, 50, True, dec == "BP_MS")
+        assert it == ri
+        if dec == "BP_MS":
+            assert np.array_equal(out, ro[oracle_code.bit_pos])
+        else:
+            assert _rel_err(out, ro[oracle_code.bit_pos]).max() < BP_RTOL
+    u = rng.integers(0, 2, code.kct)
+    cw = code.encode(u)
+    assert cw.shape == (code.nct,)
+    assert code.rank() == 1021
+    word = np.zeros(code.n, dtype=np.uint8); word[5] = 1
+    assert np.array_equal(code.syndrome(word), oracle_code.syndrome(word))
+    code.simulate(snr=[-5.5, -4.4, 0.5], iterations=50, decoding="BP_MS", maxFrames=20000, fec=40)
+    code.wait(120)
+    res = code.get_results()
+    assert len(res["fer"]) == 3 and all(f >= 40 for f in res["fec"])
+    assert res["fer"][0] > res["fer"][1] > res["fer"][2] > 0
+
+
+def test_cli_results_file(built_lib, tmp_path):
+    import os, subprocess
+    from conftest import ROOT
+    out = tmp_path / "res.txt"
+    cli = os.path.join(ROOT, "libldpc_b200", "ldpcsim")
+    r = subprocess.run([cli, H_FILE, str(out), "-6", "-4.9", "0.5", "--decoding", "BP_MS", "--frame-error-count", "30",
+                        "--max-frames", "20000", "-t", "4", "-s", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = out.read_text().split("\n")
+    assert lines[0] == "snr fer ber frames avg_iter frame_time"
+    assert len(lines) == 1 + 3 + 1 and lines[-1] == ""       # header + one line per point + trailing newline
+    x, fer, ber, frames, avg_iter, t = lines[1].split()
+    assert float(x) == -6.0 and 0.5 < float(fer) <= 1.0 and int(frames) > 0
+    assert "N : 1152" in r.stdout and "== Decoder Parameters" in r.stdout and "FEC   |      FRAME" in r.stdout
+    bad = subprocess.run([cli, H_FILE, str(out), "3", "1", "0.5"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "snr min > snr max" in bad.stdout
