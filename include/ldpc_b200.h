@@ -180,6 +180,16 @@ typedef void (*ldpc_b200_allreduce_fn)(uint64_t *values, int n, void *user); /* 
 int ldpc_b200_simulate(ldpc_b200_ctx *ctx, decoder_param dp, channel_param cp, simulation_param sp,
                        sim_results_t *results, bool *stopFlag, int rank, int world,
                        ldpc_b200_allreduce_fn allreduce, void *user, int quiet);
+/* Same sweep with the frame processor injected: round_fn (if non-NULL) is called instead of the GPU
+ * launch to process global frames [frame0, frame0+n_frames) of sweep point `point` at channel value x
+ * and must add {frame errors, bit errors, frames, iterations} to counters4.  Lets a multi-GPU host
+ * drive its own asynchronous launches, and lets the host-side logic (sharding, stop rule, results
+ * writer) be exercised on machines without a GPU.  Returns non-zero from round_fn to abort. */
+typedef int (*ldpc_b200_round_fn)(uint32_t point, double x, uint64_t frame0, uint64_t n_frames,
+                                  uint64_t *counters4, void *user);
+int ldpc_b200_simulate_ex(ldpc_b200_ctx *ctx, decoder_param dp, channel_param cp, simulation_param sp,
+                          sim_results_t *results, bool *stopFlag, int rank, int world,
+                          ldpc_b200_allreduce_fn allreduce, ldpc_b200_round_fn round_fn, void *user, int quiet);
 
 /* execution statistics of the last simulate/sim_point/decode_batch call on this context */
 typedef struct

@@ -48,6 +48,7 @@ class stats(ct.Structure):
 
 
 ALLREDUCE_FN = ct.CFUNCTYPE(None, ct.POINTER(ct.c_uint64), ct.c_int, ct.c_void_p)
+ROUND_FN = ct.CFUNCTYPE(ct.c_int, ct.c_uint32, ct.c_double, ct.c_uint64, ct.c_uint64, ct.POINTER(ct.c_uint64), ct.c_void_p)
 F64, F32 = 0, 1
 AUTO, SMEM, GLOBAL = 0, 1, 2
 
@@ -56,7 +57,7 @@ HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device
                   "ldpc_b200_info", "ldpc_b200_set_tuning", "ldpc_b200_get_tuning", "ldpc_b200_get_edges", "ldpc_b200_get_bit_pos",
                   "ldpc_b200_get_puncture", "ldpc_b200_get_layout", "ldpc_b200_rank", "ldpc_b200_encode", "ldpc_b200_syndrome",
                   "ldpc_b200_decode_batch", "ldpc_b200_decode_batch_device", "ldpc_b200_decode_bec_batch", "ldpc_b200_channel",
-                  "ldpc_b200_sim_point", "ldpc_b200_sim_point_async", "ldpc_b200_simulate", "ldpc_b200_get_stats",
+                  "ldpc_b200_sim_point", "ldpc_b200_sim_point_async", "ldpc_b200_simulate", "ldpc_b200_simulate_ex", "ldpc_b200_get_stats",
                   "ldpc_b200_reset_stats")
 
 _lib = None
@@ -97,6 +98,8 @@ def load_library(path=None):
     L.ldpc_b200_sim_point_async.argtypes = [vp, decoder_param, ct.c_char_p, ct.c_double, u64, u32, u64, u64, vp, vp]
     L.ldpc_b200_simulate.argtypes = [vp, decoder_param, channel_param, simulation_param, ct.POINTER(sim_results_t), ct.POINTER(ct.c_bool),
                                      ct.c_int, ct.c_int, ALLREDUCE_FN, vp, ct.c_int]
+    L.ldpc_b200_simulate_ex.argtypes = [vp, decoder_param, channel_param, simulation_param, ct.POINTER(sim_results_t), ct.POINTER(ct.c_bool),
+                                        ct.c_int, ct.c_int, ALLREDUCE_FN, ROUND_FN, vp, ct.c_int]
     L.ldpc_b200_get_stats.argtypes = [vp, ct.POINTER(stats)]
     L.ldpc_b200_reset_stats.argtypes = [vp]
     if path is None:
@@ -237,15 +240,18 @@ class Context:
                                                            ct.c_void_p(stream_ptr)))
 
     def simulate(self, snr, channel="AWGN", decoding="BP", iterations=50, early_term=True, seed=0, max_frames=int(10e9), fec=50,
-                 result_file="", rank=0, world=1, allreduce=None, quiet=True, max_points=512):
-        """Blocking sweep with the reference's semantics; returns the per-point result arrays."""
+                 result_file="", rank=0, world=1, allreduce=None, quiet=True, max_points=512, round_fn=None):
+        """Blocking sweep with the reference's semantics; returns the per-point result arrays.
+        allreduce(values_ptr, n, user) sums a uint64 array over ranks; round_fn (tests / custom hosts)
+        replaces the GPU launch, see ldpc_b200_simulate_ex."""
         res = sim_results_t(*[(ct.c_double * max_points)() for _ in range(4)], (ct.c_uint64 * max_points)(), (ct.c_uint64 * max_points)())
         stop = ct.c_bool(False)
         cb = ALLREDUCE_FN(allreduce) if allreduce is not None else ct.cast(None, ALLREDUCE_FN)
         cp = channel_param(int(seed), (ct.c_double * 3)(*snr), channel.encode())
         sp = simulation_param(1, int(max_frames), int(fec), str(result_file).encode())
-        self._check(self.lib.ldpc_b200_simulate(self._h, self._dp(decoding, iterations, early_term), cp, sp, ct.byref(res), ct.byref(stop),
-                                                int(rank), int(world), cb, None, int(bool(quiet))))
+        rf = ROUND_FN(round_fn) if round_fn is not None else ct.cast(None, ROUND_FN)
+        self._check(self.lib.ldpc_b200_simulate_ex(self._h, self._dp(decoding, iterations, early_term), cp, sp, ct.byref(res), ct.byref(stop),
+                                                   int(rank), int(world), cb, rf, None, int(bool(quiet))))
         n = int(np.sum(np.array(res.frames[0:max_points]) > 0))
         return {k: np.array(getattr(res, k)[0:n]) for k, _ in sim_results_t._fields_}
 

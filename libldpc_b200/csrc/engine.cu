@@ -376,6 +376,7 @@ namespace b200
     void Engine::sim_point(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
                            uint64_t frame0, uint64_t n_frames, uint64_t counters[5], float *device_ms)
     {
+        (void)channel_kind(channel); // argument errors first, as the reference's constructor does (ldpcsim.cpp:32-72)
         ensure_cuda();
         cudaStream_t s = (cudaStream_t)stream_;
         CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), s));

@@ -96,5 +96,5 @@ namespace b200
     // reference-semantics sweep driver (sim_driver.cpp)
     int run_sweep(Engine &eng, const decoder_param &dp, const channel_param &cp, const simulation_param &sp,
                   sim_results_t *results, bool *stop_flag, int rank, int world, ldpc_b200_allreduce_fn allreduce,
-                  void *user, bool quiet, bool write_file);
+                  void *user, bool quiet, bool write_file, ldpc_b200_round_fn round_fn = nullptr);
 } // namespace b200

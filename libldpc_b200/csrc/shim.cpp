@@ -349,6 +349,16 @@ extern "C"
         });
     }
 
+    int ldpc_b200_simulate_ex(ldpc_b200_ctx *ctx, decoder_param dp, channel_param cp, simulation_param sp, sim_results_t *results,
+                              bool *stopFlag, int rank, int world, ldpc_b200_allreduce_fn allreduce, ldpc_b200_round_fn round_fn,
+                              void *user, int quiet)
+    {
+        return guarded([&] {
+            if (!ctx) throw std::runtime_error("null argument");
+            b200::run_sweep(*ctx->eng, dp, cp, sp, results, stopFlag, rank, world, allreduce, user, quiet != 0, true, round_fn);
+        });
+    }
+
     int ldpc_b200_reset_stats(ldpc_b200_ctx *ctx)
     {
         return guarded([&] {

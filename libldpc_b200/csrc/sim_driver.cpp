@@ -20,7 +20,7 @@ namespace b200
 {
     int run_sweep(Engine &eng, const decoder_param &dp, const channel_param &cp, const simulation_param &sp,
                   sim_results_t *results, bool *stop_flag, int rank, int world, ldpc_b200_allreduce_fn allreduce,
-                  void *user, bool quiet, bool write_file)
+                  void *user, bool quiet, bool write_file, ldpc_b200_round_fn round_fn)
     {
         const std::string ch = cp.type ? cp.type : "";
         if (ch != "AWGN" && ch != "BSC" && ch != "BEC") throw std::runtime_error("No channel selected.");
@@ -58,7 +58,14 @@ namespace b200
                 const uint64_t lo = cursor + n_this * (uint64_t)rank / (uint64_t)world;
                 const uint64_t hi = cursor + n_this * (uint64_t)(rank + 1) / (uint64_t)world;
                 uint64_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (hi > lo) eng.sim_point(dp, ch, xs[i], cp.seed, (uint32_t)i, lo, hi - lo, c, nullptr);
+                if (hi > lo)
+                {
+                    if (round_fn)
+                    {
+                        if (round_fn((uint32_t)i, xs[i], lo, hi - lo, c, user) != 0) throw std::runtime_error("round callback failed");
+                    }
+                    else eng.sim_point(dp, ch, xs[i], cp.seed, (uint32_t)i, lo, hi - lo, c, nullptr);
+                }
                 c[5] = (stop_flag && *stop_flag) ? 1 : 0;
                 if (world > 1) allreduce(c, 8, user);
                 cursor += n_this;

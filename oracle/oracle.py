@@ -60,6 +60,9 @@ def lib():
         L.orc_is_codeword.argtypes = [P, bp]
         L.orc_count_bit_errors.restype = ct.c_int
         L.orc_count_bit_errors.argtypes = [P, bp, bp]
+        L.orc_llr_awgn.argtypes = [P, dp, ct.c_double, dp]
+        L.orc_llr_bsc.argtypes = [P, bp, ct.c_double, dp]
+        L.orc_llr_bec.argtypes = [P, bp, bp, bp]
         L.orc_multiply_left.argtypes = [P, bp, bp]
         L.orc_multiply_right.argtypes = [P, bp, bp]
         L.orc_rank.restype = ct.c_int

@@ -1,0 +1,137 @@
+"""CPU tests of the product's host side (no compute calls): the C-ABI library builds, loads and
+exports every symbol include/ldpc_b200.h declares; struct layouts match the reference's; the loader,
+the tile layout and the GF(2) helpers agree with the oracle; GPU entry points fail loudly without a GPU."""
+import ctypes as ct
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import G_FILE, H_FILE, ROOT
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from libldpc_b200 import api
+    header = open(os.path.join(ROOT, "include", "ldpc_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b((?:ldpc_b200_\w+)|ldpc_setup|simulate|calculate_rank|encode|decode|syndrome)\s*\(", header))
+    declared -= {"ldpc_b200_allreduce_fn"}
+    assert set(api.REFERENCE_SYMBOLS) <= declared
+    assert declared == set(api.REFERENCE_SYMBOLS) | set(api.HANDLE_SYMBOLS)
+    for name in sorted(declared):
+        assert hasattr(built_lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", api.lib_path()], capture_output=True, text=True).stdout
+    for name in api.REFERENCE_SYMBOLS:  # the exact names pyLDPC binds (pyLDPC/ldpc.py:41,102,130,160,200,216)
+        assert re.search(rf" T {name}$", out, flags=re.M), name
+
+
+def test_struct_layouts_match_reference():
+    from libldpc_b200 import api
+    assert ct.sizeof(api.decoder_param) == 16 and api.decoder_param.iterations.offset == 4 and api.decoder_param.type.offset == 8
+    assert ct.sizeof(api.channel_param) == 40 and api.channel_param.xRange.offset == 8 and api.channel_param.type.offset == 32
+    assert ct.sizeof(api.simulation_param) == 32 and api.simulation_param.maxFrames.offset == 8
+    assert api.simulation_param.fec.offset == 16 and api.simulation_param.resultFile.offset == 24
+    assert ct.sizeof(api.sim_results_t) == 48
+
+
+@pytest.fixture(scope="module")
+def host_ctx(built_lib):
+    from libldpc_b200 import api
+    c = api.Context(H_FILE, G_FILE, device=-1)
+    yield c
+    c.close()
+
+
+def test_loader_matches_oracle(host_ctx, oracle_code):
+    for k in ("nc", "mc", "nnz", "kc", "nct", "mct", "kct", "max_degree"):
+        assert getattr(host_ctx, k) == getattr(oracle_code, k), k
+    r, c = host_ctx.edges()
+    assert np.array_equal(r, oracle_code.e_row) and np.array_equal(c, oracle_code.e_col)  # file order
+    assert np.array_equal(host_ctx.bit_pos(), oracle_code.bit_pos)
+    p, s = host_ctx.puncture()
+    assert np.array_equal(p, oracle_code.puncture) and len(s) == 0
+
+
+def test_loader_header_and_edge_cases(built_lib, tmp_path):
+    from libldpc_b200 import api
+    from oracle import oracle as O
+    f = tmp_path / "c.txt"
+    f.write_text("nc: 6\nsome legacy key: 1 2 3\npuncture [2]: 1 3 \nshorten [1]: 5\n"
+                 "0 0\n0 1 1\n0 2\n1 2 0\n1 3\n1 4\n2 4\n2 5\n2 0\n\n")   # value column, explicit 0 value, blank last line
+    c = api.Context(str(f), "", device=-1)
+    o = O.Code(str(f))
+    assert (c.nc, c.mc, c.nnz, c.nct, c.mct, c.kct) == (o.nc, o.mc, o.nnz, o.nct, o.mct, o.kct) == (6, 3, 9, 3, 1, 2)
+    assert list(c.bit_pos()) == list(o.bit_pos) == [0, 2, 4]
+    p, s = c.puncture()
+    assert list(p) == [1, 3] and list(s) == [5]
+    r, cc = c.edges()
+    assert list(r) == [0, 0, 0, 1, 1, 1, 2, 2, 2] and list(cc) == [0, 1, 2, 2, 3, 4, 4, 5, 0]
+    c.close()
+    assert not built_lib.ldpc_b200_open(b"/nonexistent/file.txt", b"", -1)
+    assert b"can not open file for reading" in built_lib.ldpc_b200_last_error()
+    g = tmp_path / "deg1.txt"
+    g.write_text("0 0\n1 0\n1 1\n")   # a degree-1 check is undefined behaviour in the reference; rejected by the layout
+    c = api.Context(str(g), "", device=-1)
+    with pytest.raises(RuntimeError, match="degree < 2"):
+        c.layout()
+    c.close()
+
+
+@pytest.mark.parametrize("precision,fpc", [(0, 0), (1, 0), (0, 32), (1, 16), (0, 1)])
+def test_tile_layout_is_a_valid_schedule(host_ctx, precision, fpc):
+    from libldpc_b200 import api
+    host_ctx.set_tuning(precision=precision, residency=api.AUTO if fpc == 0 else api.GLOBAL, frames_per_cta=fpc)
+    lay = host_ctx.layout()
+    es = lay["edge_slot"]
+    assert len(np.unique(es)) == host_ctx.nnz and es.min() >= 0 and es.max() < lay["n_slots"]
+    if fpc == 0:   # the 1152x1024 sample code fits shared memory: 4 frames/CTA in f64, 8 in f32
+        assert lay["residency"] == api.SMEM and lay["frames_per_cta"] == (8 if precision else 4)
+    else:
+        assert lay["residency"] == api.GLOBAL and lay["frames_per_cta"] == fpc
+    host_ctx.set_tuning(precision=0, residency=api.AUTO, frames_per_cta=0)
+
+
+def test_gf2_helpers_match_oracle(host_ctx, oracle_code, oracle_gen):
+    rng = np.random.default_rng(3)
+    assert host_ctx.rank() == oracle_code.rank() == 1021
+    for _ in range(4):
+        u = rng.integers(0, 2, host_ctx.g_rows).astype(np.uint8)
+        cw = host_ctx.encode(u)
+        assert np.array_equal(cw, oracle_gen.multiply_left(u))
+        assert not host_ctx.syndrome(cw).any()
+        w = rng.integers(0, 2, host_ctx.nc).astype(np.uint8)
+        assert np.array_equal(host_ctx.syndrome(w), oracle_code.syndrome(w))
+
+
+def test_compute_fails_loudly_without_gpu(host_ctx, built_lib):
+    if built_lib.ldpc_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        host_ctx.decode_batch(np.zeros((1, host_ctx.nc)))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        host_ctx.sim_point("AWGN", 1.0, nframes=10)
+    with pytest.raises(RuntimeError, match="No channel selected"):
+        host_ctx.sim_point("XYZ", 1.0, nframes=10)
+
+
+def test_cli_argument_handling(built_lib, tmp_path):
+    cli = os.path.join(ROOT, "libldpc_b200", "ldpcsim")
+    assert os.path.exists(cli)
+    r = subprocess.run([cli, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--frame-error-count" in r.stdout and "--no-early-term" in r.stdout
+    r = subprocess.run([cli, H_FILE, str(tmp_path / "o.txt"), "-3", "-7", "0.5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "snr min > snr max" in r.stdout          # src/sim_cpu.cpp:28-29, negative positionals
+    r = subprocess.run([cli, str(tmp_path / "missing.txt"), str(tmp_path / "o.txt"), "0", "1", "0.5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error: ldpc_code(): can not open file for reading" in r.stdout
+    r = subprocess.run([cli, H_FILE], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stdout
+
+
+def test_python_wrapper_is_api_compatible():
+    """Same public surface as pyLDPC.ldpc.LDPC (pyLDPC/ldpc.py)."""
+    from libldpc_b200 import ldpc
+    for m in ("encode", "decode", "simulate", "stop_simulation", "get_results", "rank", "syndrome"):
+        assert callable(getattr(ldpc.LDPC, m))
+    assert ldpc.LIB_PATH.endswith("libldpc.so")
