@@ -13,8 +13,9 @@ CLI = os.path.join(HERE, "ldpcsim")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
-SOURCES = ["engine.cu", "code.cpp", "sim_driver.cpp", "shim.cpp"]
-HEADERS = ["engine.hpp", "code.hpp", "kernels.cuh", "bec_kernel.cuh", "../../include/ldpc_b200.h"]
+SOURCES = ["tile_ms_f64.cu", "tile_ms_f32.cu", "tile_bp_f64.cu", "tile_bp_f32.cu", "engine.cu", "code.cpp", "sim_driver.cpp", "shim.cpp"]
+HEADERS = ["engine.hpp", "code.hpp", "kernels.cuh", "tile_launch.cuh", "bec_kernel.cuh", "../../include/ldpc_b200.h"]
+OBJDIR = os.path.join(HERE, "build")
 
 
 def _stale(target, deps):
@@ -28,11 +29,26 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     if force or _stale(LIB, deps):
-        cmd = [NVCC] + ARCH + COMMON + ["-shared", "-cudart", "static", "-o", LIB] + srcs
-        if verbose:
-            cmd += ["-Xptxas", "-v"]
-            print(" ".join(cmd))
-        subprocess.run(cmd, check=True)
+        from concurrent.futures import ThreadPoolExecutor
+        os.makedirs(OBJDIR, exist_ok=True)
+        hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+
+        def compile_one(src):
+            obj = os.path.join(OBJDIR, os.path.basename(src) + ".o")
+            if force or _stale(obj, [src] + hdrs):
+                cmd = [NVCC] + ARCH + COMMON + ["-c", "-o", obj, src]
+                if verbose:
+                    cmd += ["-Xptxas", "-v"]
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                if verbose or r.returncode != 0:
+                    sys.stderr.write(r.stdout + r.stderr)
+                if r.returncode != 0:
+                    raise RuntimeError("nvcc failed for " + src)
+            return obj
+
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            objs = list(ex.map(compile_one, srcs))
+        subprocess.run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs, check=True)
     cli_src = os.path.join(CSRC, "cli_main.cpp")
     if force or _stale(CLI, [cli_src, LIB]):
         cmd = [NVCC] + ARCH + COMMON + ["-o", CLI, cli_src, LIB, "-Xlinker", "-rpath,$ORIGIN"]

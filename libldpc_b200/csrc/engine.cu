@@ -7,7 +7,7 @@
 #include <stdexcept>
 #include <tuple>
 
-#include "kernels.cuh"
+#include "tile_launch.cuh"
 #include "bec_kernel.cuh"
 
 namespace b200
@@ -62,30 +62,6 @@ namespace b200
             return b + 16;
         }
 
-        template <typename T, typename IdxT, int ALG, bool SMEM>
-        void launch_tile(const KParams &kp, int ctas, int threads, size_t smem, cudaStream_t s)
-        {
-            static bool attr_set = false;
-            if (SMEM && !attr_set)
-            {
-                CUDA_OK(cudaFuncSetAttribute(tile_kernel<T, IdxT, ALG, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048));
-                attr_set = true;
-            }
-            tile_kernel<T, IdxT, ALG, SMEM><<<ctas, threads, SMEM ? smem : 0, s>>>(kp);
-            CUDA_OK(cudaGetLastError());
-        }
-
-        template <typename T, int ALG>
-        void dispatch2(const KParams &kp, bool smem, bool idx16, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
-        {
-            if (smem)
-            {
-                if (!idx16) throw std::runtime_error("internal: shared-memory residency needs 16-bit indices");
-                launch_tile<T, uint16_t, ALG, true>(kp, ctas, threads, smem_bytes, s);
-            }
-            else if (idx16) launch_tile<T, uint16_t, ALG, false>(kp, ctas, threads, 0, s);
-            else launch_tile<T, uint32_t, ALG, false>(kp, ctas, threads, 0, s);
-        }
     } // namespace
 
     // ------------------------------------------------------------------------------------------
@@ -170,7 +146,7 @@ namespace b200
         const size_t limit = smem_optin_ - 2048; // static shared memory of the kernel + slack
         if (tuning.residency != LDPC_B200_GLOBAL)
         {
-            for (int fpc = 32; fpc >= 1; fpc >>= 1)
+            for (int fpc = 32; fpc >= 4; fpc >>= 1)
             {
                 if (tuning.frames_per_cta > 0 && fpc != tuning.frames_per_cta) continue;
                 if (threads / fpc < 1) continue;
@@ -201,7 +177,7 @@ namespace b200
         const TileLayout &l = layout_for(precision, alg, &c.residency, &c.smem_bytes);
         c.fpc = l.fpc;
         c.threads = l.threads;
-        c.idx16 = std::max({l.n_slots, l.n_vslots, H.nc}) <= 65535;
+        c.idx16 = (c.residency == LDPC_B200_SMEM); // shared-memory residency: 16-bit tables; global: 32-bit
         int ctas = tuning.ctas > 0 ? tuning.ctas : sm_count_;
         const uint64_t need = (n_frames + c.fpc - 1) / c.fpc;
         if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
@@ -309,13 +285,13 @@ namespace b200
         const bool smem = c.residency == LDPC_B200_SMEM;
         if (c.precision == LDPC_B200_F32)
         {
-            if (alg == ALG_MS) dispatch2<float, ALG_MS>(kp, smem, c.idx16, c.ctas, c.threads, c.smem_bytes, s);
-            else dispatch2<float, ALG_BP>(kp, smem, c.idx16, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.fpc, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<float, ALG_BP>(kp, smem, c.fpc, c.ctas, c.threads, c.smem_bytes, s);
         }
         else
         {
-            if (alg == ALG_MS) dispatch2<double, ALG_MS>(kp, smem, c.idx16, c.ctas, c.threads, c.smem_bytes, s);
-            else dispatch2<double, ALG_BP>(kp, smem, c.idx16, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.fpc, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<double, ALG_BP>(kp, smem, c.fpc, c.ctas, c.threads, c.smem_bytes, s);
         }
         stats.launches += 1;
         stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;

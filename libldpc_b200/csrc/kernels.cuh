@@ -1,14 +1,19 @@
 // sm_100a kernels of the decode hot path: Philox channel -> flooding min-sum / box-plus decode ->
 // hard decision + error accounting, fused into ONE persistent kernel.
 //
-// Mapping ("tile"): a CTA owns `fpc` frame lanes; thread t serves frame lane f = t % fpc as node
-// thread t / fpc.  All per-frame arrays are laid out [index][fpc] with the frame lane fastest, so a
-// warp touching npw = 32/fpc consecutive indices moves one contiguous 32*sizeof(T) block (conflict
+// Mapping ("tile"): a CTA owns FPC frame lanes; thread t serves frame lane f = t % FPC as node
+// thread t / FPC.  All per-frame arrays are laid out [index][FPC] with the frame lane fastest, so a
+// warp touching NPW = 32/FPC consecutive indices moves one contiguous 32*sizeof(T) block (conflict
 // free in shared memory, fully coalesced in HBM).  State per lane: c2v message per edge slot, the
 // posterior `out` per variable and the channel LLR per variable; v2c is never stored — it is
 // recomputed as out - c2v, which is exactly the value the reference stores
 // (src/decoding/decoder.cpp:60-63), so results stay bit-identical while one of the reference's two
 // message arrays disappears.
+//
+// Node groups of equal degree are scheduled per warp (code.cpp), so the degree is warp-uniform and
+// the node updates are dispatched to fully unrolled fixed-degree bodies: all loads of a node are
+// issued back to back, message slots are reached with immediate offsets (slot stride = 32*sizeof(T)
+// bytes), and no per-edge loop/address arithmetic remains.
 //
 // A lane that finishes its frame (syndrome clear after an iteration, or iteration limit) is refilled
 // at once with the next frame (LLRs regenerated from the counter-based Philox stream), so early
@@ -26,7 +31,6 @@ namespace b200
 
     __host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1)
     {
-#pragma unroll
         for (int r = 0; r < 10; ++r)
         {
             const uint64_t p0 = (uint64_t)0xD2511F53u * c.x;
@@ -83,71 +87,92 @@ namespace b200
         size_t state_stride;
     };
 
+    // ------------------------------------------------------------------------------------------
+    // memory-space policies: shared window (32-bit byte addresses, explicit ld/st.shared so that no
+    // generic-address arithmetic is rematerialised in the inner loops) or global memory
+    // ------------------------------------------------------------------------------------------
+    // (explicit overload set instead of partial specialisation: OFF must be an immediate)
+#define B200_SMEM_LD(NAME, TYPE, PTXT, CONS)                                                        \
+    template <int OFF> __device__ __forceinline__ TYPE NAME(uint32_t a)                             \
+    {                                                                                               \
+        TYPE v;                                                                                     \
+        asm volatile("ld.shared." PTXT " %0, [%1+%2];" : "=" CONS(v) : "r"(a), "n"(OFF));           \
+        return v;                                                                                   \
+    }
+#define B200_SMEM_ST(NAME, TYPE, PTXT, CONS)                                                        \
+    template <int OFF> __device__ __forceinline__ void NAME(uint32_t a, TYPE v)                     \
+    {                                                                                               \
+        asm volatile("st.shared." PTXT " [%0+%1], %2;" ::"r"(a), "n"(OFF), CONS(v) : "memory");     \
+    }
+    B200_SMEM_LD(lds_f64, double, "f64", "d")
+    B200_SMEM_LD(lds_f32, float, "f32", "f")
+    B200_SMEM_LD(lds_u32, uint32_t, "u32", "r")
+    B200_SMEM_ST(sts_f64, double, "f64", "d")
+    B200_SMEM_ST(sts_f32, float, "f32", "f")
+    B200_SMEM_ST(sts_u32, uint32_t, "u32", "r")
+    template <int OFF> __device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+    {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(a), "n"(OFF));
+        return v;
+    }
+    template <int OFF> __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
+    {
+        asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(a), "n"(OFF), "h"((uint16_t)v) : "memory");
+    }
+
+    // typed front ends ----------------------------------------------------------------------------
+    template <bool SMEM, typename V, int OFF> struct Acc;
+    template <int OFF> struct Acc<true, double, OFF>
+    {
+        static __device__ __forceinline__ double ld(uint32_t a) { return lds_f64<OFF>(a); }
+        static __device__ __forceinline__ void st(uint32_t a, double v) { sts_f64<OFF>(a, v); }
+    };
+    template <int OFF> struct Acc<true, float, OFF>
+    {
+        static __device__ __forceinline__ float ld(uint32_t a) { return lds_f32<OFF>(a); }
+        static __device__ __forceinline__ void st(uint32_t a, float v) { sts_f32<OFF>(a, v); }
+    };
+    template <int OFF> struct Acc<true, uint32_t, OFF>
+    {
+        static __device__ __forceinline__ uint32_t ld(uint32_t a) { return lds_u32<OFF>(a); }
+        static __device__ __forceinline__ void st(uint32_t a, uint32_t v) { sts_u32<OFF>(a, v); }
+    };
+    template <int OFF> struct Acc<true, uint16_t, OFF>
+    {
+        static __device__ __forceinline__ uint32_t ld(uint32_t a) { return lds_u16<OFF>(a); }
+        static __device__ __forceinline__ void st(uint32_t a, uint32_t v) { sts_u16<OFF>(a, v); }
+    };
+    template <typename V, int OFF> struct Acc<false, V, OFF>
+    {
+        static __device__ __forceinline__ V ld(const unsigned char *a) { return *reinterpret_cast<const V *>(a + OFF); }
+        static __device__ __forceinline__ void st(unsigned char *a, V v) { *reinterpret_cast<V *>(a + OFF) = v; }
+    };
+    template <bool SMEM> struct PtrOf { typedef uint32_t type; };
+    template <> struct PtrOf<false> { typedef unsigned char *type; };
+
     template <typename T> struct Num;
     template <> struct Num<double>
     {
-        static __device__ __forceinline__ uint32_t sign(double v) { return (uint32_t)__double2hiint(v) >> 31; }
+        static __device__ __forceinline__ uint32_t hi(double v) { return (uint32_t)__double2hiint(v); }
         static __device__ __forceinline__ double abs(double v) { return fabs(v); }
-        static __device__ __forceinline__ double with_sign(double mag, uint32_t s) { return __hiloint2double(__double2hiint(mag) | (int)(s << 31), __double2loint(mag)); }
+        // mag >= 0; sign bit taken from bit 31 of s
+        static __device__ __forceinline__ double with_sign(double mag, uint32_t s) { return __hiloint2double(__double2hiint(mag) | (int)(s & 0x80000000u), __double2loint(mag)); }
         static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
+        static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
         static __device__ __forceinline__ double exp_(double v) { return exp(v); }
         static __device__ __forceinline__ double log_(double v) { return log(v); }
     };
     template <> struct Num<float>
     {
-        static __device__ __forceinline__ uint32_t sign(float v) { return __float_as_uint(v) >> 31; }
+        static __device__ __forceinline__ uint32_t hi(float v) { return __float_as_uint(v); }
         static __device__ __forceinline__ float abs(float v) { return fabsf(v); }
-        static __device__ __forceinline__ float with_sign(float mag, uint32_t s) { return __uint_as_float(__float_as_uint(mag) | (s << 31)); }
+        static __device__ __forceinline__ float with_sign(float mag, uint32_t s) { return __uint_as_float(__float_as_uint(mag) | (s & 0x80000000u)); }
         static __device__ __forceinline__ float inf() { return __uint_as_float(0x7f800000u); }
+        static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
         static __device__ __forceinline__ float exp_(float v) { return __expf(v); }
         static __device__ __forceinline__ float log_(float v) { return __logf(v); }
     };
-
-    // ------------------------------------------------------------------------------------------
-    // check-node updates.  slot(k) = p0 + k*npw, value index = slot*fpc + f.
-    // Both return the parity of the hard decisions of the check's variables (the syndrome bit of the
-    // previous iteration's output, reference: decoder.h:47-64) — computed from the gathered `out`
-    // values for free.
-    // ------------------------------------------------------------------------------------------
-
-    // min-sum: the forward/backward recursion of decoder.cpp:30-44 with f = minsum (decoder.h:17-20)
-    // yields, for every edge, (product of the other signs) * (minimum of the other magnitudes); with
-    // sign *bits* (std::signbit, -0.0 negative) that is reproduced exactly by min1/min2 + sign parity.
-    template <typename T, typename IdxT>
-    __device__ __forceinline__ uint32_t cn_minsum(const T *__restrict__ src, T *__restrict__ c2v, const IdxT *__restrict__ cn_col,
-                                                  uint32_t p0, int deg, int npw, int fpc, int f, bool first)
-    {
-        T min1 = Num<T>::inf(), min2 = Num<T>::inf();
-        int arg = 0;
-        unsigned long long smask = 0;
-        uint32_t par = 0;
-#pragma unroll 4
-        for (int k = 0; k < deg; ++k)
-        {
-            const uint32_t slot = p0 + k * npw;
-            const uint32_t col = cn_col[slot];
-            const T o = src[col * fpc + f];
-            const T c = first ? T(0) : c2v[slot * fpc + f];
-            const T v = o - c; // == the reference's stored v2c (decoder.cpp:62), or LLRin on the first pass (:18)
-            par ^= (o <= T(0)) ? 1u : 0u;
-            smask |= (unsigned long long)Num<T>::sign(v) << k;
-            const T a = Num<T>::abs(v);
-            const bool lt1 = a < min1, lt2 = a < min2;
-            min2 = lt1 ? min1 : (lt2 ? a : min2);
-            arg = lt1 ? k : arg;
-            min1 = lt1 ? a : min1;
-        }
-        const uint32_t tot = (uint32_t)__popcll(smask) & 1u;
-#pragma unroll 4
-        for (int k = 0; k < deg; ++k)
-        {
-            const uint32_t slot = p0 + k * npw;
-            const T mag = (k == arg) ? min2 : min1;
-            const uint32_t s = tot ^ (uint32_t)((smask >> k) & 1ull);
-            c2v[slot * fpc + f] = Num<T>::with_sign(mag, s);
-        }
-        return par;
-    }
 
     // pairwise box-plus with the Jacobian correction, decoder.h:12-15 (same expression, same order)
     template <typename T>
@@ -155,86 +180,205 @@ namespace b200
     {
         const T ax = Num<T>::abs(x), ay = Num<T>::abs(y);
         const T m = (ay < ax) ? ay : ax;
-        const T sm = Num<T>::with_sign(m, Num<T>::sign(x) ^ Num<T>::sign(y));
+        const T sm = Num<T>::with_sign(m, Num<T>::hi(x) ^ Num<T>::hi(y));
         const T num = T(1) + Num<T>::exp_(-Num<T>::abs(x + y));
         const T den = T(1) + Num<T>::exp_(-Num<T>::abs(x - y));
         return sm + Num<T>::log_(num / den);
     }
 
-    // sum-product by the reference's forward/backward recursion (decoder.cpp:30-44), file order.
-    template <typename T, typename IdxT, int MAXD>
-    __device__ __forceinline__ uint32_t cn_boxplus(const T *__restrict__ src, T *__restrict__ c2v, const IdxT *__restrict__ cn_col,
-                                                   uint32_t p0, int deg, int npw, int fpc, int f, bool first)
+    // ------------------------------------------------------------------------------------------
+    // check-node updates.  A node is described by
+    //   src   : &src[0][f]                      (src = out, or llr on a frame's first iteration)
+    //   c2v0  : &c2v[p0][f]   slot k at + k*CS  (CS = 32*sizeof(T): slots of a node are NPW apart)
+    //   col0  : &cn_col[p0]   entry k at + k*IS (IS = NPW*sizeof(IdxT))
+    // Both variants return the parity of the hard decisions of the check's variables (the syndrome
+    // bit of the previous iteration's output, reference: decoder.h:47-64) — free with the gather.
+    // ------------------------------------------------------------------------------------------
+    template <typename T, typename IdxT, bool SMEM, int FPC, int ALG, int D>
+    struct CnFixed
     {
-        T v[MAXD], F[MAXD];
-        uint32_t par = 0;
-#pragma unroll
-        for (int k = 0; k < MAXD; ++k)
-            if (k < deg)
+        typedef typename PtrOf<SMEM>::type P;
+        static constexpr int CS = 32 * (int)sizeof(T), IS = (32 / FPC) * (int)sizeof(IdxT), VS = FPC * (int)sizeof(T);
+
+        template <int K> struct Step
+        {
+            static __device__ __forceinline__ void load(P src, P c2v0, P col0, bool first, T (&v)[D], uint32_t &par)
             {
-                const uint32_t slot = p0 + k * npw;
-                const T o = src[(uint32_t)cn_col[slot] * fpc + f];
-                const T c = first ? T(0) : c2v[slot * fpc + f];
+                const uint32_t col = Acc<SMEM, IdxT, K * IS>::ld(col0);
+                const T o = Acc<SMEM, T, 0>::ld(src + col * VS);
+                T c = T(0);
+                if (!first) c = Acc<SMEM, T, K * CS>::ld(c2v0);
+                v[K] = o - c; // == the reference's stored v2c (decoder.cpp:62), or LLRin on the first pass (:18)
+                par ^= (o <= T(0)) ? 1u : 0u;
+                if constexpr (K + 1 < D) Step<K + 1>::load(src, c2v0, col0, first, v, par);
+            }
+            static __device__ __forceinline__ void store(P c2v0, const T (&r)[D])
+            {
+                Acc<SMEM, T, K * CS>::st(c2v0, r[K]);
+                if constexpr (K + 1 < D) Step<K + 1>::store(c2v0, r);
+            }
+        };
+
+        static __device__ __forceinline__ uint32_t run(P src, P c2v0, P col0, bool first)
+        {
+            T v[D], r[D];
+            uint32_t par = 0;
+            Step<0>::load(src, c2v0, col0, first, v, par);
+            if (ALG == ALG_MS)
+            {
+                // min-sum: f = sign*sign*min (decoder.h:17-20) through the forward/backward recursion of
+                // decoder.cpp:30-44.  Magnitudes: exact prefix/suffix minima; signs: XOR of sign BITS
+                // (std::signbit semantics, -0.0 is negative).
+                uint32_t sx = 0;
+                T a[D], pre[D], suf[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) { sx ^= Num<T>::hi(v[k]); a[k] = Num<T>::abs(v[k]); }
+                pre[0] = a[0];
+#pragma unroll
+                for (int k = 1; k < D; ++k) pre[k] = Num<T>::min_(pre[k - 1], a[k]);
+                suf[D - 1] = a[D - 1];
+#pragma unroll
+                for (int k = D - 2; k >= 0; --k) suf[k] = Num<T>::min_(suf[k + 1], a[k]);
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                {
+                    const T mag = (k == 0) ? suf[1] : (k == D - 1) ? pre[D - 2] : Num<T>::min_(pre[k - 1], suf[k + 1]);
+                    r[k] = Num<T>::with_sign(mag, sx ^ Num<T>::hi(v[k]));
+                }
+            }
+            else
+            {
+                // sum-product: the reference's forward/backward box-plus recursion, file order
+                T F[D];
+                F[0] = v[0];
+#pragma unroll
+                for (int k = 1; k < D; ++k) F[k] = boxplus(F[k - 1], v[k]);
+                T B = v[D - 1];
+                r[D - 1] = F[D - 2];
+#pragma unroll
+                for (int k = D - 2; k >= 1; --k) { r[k] = boxplus(F[k - 1], B); B = boxplus(B, v[k]); }
+                r[0] = B;
+            }
+            Step<0>::store(c2v0, r);
+            return par;
+        }
+    };
+
+    // arbitrary degree (<= 64): running min1/min2 + sign mask for min-sum, parked forward values for box-plus
+    template <typename T, typename IdxT, bool SMEM, int FPC, int ALG>
+    __device__ __noinline__ uint32_t cn_any(typename PtrOf<SMEM>::type src, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type col0,
+                                            int deg, bool first)
+    {
+        constexpr int CS = 32 * (int)sizeof(T), IS = (32 / FPC) * (int)sizeof(IdxT), VS = FPC * (int)sizeof(T);
+        uint32_t par = 0;
+        if (ALG == ALG_MS)
+        {
+            T min1 = Num<T>::inf(), min2 = Num<T>::inf();
+            int arg = 0;
+            unsigned long long smask = 0;
+            for (int k = 0; k < deg; ++k)
+            {
+                const uint32_t col = Acc<SMEM, IdxT, 0>::ld(col0 + k * IS);
+                const T o = Acc<SMEM, T, 0>::ld(src + col * VS);
+                const T c = first ? T(0) : Acc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                const T v = o - c;
+                par ^= (o <= T(0)) ? 1u : 0u;
+                smask |= (unsigned long long)(Num<T>::hi(v) >> 31) << k;
+                const T a = Num<T>::abs(v);
+                const bool lt1 = a < min1, lt2 = a < min2;
+                min2 = lt1 ? min1 : (lt2 ? a : min2);
+                arg = lt1 ? k : arg;
+                min1 = lt1 ? a : min1;
+            }
+            const uint32_t tot = (uint32_t)__popcll(smask) & 1u;
+            for (int k = 0; k < deg; ++k)
+            {
+                const T mag = (k == arg) ? min2 : min1;
+                const uint32_t s = tot ^ (uint32_t)((smask >> k) & 1ull);
+                Acc<SMEM, T, 0>::st(c2v0 + k * CS, Num<T>::with_sign(mag, s << 31));
+            }
+        }
+        else
+        {
+            T v[64];
+            for (int k = 0; k < deg; ++k)
+            {
+                const uint32_t col = Acc<SMEM, IdxT, 0>::ld(col0 + k * IS);
+                const T o = Acc<SMEM, T, 0>::ld(src + col * VS);
+                const T c = first ? T(0) : Acc<SMEM, T, 0>::ld(c2v0 + k * CS);
                 v[k] = o - c;
                 par ^= (o <= T(0)) ? 1u : 0u;
             }
-        F[0] = v[0];
-#pragma unroll
-        for (int k = 1; k < MAXD; ++k)
-            if (k < deg) F[k] = boxplus(F[k - 1], v[k]);
-        // backward sweep: B holds the combination of v[k+1..deg-1]
-        T B = T(0);
-#pragma unroll
-        for (int k = MAXD - 1; k >= 0; --k)
-            if (k < deg)
+            T Fp = v[0]; // F[k-1] while visiting k
+            for (int k = 1; k < deg; ++k)
             {
-                T r;
-                if (k == deg - 1) { r = F[(k > 0) ? k - 1 : 0]; B = v[k]; }                     // c2v[last] = F[cw-2]
-                else if (k == 0) { r = B; }                                                     // c2v[0] = B[1]
-                else { r = boxplus(F[k - 1], B); B = boxplus(B, v[k]); }                         // f(F[j-1], B[j+1])
-                c2v[(p0 + k * npw) * fpc + f] = r;
+                Acc<SMEM, T, 0>::st(c2v0 + k * CS, Fp); // park F[k-1] in slot k (slot deg-1 thereby gets its final value)
+                Fp = boxplus(Fp, v[k]);
             }
+            T B = v[deg - 1];
+            for (int k = deg - 2; k >= 1; --k)
+            {
+                const T f = Acc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                Acc<SMEM, T, 0>::st(c2v0 + k * CS, boxplus(f, B));
+                B = boxplus(B, v[k]);
+            }
+            Acc<SMEM, T, 0>::st(c2v0, B);
+        }
         return par;
     }
 
-    // same recursion for arbitrary degree: F is parked in the (about to be overwritten) message slots
-    template <typename T, typename IdxT>
-    __device__ __noinline__ uint32_t cn_boxplus_any(const T *__restrict__ src, T *__restrict__ c2v, const IdxT *__restrict__ cn_col,
-                                                    uint32_t p0, int deg, int npw, int fpc, int f, bool first)
+    // variable node: posterior = LLRin + sum of incoming c2v, strictly in file order (decoder.cpp:50-56)
+    template <typename T, typename IdxT, bool SMEM, int FPC, int D>
+    struct VnFixed
     {
-        T v[64];
-        uint32_t par = 0;
-        for (int k = 0; k < deg; ++k)
+        typedef typename PtrOf<SMEM>::type P;
+        static constexpr int IS = (32 / FPC) * (int)sizeof(IdxT), VS = FPC * (int)sizeof(T);
+        template <int K> struct Step
         {
-            const uint32_t slot = p0 + k * npw;
-            const T o = src[(uint32_t)cn_col[slot] * fpc + f];
-            const T c = first ? T(0) : c2v[slot * fpc + f];
-            v[k] = o - c;
-            par ^= (o <= T(0)) ? 1u : 0u;
-        }
-        T Fp = v[0]; // F[k-1] while visiting k
-        for (int k = 1; k < deg; ++k)
+            static __device__ __forceinline__ void load(P c2v, P slot0, T (&m)[D])
+            {
+                const uint32_t s = Acc<SMEM, IdxT, K * IS>::ld(slot0);
+                m[K] = Acc<SMEM, T, 0>::ld(c2v + s * VS);
+                if constexpr (K + 1 < D) Step<K + 1>::load(c2v, slot0, m);
+            }
+        };
+        static __device__ __forceinline__ T run(P c2v, P slot0, T acc)
         {
-            c2v[(p0 + k * npw) * fpc + f] = Fp; // park F[k-1] in slot k
-            Fp = boxplus(Fp, v[k]);
+            T m[D];
+            Step<0>::load(c2v, slot0, m);
+#pragma unroll
+            for (int k = 0; k < D; ++k) acc += m[k];
+            return acc;
         }
-        T B = v[deg - 1]; // slot deg-1 already holds F[deg-2] == its final value
-        for (int k = deg - 2; k >= 1; --k)
+    };
+
+    template <typename T, typename IdxT, bool SMEM, int FPC>
+    __device__ __forceinline__ T vn_any(typename PtrOf<SMEM>::type c2v, typename PtrOf<SMEM>::type slot0, int deg, T acc)
+    {
+        constexpr int IS = (32 / FPC) * (int)sizeof(IdxT), VS = FPC * (int)sizeof(T);
+        int k = 0;
+        for (; k + 4 <= deg; k += 4)
         {
-            const uint32_t idx = (p0 + k * npw) * fpc + f;
-            c2v[idx] = boxplus(c2v[idx], B);
-            B = boxplus(B, v[k]);
+            const uint32_t s0 = Acc<SMEM, IdxT, 0>::ld(slot0 + k * IS), s1 = Acc<SMEM, IdxT, IS>::ld(slot0 + k * IS);
+            const uint32_t s2 = Acc<SMEM, IdxT, 2 * IS>::ld(slot0 + k * IS), s3 = Acc<SMEM, IdxT, 3 * IS>::ld(slot0 + k * IS);
+            const T m0 = Acc<SMEM, T, 0>::ld(c2v + s0 * VS), m1 = Acc<SMEM, T, 0>::ld(c2v + s1 * VS);
+            const T m2 = Acc<SMEM, T, 0>::ld(c2v + s2 * VS), m3 = Acc<SMEM, T, 0>::ld(c2v + s3 * VS);
+            acc += m0; acc += m1; acc += m2; acc += m3;
         }
-        c2v[p0 * fpc + f] = B;
-        return par;
+        for (; k < deg; ++k) acc += Acc<SMEM, T, 0>::ld(c2v + (uint32_t)Acc<SMEM, IdxT, 0>::ld(slot0 + k * IS) * VS);
+        return acc;
     }
 
     // ------------------------------------------------------------------------------------------
     // the persistent tile kernel
     // ------------------------------------------------------------------------------------------
-    template <typename T, typename IdxT, int ALG, bool SMEM>
+    template <typename T, typename IdxT, int ALG, bool SMEM, int FPC>
     __global__ void __launch_bounds__(ALG == ALG_MS ? 1024 : 512, 1) tile_kernel(const KParams p)
     {
+        typedef typename PtrOf<SMEM>::type P;
+        constexpr int FSHIFT = (FPC == 32) ? 5 : (FPC == 16) ? 4 : (FPC == 8) ? 3 : (FPC == 4) ? 2 : (FPC == 2) ? 1 : 0;
+        constexpr int NPW = 32 / FPC;
+        constexpr int TS = (int)sizeof(T), VS = FPC * TS, IS1 = (int)sizeof(IdxT);
         extern __shared__ __align__(16) unsigned char dyn_smem[];
         __shared__ unsigned long long s_frame[32];
         __shared__ unsigned long long s_cnt[5];
@@ -243,45 +387,44 @@ namespace b200
         __shared__ uint32_t s_done_mask, s_next;
 
         const int tid = threadIdx.x, nthreads = blockDim.x;
-        const int fpc = p.fpc;
-        const int f = tid & (fpc - 1);
-        const int nth = tid >> p.fshift;     // node thread
-        const int NT = nthreads >> p.fshift; // node threads per CTA
-        const int npw = 32 >> p.fshift;
+        const int f = tid & (FPC - 1);
+        const int nth = tid >> FSHIFT;     // node thread
+        const int NT = nthreads >> FSHIFT; // node threads per CTA
         const int lane = tid & 31;
         const int nc = p.nc;
 
         // ---- carve state and tables --------------------------------------------------------
-        T *c2v, *out, *llr;
-        const uint32_t *cn_desc, *vn_desc;
-        const IdxT *cn_col, *vn_slot, *vn_id;
-        if (SMEM)
+        P c2v, out, llr, cn_desc, vn_desc, cn_col, vn_slot, vn_id;
+        if constexpr (SMEM)
         {
-            unsigned char *q = dyn_smem;
-            c2v = reinterpret_cast<T *>(q); q += sizeof(T) * (size_t)p.n_slots * fpc;
-            out = reinterpret_cast<T *>(q); q += sizeof(T) * (size_t)nc * fpc;
-            llr = reinterpret_cast<T *>(q); q += sizeof(T) * (size_t)nc * fpc;
-            uint32_t *cd = reinterpret_cast<uint32_t *>(q); q += 4 * (size_t)p.cn_rounds * NT;
-            uint32_t *vd = reinterpret_cast<uint32_t *>(q); q += 4 * (size_t)p.vn_rounds * NT;
-            IdxT *cc = reinterpret_cast<IdxT *>(q); q += sizeof(IdxT) * (size_t)p.n_slots;
-            IdxT *vs = reinterpret_cast<IdxT *>(q); q += sizeof(IdxT) * (size_t)p.n_vslots;
-            IdxT *vi = reinterpret_cast<IdxT *>(q);
-            for (int i = tid; i < p.cn_rounds * NT; i += nthreads) cd[i] = p.cn_desc[i];
-            for (int i = tid; i < p.vn_rounds * NT; i += nthreads) { vd[i] = p.vn_desc[i]; vi[i] = static_cast<const IdxT *>(p.vn_id)[i]; }
-            for (int i = tid; i < p.n_slots; i += nthreads) cc[i] = static_cast<const IdxT *>(p.cn_col)[i];
-            for (int i = tid; i < p.n_vslots; i += nthreads) vs[i] = static_cast<const IdxT *>(p.vn_slot)[i];
-            cn_desc = cd; vn_desc = vd; cn_col = cc; vn_slot = vs; vn_id = vi;
+            uint32_t q = (uint32_t)__cvta_generic_to_shared(dyn_smem);
+            uint32_t a_c2v = q; q += TS * p.n_slots * FPC;
+            uint32_t a_out = q; q += TS * nc * FPC;
+            uint32_t a_llr = q; q += TS * nc * FPC;
+            uint32_t a_cd = q; q += 4 * p.cn_rounds * NT;
+            uint32_t a_vd = q; q += 4 * p.vn_rounds * NT;
+            uint32_t a_cc = q; q += IS1 * p.n_slots;
+            uint32_t a_vs = q; q += IS1 * p.n_vslots;
+            uint32_t a_vi = q;
+            for (int i = tid; i < p.cn_rounds * NT; i += nthreads) sts_u32<0>(a_cd + 4 * i, p.cn_desc[i]);
+            for (int i = tid; i < p.vn_rounds * NT; i += nthreads)
+            {
+                sts_u32<0>(a_vd + 4 * i, p.vn_desc[i]);
+                Acc<true, IdxT, 0>::st(a_vi + IS1 * i, static_cast<const IdxT *>(p.vn_id)[i]);
+            }
+            for (int i = tid; i < p.n_slots; i += nthreads) Acc<true, IdxT, 0>::st(a_cc + IS1 * i, static_cast<const IdxT *>(p.cn_col)[i]);
+            for (int i = tid; i < p.n_vslots; i += nthreads) Acc<true, IdxT, 0>::st(a_vs + IS1 * i, static_cast<const IdxT *>(p.vn_slot)[i]);
+            c2v = a_c2v; out = a_out; llr = a_llr; cn_desc = a_cd; vn_desc = a_vd; cn_col = a_cc; vn_slot = a_vs; vn_id = a_vi;
         }
         else
         {
             unsigned char *q = p.state + p.state_stride * blockIdx.x;
-            c2v = reinterpret_cast<T *>(q); q += sizeof(T) * (size_t)p.n_slots * fpc;
-            out = reinterpret_cast<T *>(q); q += sizeof(T) * (size_t)nc * fpc;
-            llr = reinterpret_cast<T *>(q);
-            cn_desc = p.cn_desc; vn_desc = p.vn_desc;
-            cn_col = static_cast<const IdxT *>(p.cn_col);
-            vn_slot = static_cast<const IdxT *>(p.vn_slot);
-            vn_id = static_cast<const IdxT *>(p.vn_id);
+            unsigned char *g_c2v = q; q += (size_t)TS * p.n_slots * FPC;
+            unsigned char *g_out = q; q += (size_t)TS * nc * FPC;
+            unsigned char *g_llr = q;
+            c2v = g_c2v; out = g_out; llr = g_llr;
+            cn_desc = (unsigned char *)p.cn_desc; vn_desc = (unsigned char *)p.vn_desc;
+            cn_col = (unsigned char *)p.cn_col; vn_slot = (unsigned char *)p.vn_slot; vn_id = (unsigned char *)p.vn_id;
         }
         if (tid < 5) s_cnt[tid] = 0;
         if (tid < 32) { s_synd[tid] = 0; s_err[tid] = 0; s_newstate[tid] = 0; }
@@ -295,10 +438,11 @@ namespace b200
         // Writes the decoder input of global frame gf into lane g (all threads of the CTA cooperate).
         auto generate = [&](int g, unsigned long long gf)
         {
+            const P dst = llr + g * TS;
             if (p.kind == SRC_LLR)
             {
                 const double *src = p.llr_in + (size_t)gf * nc;
-                for (int i = tid; i < nc; i += nthreads) llr[i * fpc + g] = (T)src[i];
+                for (int i = tid; i < nc; i += nthreads) Acc<SMEM, T, 0>::st(dst + i * VS, (T)src[i]);
                 return;
             }
             const unsigned long long frame = p.frame0 + gf;
@@ -316,11 +460,11 @@ namespace b200
                     const double y0 = __dadd_rn(__dmul_rn(rad * cs, p.sigma), 1.0);
                     const double y1 = __dadd_rn(__dmul_rn(rad * sn, p.sigma), 1.0);
                     const int t = 2 * j;
-                    llr[p.bit_pos[t] * fpc + g] = (T)(__dmul_rn(2.0, y0) / p.sigma2);
-                    if (t + 1 < p.nct) llr[p.bit_pos[t + 1] * fpc + g] = (T)(__dmul_rn(2.0, y1) / p.sigma2);
+                    Acc<SMEM, T, 0>::st(dst + p.bit_pos[t] * VS, (T)(__dmul_rn(2.0, y0) / p.sigma2));
+                    if (t + 1 < p.nct) Acc<SMEM, T, 0>::st(dst + p.bit_pos[t + 1] * VS, (T)(__dmul_rn(2.0, y1) / p.sigma2));
                 }
-                for (int i = tid; i < p.n_punct; i += nthreads) llr[p.punct[i] * fpc + g] = T(0);
-                for (int i = tid; i < p.n_short; i += nthreads) llr[p.shorten[i] * fpc + g] = (T)99999.9;
+                for (int i = tid; i < p.n_punct; i += nthreads) Acc<SMEM, T, 0>::st(dst + p.punct[i] * VS, T(0));
+                for (int i = tid; i < p.n_short; i += nthreads) Acc<SMEM, T, 0>::st(dst + p.shorten[i] * VS, (T)99999.9);
             }
             else
             { // BSC: y = x ^ Bernoulli(eps), LLR = delta*(1-2y) (src/sim/channel.cpp:123-162)
@@ -333,11 +477,11 @@ namespace b200
                     for (int q = 0; q < 4; ++q)
                     {
                         const int t = 4 * j + q;
-                        if (t < p.nct) llr[p.bit_pos[t] * fpc + g] = (T)((w[q] < p.thr) ? -p.delta : p.delta);
+                        if (t < p.nct) Acc<SMEM, T, 0>::st(dst + p.bit_pos[t] * VS, (T)((w[q] < p.thr) ? -p.delta : p.delta));
                     }
                 }
-                for (int i = tid; i < p.n_punct; i += nthreads) llr[p.punct[i] * fpc + g] = T(0);
-                for (int i = tid; i < p.n_short; i += nthreads) llr[p.shorten[i] * fpc + g] = (T)p.delta;
+                for (int i = tid; i < p.n_punct; i += nthreads) Acc<SMEM, T, 0>::st(dst + p.punct[i] * VS, T(0));
+                for (int i = tid; i < p.n_short; i += nthreads) Acc<SMEM, T, 0>::st(dst + p.shorten[i] * VS, (T)p.delta);
             }
         };
 
@@ -347,13 +491,13 @@ namespace b200
         {
             if (write_outputs && (p.llr_out || p.hard_out || p.iters_out))
             {
-                for (int g = 0; g < fpc; ++g)
+                for (int g = 0; g < FPC; ++g)
                     if ((mask >> g) & 1u)
                     {
                         const size_t o = (size_t)s_frame[g] * nc;
                         for (int i = tid; i < nc; i += nthreads)
                         {
-                            const T v = out[i * fpc + g];
+                            const T v = Acc<SMEM, T, 0>::ld(out + i * VS + g * TS);
                             if (p.llr_out) p.llr_out[o + i] = (double)v;
                             if (p.hard_out) p.hard_out[o + i] = (v <= T(0)) ? 1 : 0; // decoder.cpp:58
                         }
@@ -363,7 +507,7 @@ namespace b200
             }
             if (tid == 0)
             {
-                for (int g = 0; g < fpc; ++g)
+                for (int g = 0; g < FPC; ++g)
                     if ((mask >> g) & 1u)
                     {
                         const unsigned long long gf = (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * s_next;
@@ -372,16 +516,19 @@ namespace b200
                     }
             }
             __syncthreads();
-            for (int g = 0; g < fpc; ++g)
+            for (int g = 0; g < FPC; ++g)
                 if (((mask >> g) & 1u) && s_newstate[g]) generate(g, s_frame[g]);
             if ((mask >> f) & 1u) { st = s_newstate[f]; it = 0; }
         };
 
-        retire_and_refill(fpc == 32 ? 0xFFFFFFFFu : ((1u << fpc) - 1u), 1u, false);
+        retire_and_refill(FPC == 32 ? 0xFFFFFFFFu : ((1u << FPC) - 1u), 1u, false);
 
         // bit pattern of the warp lanes that serve frame lane 0
         uint32_t lane_pattern = 0;
-        for (int b = 0; b < 32; b += fpc) lane_pattern |= 1u << b;
+#pragma unroll
+        for (int b = 0; b < 32; b += FPC) lane_pattern |= 1u << b;
+
+        const P c2v_f = c2v + f * TS, out_f = out + f * TS, llr_f = llr + f * TS;
 
         for (;;)
         {
@@ -394,7 +541,7 @@ namespace b200
                 if (tid < 32)
                 {
                     bool fin = false;
-                    if (tid < fpc && st == 1 && it >= p.max_iter)
+                    if (tid < FPC && st == 1 && it >= p.max_iter)
                     {
                         const uint32_t e = s_err[f];
                         atomicAdd(&s_cnt[0], (unsigned long long)(e ? 1 : 0));
@@ -422,22 +569,32 @@ namespace b200
             if (st)
             {
                 const bool first = (it == 0);
-                const T *src = first ? llr : out;
+                const P src = first ? llr_f : out_f;
                 for (int r = 0; r < p.cn_rounds; ++r)
                 {
-                    const uint32_t d = cn_desc[r * NT + nth];
+                    const uint32_t d = Acc<SMEM, uint32_t, 0>::ld(cn_desc + 4 * (r * NT + nth));
                     if (d == IDLE) continue;
                     const uint32_t p0 = d & 0xFFFFFFu;
                     const int deg = (int)(d >> 24);
-                    if (ALG == ALG_MS) par |= cn_minsum<T, IdxT>(src, c2v, cn_col, p0, deg, npw, fpc, f, first);
-                    else if (deg <= 8) par |= cn_boxplus<T, IdxT, 8>(src, c2v, cn_col, p0, deg, npw, fpc, f, first);
-                    else par |= cn_boxplus_any<T, IdxT>(src, c2v, cn_col, p0, deg, npw, fpc, f, first);
+                    const P c2v0 = c2v_f + p0 * VS;
+                    const P col0 = cn_col + p0 * IS1;
+                    switch (deg) // warp-uniform: a warp's node group has one degree
+                    {
+                    case 2: par |= CnFixed<T, IdxT, SMEM, FPC, ALG, 2>::run(src, c2v0, col0, first); break;
+                    case 3: par |= CnFixed<T, IdxT, SMEM, FPC, ALG, 3>::run(src, c2v0, col0, first); break;
+                    case 4: par |= CnFixed<T, IdxT, SMEM, FPC, ALG, 4>::run(src, c2v0, col0, first); break;
+                    case 5: par |= CnFixed<T, IdxT, SMEM, FPC, ALG, 5>::run(src, c2v0, col0, first); break;
+                    case 6: par |= CnFixed<T, IdxT, SMEM, FPC, ALG, 6>::run(src, c2v0, col0, first); break;
+                    case 7: par |= CnFixed<T, IdxT, SMEM, FPC, ALG, 7>::run(src, c2v0, col0, first); break;
+                    case 8: par |= CnFixed<T, IdxT, SMEM, FPC, ALG, 8>::run(src, c2v0, col0, first); break;
+                    default: par |= cn_any<T, IdxT, SMEM, FPC, ALG>(src, c2v0, col0, deg, first); break;
+                    }
                 }
             }
             // warp-ballot syndrome test: one vote per thread, folded per frame lane
             {
                 const uint32_t b = __ballot_sync(0xffffffffu, par != 0);
-                if (lane < fpc && (b & (lane_pattern << lane))) s_synd[lane] = 1;
+                if (lane < FPC && (b & (lane_pattern << lane))) s_synd[lane] = 1;
             }
             __syncthreads();
 
@@ -445,7 +602,7 @@ namespace b200
             if (tid < 32)
             {
                 bool fin = false;
-                if (tid < fpc)
+                if (tid < FPC)
                 {
                     if (st == 1)
                     {
@@ -481,22 +638,35 @@ namespace b200
             {
                 for (int r = 0; r < p.vn_rounds; ++r)
                 {
-                    const uint32_t d = vn_desc[r * NT + nth];
+                    const uint32_t d = Acc<SMEM, uint32_t, 0>::ld(vn_desc + 4 * (r * NT + nth));
                     if (d == IDLE) continue;
-                    const uint32_t id = vn_id[r * NT + nth];
+                    const uint32_t id = Acc<SMEM, IdxT, 0>::ld(vn_id + IS1 * (r * NT + nth));
                     const uint32_t q0 = d & 0x7FFFFFu;
                     const int deg = (int)((d >> 23) & 0xFFu);
-                    T acc = llr[id * fpc + f]; // decoder.cpp:50
-#pragma unroll 4
-                    for (int k = 0; k < deg; ++k) acc += c2v[(uint32_t)vn_slot[q0 + k * npw] * fpc + f]; // file order, decoder.cpp:53-56
-                    out[id * fpc + f] = acc;
+                    const P slot0 = vn_slot + q0 * IS1;
+                    T acc = Acc<SMEM, T, 0>::ld(llr_f + id * VS); // decoder.cpp:50
+                    switch (deg)
+                    {
+                    case 0: break;
+                    case 1: acc = VnFixed<T, IdxT, SMEM, FPC, 1>::run(c2v_f, slot0, acc); break;
+                    case 2: acc = VnFixed<T, IdxT, SMEM, FPC, 2>::run(c2v_f, slot0, acc); break;
+                    case 3: acc = VnFixed<T, IdxT, SMEM, FPC, 3>::run(c2v_f, slot0, acc); break;
+                    case 4: acc = VnFixed<T, IdxT, SMEM, FPC, 4>::run(c2v_f, slot0, acc); break;
+                    case 5: acc = VnFixed<T, IdxT, SMEM, FPC, 5>::run(c2v_f, slot0, acc); break;
+                    case 6: acc = VnFixed<T, IdxT, SMEM, FPC, 6>::run(c2v_f, slot0, acc); break;
+                    case 8: acc = VnFixed<T, IdxT, SMEM, FPC, 8>::run(c2v_f, slot0, acc); break;
+                    case 15: acc = VnFixed<T, IdxT, SMEM, FPC, 15>::run(c2v_f, slot0, acc); break;
+                    default: acc = vn_any<T, IdxT, SMEM, FPC>(c2v_f, slot0, deg, acc); break;
+                    }
+                    Acc<SMEM, T, 0>::st(out_f + id * VS, acc);
                     err += ((d >> 31) && acc <= T(0)) ? 1u : 0u; // all-zero codeword: ldpcsim.cpp:184-188
                 }
                 ++it;
             }
             else if (st == 2) st = 1;
-            for (int o = fpc; o < 32; o <<= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
-            if (lane < fpc && err) atomicAdd(&s_err[lane], err);
+#pragma unroll
+            for (int o = FPC; o < 32; o <<= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+            if (lane < FPC && err) atomicAdd(&s_err[lane], err);
         }
 
         __syncthreads();

@@ -1,0 +1,6 @@
+// tile kernel family instantiation: T = float, algorithm = ALG_MS
+#include "tile_launch.cuh"
+namespace b200
+{
+    B200_DEFINE_TILE_FAMILY(float, ALG_MS)
+}

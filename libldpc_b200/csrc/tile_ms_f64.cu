@@ -1,0 +1,6 @@
+// tile kernel family instantiation: T = double, algorithm = ALG_MS
+#include "tile_launch.cuh"
+namespace b200
+{
+    B200_DEFINE_TILE_FAMILY(double, ALG_MS)
+}
