@@ -63,4 +63,30 @@ namespace b200
 
         void build(const HostCode &code, int fpc, int threads);
     };
+
+    // Vector-tile mapping (tile3.cuh): one thread owns ONE 16-byte vector of adjacent frame lanes
+    // (2 doubles / 4 floats) of one node; `lanes` warp lanes serve the same node (so a CTA holds
+    // lanes * 16/sizeof(T) frames).  Work is cut into warp tasks: npw = 32/lanes nodes of equal degree
+    // (variable tasks also of equal transmitted/punctured status), spread longest-first over the warps;
+    // a task is described once per warp (8 bytes, broadcast load) instead of once per thread.
+    // Variables are renumbered into schedule order ("positions") so that the variable phase walks
+    // llr/out contiguously; the check side gathers by position.
+    struct TaskLayout
+    {
+        int lanes = 0, threads = 0, warps = 0, npw = 0;
+        int n_slots = 0;  // padded message slots: task base + k*npw + node
+        int n_pos = 0;    // padded variable positions: task base + node
+        int n_vslots = 0; // padded entries of vn_slot
+        int cn_rounds = 0, vn_rounds = 0;
+        // entry (round r, warp w) at 2*(r*warps + w): {slot base | degree << 24, node count (0 = idle)}
+        std::vector<uint32_t> cn_task;
+        std::vector<uint32_t> cn_col; // [n_slots] position of the variable each slot gathers from
+        // entry (round r, warp w): {vn_slot base | degree << 23 | transmitted << 31, position base | node count << 24}
+        std::vector<uint32_t> vn_task;
+        std::vector<uint32_t> vn_slot; // [n_vslots] message slot of edge k (file order) of node j at base + k*npw + j
+        std::vector<uint32_t> var_pos; // [nc] variable id -> position
+        std::vector<int> edge_slot;    // [nnz] file-order edge -> message slot
+
+        void build(const HostCode &code, int lanes, int threads);
+    };
 } // namespace b200

@@ -31,6 +31,19 @@ namespace b200
         }
     };
 
+    struct DeviceTaskLayout
+    {
+        uint32_t *cn_task = nullptr, *vn_task = nullptr, *var_pos = nullptr;
+        void *cn_col = nullptr, *vn_slot = nullptr;
+        int32_t *tx_pos = nullptr, *punct_pos = nullptr, *short_pos = nullptr;
+        const TaskLayout *host = nullptr;
+        ~DeviceTaskLayout()
+        {
+            cudaFree(cn_task); cudaFree(vn_task); cudaFree(var_pos); cudaFree(cn_col); cudaFree(vn_slot);
+            cudaFree(tx_pos); cudaFree(punct_pos); cudaFree(short_pos);
+        }
+    };
+
     namespace
     {
         template <typename IdxT>
@@ -62,6 +75,24 @@ namespace b200
             return b + 16;
         }
 
+        size_t task_smem_bytes(const TaskLayout &l, bool idx16)
+        {
+            const size_t idx = idx16 ? 2 : 4, rs = 16 * (size_t)l.lanes;
+            size_t b = rs * ((size_t)l.n_slots + 2 * (size_t)l.n_pos);
+            b += 8 * ((size_t)l.cn_rounds + l.vn_rounds) * l.warps;
+            b += (idx * (size_t)l.n_slots + 15) & ~(size_t)15;
+            b += idx * (size_t)l.n_vslots;
+            return b + 16;
+        }
+
+        int family_occupancy(int precision, int alg, bool smem, int lanes, int threads, size_t smem_bytes)
+        {
+            if (precision == LDPC_B200_F32)
+                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, lanes, threads, smem_bytes)
+                                     : tile_family_occupancy<float, ALG_BP>(smem, lanes, threads, smem_bytes);
+            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, lanes, threads, smem_bytes)
+                                 : tile_family_occupancy<double, ALG_BP>(smem, lanes, threads, smem_bytes);
+        }
     } // namespace
 
     // ------------------------------------------------------------------------------------------
@@ -84,6 +115,7 @@ namespace b200
         if (!cuda_ready_) return;
         cudaSetDevice(device);
         dev_layouts_.clear();
+        dev_task_layouts_.clear();
         cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
         if (ev0_) cudaEventDestroy((cudaEvent_t)ev0_);
         if (ev1_) cudaEventDestroy((cudaEvent_t)ev1_);
@@ -125,6 +157,116 @@ namespace b200
         cuda_ready_ = true;
     }
 
+    const TaskLayout &Engine::get_task_layout(int lanes, int threads)
+    {
+        auto key = std::make_pair(lanes, threads);
+        auto it = task_layouts_.find(key);
+        if (it == task_layouts_.end())
+        {
+            auto l = std::make_unique<TaskLayout>();
+            l->build(H, lanes, threads);
+            it = task_layouts_.emplace(key, std::move(l)).first;
+        }
+        return *it->second;
+    }
+
+    // Configuration policy.  A CTA holds lanes * VEC frames (VEC = 2 doubles / 4 floats per 16-byte
+    // vector).  Shared-memory residency is used whenever the code fits: the widest tile that fits
+    // with the default thread count wins (it shares every index load / address computation between
+    // the most frames); otherwise messages live in global memory (L2 / HBM).
+    const TaskLayout &Engine::layout_for(int precision, int alg, int *residency, size_t *smem_bytes)
+    {
+        const int vec = precision == LDPC_B200_F32 ? 4 : 2;
+        const int max_threads = alg == ALG_MS ? 1024 : 512;
+        const int threads = tuning.threads_per_cta > 0 ? std::min(tuning.threads_per_cta, max_threads) : max_threads;
+        int want_lanes = 0;
+        if (tuning.frames_per_cta > 0)
+        {
+            if (tuning.frames_per_cta % vec) throw std::runtime_error("frames_per_cta must be a multiple of the vector width (2 for f64, 4 for f32)");
+            want_lanes = tuning.frames_per_cta / vec;
+            if (want_lanes != 1 && want_lanes != 2 && want_lanes != 4 && want_lanes != 8)
+                throw std::runtime_error("frames_per_cta / vector width must be 1, 2, 4 or 8");
+        }
+        const size_t limit = std::min<size_t>(smem_optin_ > 1024 ? smem_optin_ - 1024 : 0, (size_t)TILE_SMEM_OPTIN);
+        if (tuning.residency != LDPC_B200_GLOBAL)
+        {
+            for (int lanes = 8; lanes >= 1; lanes >>= 1)
+            {
+                if (want_lanes && lanes != want_lanes) continue;
+                const TaskLayout &l = get_task_layout(lanes, threads);
+                if (std::max({l.n_slots, l.n_vslots, l.n_pos}) > 65535) continue;
+                const size_t need = task_smem_bytes(l, true);
+                if (need <= limit)
+                {
+                    *residency = LDPC_B200_SMEM;
+                    *smem_bytes = need;
+                    return l;
+                }
+            }
+            if (tuning.residency == LDPC_B200_SMEM) throw std::runtime_error("code does not fit shared-memory residency with this tuning");
+        }
+        *residency = LDPC_B200_GLOBAL;
+        *smem_bytes = 0;
+        return get_task_layout(want_lanes ? want_lanes : 2, threads);
+    }
+
+    Engine::Config Engine::choose(int precision, int alg, uint64_t n_frames)
+    {
+        Config c{};
+        c.precision = precision;
+        c.alg = alg;
+        const TaskLayout &l = layout_for(precision, alg, &c.residency, &c.smem_bytes);
+        c.lanes = l.lanes;
+        c.fpc = l.lanes * (precision == LDPC_B200_F32 ? 4 : 2);
+        c.threads = l.threads;
+        c.idx16 = (c.residency == LDPC_B200_SMEM); // shared-memory residency: 16-bit tables; global: 32-bit
+        int ctas = tuning.ctas;
+        if (ctas <= 0)
+        { // persistent grid: every SM gets as many CTAs as the runtime keeps resident
+            auto key = std::make_tuple(precision, alg, c.residency, c.lanes, c.threads, c.smem_bytes);
+            auto it = occupancy_.find(key);
+            if (it == occupancy_.end())
+                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.idx16, c.lanes, c.threads, c.smem_bytes)).first;
+            if (it->second < 1) throw std::runtime_error("tile kernel does not fit on this device with the current tuning");
+            ctas = sm_count_ * it->second;
+        }
+        const uint64_t need = (n_frames + c.fpc - 1) / c.fpc;
+        if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
+        c.ctas = ctas;
+        return c;
+    }
+
+    DeviceTaskLayout &Engine::device_task_layout(int lanes, int threads, bool idx16)
+    {
+        auto key = std::make_tuple(lanes, threads, idx16);
+        auto it = dev_task_layouts_.find(key);
+        if (it != dev_task_layouts_.end()) return *it->second;
+        const TaskLayout &l = get_task_layout(lanes, threads);
+        auto d = std::make_unique<DeviceTaskLayout>();
+        d->host = &l;
+        d->cn_task = upload(l.cn_task);
+        d->vn_task = upload(l.vn_task);
+        d->var_pos = upload(l.var_pos);
+        if (idx16)
+        {
+            d->cn_col = upload_idx<uint16_t>(l.cn_col);
+            d->vn_slot = upload_idx<uint16_t>(l.vn_slot);
+        }
+        else
+        {
+            d->cn_col = upload_idx<uint32_t>(l.cn_col);
+            d->vn_slot = upload_idx<uint32_t>(l.vn_slot);
+        }
+        std::vector<int32_t> tx, pu, sh;
+        for (int v : H.bit_pos) tx.push_back((int32_t)l.var_pos[v]);
+        for (int v : H.puncture) if (v >= 0 && v < H.nc) pu.push_back((int32_t)l.var_pos[v]);
+        for (int v : H.shorten) if (v >= 0 && v < H.nc) sh.push_back((int32_t)l.var_pos[v]);
+        d->tx_pos = upload(tx);
+        d->punct_pos = upload(pu);
+        d->short_pos = upload(sh);
+        return *dev_task_layouts_.emplace(key, std::move(d)).first->second;
+    }
+
     const TileLayout &Engine::get_layout(int fpc, int threads)
     {
         auto key = std::make_pair(fpc, threads);
@@ -136,53 +278,6 @@ namespace b200
             it = layouts_.emplace(key, std::move(l)).first;
         }
         return *it->second;
-    }
-
-    const TileLayout &Engine::layout_for(int precision, int alg, int *residency, size_t *smem_bytes)
-    {
-        const size_t st = precision == LDPC_B200_F32 ? 4 : 8;
-        const int threads = tuning.threads_per_cta > 0 ? tuning.threads_per_cta : (alg == ALG_MS ? 1024 : 512);
-        auto get = [&](int fpc) -> const TileLayout & { return get_layout(fpc, threads); };
-        const size_t limit = smem_optin_ - 2048; // static shared memory of the kernel + slack
-        if (tuning.residency != LDPC_B200_GLOBAL)
-        {
-            for (int fpc = 32; fpc >= 4; fpc >>= 1)
-            {
-                if (tuning.frames_per_cta > 0 && fpc != tuning.frames_per_cta) continue;
-                if (threads / fpc < 1) continue;
-                const TileLayout &l = get(fpc);
-                const bool idx16 = std::max({l.n_slots, l.n_vslots, H.nc}) <= 65535;
-                if (!idx16) continue;
-                const size_t need = tile_smem_bytes(l, st, H.nc, true);
-                if (need <= limit)
-                {
-                    *residency = LDPC_B200_SMEM;
-                    *smem_bytes = need;
-                    return l;
-                }
-            }
-            if (tuning.residency == LDPC_B200_SMEM) throw std::runtime_error("code does not fit shared-memory residency with this tuning");
-        }
-        const int fpc = tuning.frames_per_cta > 0 ? tuning.frames_per_cta : (int)(128 / st);
-        *residency = LDPC_B200_GLOBAL;
-        *smem_bytes = 0;
-        return get(fpc);
-    }
-
-    Engine::Config Engine::choose(int precision, int alg, uint64_t n_frames)
-    {
-        Config c{};
-        c.precision = precision;
-        c.alg = alg;
-        const TileLayout &l = layout_for(precision, alg, &c.residency, &c.smem_bytes);
-        c.fpc = l.fpc;
-        c.threads = l.threads;
-        c.idx16 = (c.residency == LDPC_B200_SMEM); // shared-memory residency: 16-bit tables; global: 32-bit
-        int ctas = tuning.ctas > 0 ? tuning.ctas : sm_count_;
-        const uint64_t need = (n_frames + c.fpc - 1) / c.fpc;
-        if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
-        c.ctas = ctas;
-        return c;
     }
 
     DeviceLayout &Engine::device_layout(int fpc, int threads, bool idx16)
@@ -245,18 +340,18 @@ namespace b200
 
         const int alg = minsum ? ALG_MS : ALG_BP;
         const Config c = choose(tuning.precision, alg, n_frames);
-        DeviceLayout &dl = device_layout(c.fpc, c.threads, c.idx16);
-        const TileLayout &l = *dl.host;
+        DeviceTaskLayout &dl = device_task_layout(c.lanes, c.threads, c.idx16);
+        const TaskLayout &l = *dl.host;
 
-        KParams kp{};
-        kp.cn_desc = dl.cn_desc; kp.vn_desc = dl.vn_desc;
-        kp.cn_col = dl.cn_col; kp.vn_slot = dl.vn_slot; kp.vn_id = dl.vn_id;
-        kp.bit_pos = d_bit_pos_; kp.punct = d_punct_; kp.shorten = d_short_;
-        kp.cn_rounds = l.cn_rounds; kp.vn_rounds = l.vn_rounds; kp.n_slots = l.n_slots; kp.n_vslots = l.n_vslots;
-        kp.nc = H.nc; kp.nct = H.nct(); kp.n_punct = (int)H.puncture.size(); kp.n_short = (int)H.shorten.size();
-        kp.fpc = c.fpc;
-        kp.fshift = 0;
-        while ((1 << kp.fshift) < c.fpc) ++kp.fshift;
+        K3Params kp{};
+        kp.cn_task = dl.cn_task; kp.vn_task = dl.vn_task;
+        kp.cn_col = dl.cn_col; kp.vn_slot = dl.vn_slot; kp.var_pos = dl.var_pos;
+        kp.tx_pos = dl.tx_pos; kp.punct_pos = dl.punct_pos; kp.short_pos = dl.short_pos;
+        kp.cn_rounds = l.cn_rounds; kp.vn_rounds = l.vn_rounds; kp.n_slots = l.n_slots; kp.n_vslots = l.n_vslots; kp.n_pos = l.n_pos;
+        kp.nc = H.nc; kp.nct = H.nct();
+        kp.n_punct = 0; kp.n_short = 0;
+        for (int v : H.puncture) if (v >= 0 && v < H.nc) ++kp.n_punct;
+        for (int v : H.shorten) if (v >= 0 && v < H.nc) ++kp.n_short;
         kp.max_iter = (int)dp.iterations;
         kp.early_term = dp.earlyTerm ? 1 : 0;
         kp.kind = src.kind;
@@ -277,21 +372,20 @@ namespace b200
         kp.counters = sink.d_counters ? sink.d_counters : d_counters_;
         if (c.residency == LDPC_B200_GLOBAL)
         {
-            const size_t st = c.precision == LDPC_B200_F32 ? 4 : 8;
-            kp.state_stride = ((st * ((size_t)l.n_slots + 2 * (size_t)H.nc) * c.fpc) + 255) & ~(size_t)255;
+            kp.state_stride = ((16 * (size_t)c.lanes * ((size_t)l.n_slots + 2 * (size_t)l.n_pos)) + 255) & ~(size_t)255;
             ensure_state(kp.state_stride * c.ctas);
             kp.state = d_state_;
         }
         const bool smem = c.residency == LDPC_B200_SMEM;
         if (c.precision == LDPC_B200_F32)
         {
-            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.fpc, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<float, ALG_BP>(kp, smem, c.fpc, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<float, ALG_BP>(kp, smem, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         else
         {
-            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.fpc, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<double, ALG_BP>(kp, smem, c.fpc, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<double, ALG_BP>(kp, smem, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         stats.launches += 1;
         stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;

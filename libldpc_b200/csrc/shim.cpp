@@ -245,7 +245,7 @@ extern "C"
             const auto &l = ctx->eng->layout_for(ctx->eng->tuning.precision, 0, &res, &smem);
             if (edge_slot) for (int e = 0; e < ctx->eng->H.nnz; ++e) edge_slot[e] = l.edge_slot[e];
             if (n_slots) *n_slots = l.n_slots;
-            if (frames_per_cta) *frames_per_cta = l.fpc;
+            if (frames_per_cta) *frames_per_cta = l.lanes * (ctx->eng->tuning.precision == LDPC_B200_F32 ? 4 : 2);
             if (threads_per_cta) *threads_per_cta = l.threads;
             if (residency) *residency = res;
         });

@@ -5,53 +5,82 @@
 #include <stdexcept>
 #include <string>
 
-#include "kernels.cuh"
+#include "tile3.cuh"
 
 namespace b200
 {
     // SMEM residency uses 16-bit indices, global residency 32-bit indices.
+    // lanes = warp lanes per node (frames per CTA = lanes * 16/sizeof(T)).
     template <typename T, int ALG>
-    void launch_tile_family(const KParams &kp, bool smem, int fpc, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
+    void launch_tile_family(const K3Params &kp, bool smem, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
 
-    template <typename T, typename IdxT, int ALG, bool SMEM, int FPC>
-    void launch_tile_one(const KParams &kp, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
+    // resident CTAs per SM the runtime grants this configuration (occupancy query; 0 = does not fit)
+    template <typename T, int ALG>
+    int tile_family_occupancy(bool smem, int lanes, int threads, size_t smem_bytes);
+
+    constexpr int TILE_SMEM_OPTIN = 232448 - 1024; // 227 KB minus the kernel's static shared memory
+
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES>
+    void prepare_tile_one()
     {
         static bool attr_set = false;
         if (SMEM && !attr_set)
         {
-            cudaError_t e = cudaFuncSetAttribute(tile_kernel<T, IdxT, ALG, SMEM, FPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
+            cudaError_t e = cudaFuncSetAttribute(tile3_kernel<T, IdxT, ALG, SMEM, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
             if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
             attr_set = true;
         }
-        tile_kernel<T, IdxT, ALG, SMEM, FPC><<<ctas, threads, SMEM ? smem_bytes : 0, s>>>(kp);
+    }
+
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES>
+    void launch_tile_one(const K3Params &kp, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
+    {
+        prepare_tile_one<T, IdxT, ALG, SMEM, LANES>();
+        tile3_kernel<T, IdxT, ALG, SMEM, LANES><<<ctas, threads, SMEM ? smem_bytes : 0, s>>>(kp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " (tile kernel launch)");
     }
 
-#define B200_DEFINE_TILE_FAMILY(T, ALG)                                                                                     \
-    template <>                                                                                                             \
-    void launch_tile_family<T, ALG>(const KParams &kp, bool smem, int fpc, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
-    {                                                                                                                       \
-        if (smem)                                                                                                           \
-        {                                                                                                                   \
-            switch (fpc)                                                                                                    \
-            {                                                                                                               \
-            case 4: launch_tile_one<T, uint16_t, ALG, true, 4>(kp, ctas, threads, smem_bytes, s); return;                   \
-            case 8: launch_tile_one<T, uint16_t, ALG, true, 8>(kp, ctas, threads, smem_bytes, s); return;                   \
-            case 16: launch_tile_one<T, uint16_t, ALG, true, 16>(kp, ctas, threads, smem_bytes, s); return;                 \
-            case 32: launch_tile_one<T, uint16_t, ALG, true, 32>(kp, ctas, threads, smem_bytes, s); return;                 \
-            }                                                                                                               \
-        }                                                                                                                   \
-        else                                                                                                                \
-        {                                                                                                                   \
-            switch (fpc)                                                                                                    \
-            {                                                                                                               \
-            case 4: launch_tile_one<T, uint32_t, ALG, false, 4>(kp, ctas, threads, 0, s); return;                           \
-            case 8: launch_tile_one<T, uint32_t, ALG, false, 8>(kp, ctas, threads, 0, s); return;                           \
-            case 16: launch_tile_one<T, uint32_t, ALG, false, 16>(kp, ctas, threads, 0, s); return;                         \
-            case 32: launch_tile_one<T, uint32_t, ALG, false, 32>(kp, ctas, threads, 0, s); return;                         \
-            }                                                                                                               \
-        }                                                                                                                   \
-        throw std::runtime_error("frames_per_cta must be 4, 8, 16 or 32");                                                  \
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES>
+    int occupancy_tile_one(int threads, size_t smem_bytes)
+    {
+        prepare_tile_one<T, IdxT, ALG, SMEM, LANES>();
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile3_kernel<T, IdxT, ALG, SMEM, LANES>, threads, SMEM ? smem_bytes : 0);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
+        return n;
     }
+
+#define B200_DEFINE_TILE_FAMILY(T, ALG)                                                                                \
+    template <>                                                                                                        \
+    void launch_tile_family<T, ALG>(const K3Params &kp, bool smem, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
+    {                                                                                                                  \
+        switch (lanes)                                                                                                 \
+        {                                                                                                              \
+            B200_TILE_LAUNCH_CASES(T, ALG)                                                                             \
+        default: throw std::runtime_error("lanes per node must be 1, 2, 4 or 8");                                      \
+        }                                                                                                              \
+    }                                                                                                                  \
+    template <>                                                                                                        \
+    int tile_family_occupancy<T, ALG>(bool smem, int lanes, int threads, size_t smem_bytes)                            \
+    {                                                                                                                  \
+        switch (lanes)                                                                                                 \
+        {                                                                                                              \
+            B200_TILE_OCC_CASES(T, ALG)                                                                                \
+        default: throw std::runtime_error("lanes per node must be 1, 2, 4 or 8");                                      \
+        }                                                                                                              \
+        return 0;                                                                                                      \
+    }
+
+#define B200_LAUNCH_CASE(T, ALG, L)                                                                                    \
+    case L:                                                                                                            \
+        if (smem) launch_tile_one<T, uint16_t, ALG, true, L>(kp, ctas, threads, smem_bytes, s);                        \
+        else launch_tile_one<T, uint32_t, ALG, false, L>(kp, ctas, threads, 0, s);                                     \
+        return;
+#define B200_OCC_CASE(T, ALG, L)                                                                                       \
+    case L:                                                                                                            \
+        return smem ? occupancy_tile_one<T, uint16_t, ALG, true, L>(threads, smem_bytes)                               \
+                    : occupancy_tile_one<T, uint32_t, ALG, false, L>(threads, 0);
+#define B200_TILE_LAUNCH_CASES(T, ALG) B200_LAUNCH_CASE(T, ALG, 1) B200_LAUNCH_CASE(T, ALG, 2) B200_LAUNCH_CASE(T, ALG, 4) B200_LAUNCH_CASE(T, ALG, 8)
+#define B200_TILE_OCC_CASES(T, ALG) B200_OCC_CASE(T, ALG, 1) B200_OCC_CASE(T, ALG, 2) B200_OCC_CASE(T, ALG, 4) B200_OCC_CASE(T, ALG, 8)
 } // namespace b200

@@ -1,5 +1,5 @@
 """Short, deterministic workload for ncu captures (a few launches of the dominant kernel).
-usage: python profiles/profile_cmd.py [ms|bp|ms32|et] [frames]"""
+usage: python profiles/profile_cmd.py [ms|bp|ms32|et] [frames] [frames_per_cta] [threads_per_cta] [codefile]"""
 import os
 import sys
 
@@ -9,11 +9,13 @@ from libldpc_b200 import api  # noqa: E402
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "ms"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 4 * 8
-ctx = api.Context(os.path.join(ROOT, "codes", "ref_h_n1152_m1024.txt"), "", device=0)
-if mode == "ms32":
-    ctx.set_tuning(precision=api.F32)
+fpc = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+threads = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+code = sys.argv[5] if len(sys.argv) > 5 else os.path.join(ROOT, "codes", "ref_h_n1152_m1024.txt")
+ctx = api.Context(code, "", device=0)
+ctx.set_tuning(precision=api.F32 if mode == "ms32" else api.F64, frames_per_cta=fpc, threads_per_cta=threads)
 dec = "BP" if mode == "bp" else "BP_MS"
-for i in range(4):
+for i in range(3):
     r = ctx.sim_point("AWGN", -4.5, seed=0, point=0, frame0=i * frames, nframes=frames, decoding=dec, iterations=50, early_term=(mode == "et"))
     print(r)
 print(ctx.stats())
