@@ -346,4 +346,158 @@ namespace b200
         }
         if (n_slots >= (1 << 23) || n_vslots >= (1 << 23) || n_pos >= (1 << 24)) throw std::runtime_error("layout too large");
     }
+    void SegLayout::build(const HostCode &code, int lanes_, int threads_, int isz_)
+    {
+        if (lanes_ < 1 || lanes_ > 8 || (lanes_ & (lanes_ - 1))) throw std::runtime_error("lanes per node must be 1, 2, 4 or 8");
+        if (threads_ < 32 || threads_ > 1024 || threads_ % 32) throw std::runtime_error("threads_per_cta must be a multiple of 32 <= 1024");
+        if (isz_ != 2 && isz_ != 4) throw std::runtime_error("index entries are 2 or 4 bytes");
+        if (code.nnz >= (1 << 22)) throw std::runtime_error("code too large (nnz >= 2^22)");
+        if (code.max_cn_degree > 64) throw std::runtime_error("check degree > 64 not supported");
+        if (code.max_vn_degree > 255) throw std::runtime_error("variable degree > 255 not supported");
+        if (code.min_cn_degree < 2) throw std::runtime_error("check nodes of degree < 2 are not supported (undefined in the reference)");
+        lanes = lanes_;
+        threads = threads_;
+        warps = threads / 32;
+        npw = 32 / lanes;
+        isz = isz_;
+
+        std::vector<int> cdeg(code.mc), vdeg(code.nc);
+        for (int i = 0; i < code.mc; ++i) cdeg[i] = code.row_ptr[i + 1] - code.row_ptr[i];
+        for (int i = 0; i < code.nc; ++i) vdeg[i] = code.col_ptr[i + 1] - code.col_ptr[i];
+
+        struct Seg { int deg, cnt, ntasks; uint32_t base, idx; size_t first; };
+        auto encode = [&](const std::vector<Group> &list, std::vector<Seg> &segs)
+        { // run-length encodes one warp's task list; a task with fewer than npw nodes gets its own segment
+            for (size_t i = 0; i < list.size();)
+            {
+                const int deg = list[i].degree, cnt = (int)list[i].nodes.size();
+                size_t n = 1;
+                while (i + n < list.size() && list[i + n].degree == deg && (int)list[i + n].nodes.size() == cnt && n < 65535) ++n;
+                segs.push_back({deg, cnt, (int)n, 0u, 0u, i});
+                i += n;
+            }
+        };
+        auto put = [&](std::vector<uint8_t> &buf, size_t off, uint32_t v)
+        {
+            if (isz == 2)
+            {
+                if (v > 0xFFFFu) throw std::runtime_error("index does not fit 16 bits");
+                buf[off] = (uint8_t)(v & 0xFF); buf[off + 1] = (uint8_t)(v >> 8);
+            }
+            else
+            {
+                buf[off] = (uint8_t)(v & 0xFF); buf[off + 1] = (uint8_t)((v >> 8) & 0xFF);
+                buf[off + 2] = (uint8_t)((v >> 16) & 0xFF); buf[off + 3] = (uint8_t)(v >> 24);
+            }
+        };
+        auto flatten = [&](const std::vector<std::vector<Seg>> &segs, int &max_segs, std::vector<uint32_t> &out)
+        {
+            max_segs = 1;
+            for (auto &l : segs) max_segs = std::max<int>(max_segs, (int)l.size() + 1); // + terminator
+            out.assign((size_t)4 * warps * max_segs, 0);
+            for (int w = 0; w < warps; ++w)
+                for (size_t s = 0; s < segs[w].size(); ++s)
+                {
+                    const Seg &g = segs[w][s];
+                    uint32_t *d = &out[4 * ((size_t)w * max_segs + s)];
+                    d[0] = (uint32_t)g.deg | ((uint32_t)g.cnt << 8) | ((uint32_t)g.ntasks << 16);
+                    d[1] = g.base;
+                    d[2] = g.idx;
+                }
+        };
+
+        // ---- variable side first: it defines the positions the check side gathers from -------------
+        auto vs = schedule(vdeg, npw, warps);
+        std::vector<std::vector<Seg>> vsegs(warps), csegs(warps);
+        var_pos.assign(code.nc, 0);
+        size_t pbase = 0, ibase = 0;
+        vn_path = vn_work = 0;
+        for (int w = 0; w < warps; ++w)
+        {
+            encode(vs[w], vsegs[w]);
+            long path = 0;
+            for (Seg &sg : vsegs[w])
+            {
+                ibase = (ibase + 15) & ~(size_t)15;
+                sg.base = (uint32_t)pbase;
+                sg.idx = (uint32_t)ibase;
+                for (int t = 0; t < sg.ntasks; ++t)
+                {
+                    const Group &g = vs[w][sg.first + t];
+                    for (int j = 0; j < (int)g.nodes.size(); ++j) var_pos[g.nodes[j]] = (uint32_t)(pbase + j);
+                    pbase += npw;
+                }
+                ibase += (size_t)sg.ntasks * npw * idx_stride(sg.deg, isz);
+                path += (long)sg.ntasks * sg.deg;
+            }
+            vn_path = std::max(vn_path, path);
+            vn_work += path;
+        }
+        n_pos = (int)pbase;
+        vn_idx.assign(ibase + 16, 0);
+
+        // ---- check side ------------------------------------------------------------------------
+        auto cs = schedule(cdeg, npw, warps);
+        edge_slot.assign(code.nnz, -1);
+        size_t sbase = 0;
+        ibase = 0;
+        cn_path = cn_work = 0;
+        for (int w = 0; w < warps; ++w)
+        {
+            encode(cs[w], csegs[w]);
+            long path = 0;
+            for (Seg &sg : csegs[w])
+            {
+                ibase = (ibase + 15) & ~(size_t)15;
+                sg.base = (uint32_t)sbase;
+                sg.idx = (uint32_t)ibase;
+                sbase += (size_t)sg.ntasks * sg.deg * npw;
+                ibase += (size_t)sg.ntasks * npw * idx_stride(sg.deg, isz);
+                path += (long)sg.ntasks * sg.deg;
+            }
+            cn_path = std::max(cn_path, path);
+            cn_work += path;
+        }
+        n_slots = (int)sbase;
+        cn_idx.assign(ibase + 16, 0);
+        if (n_slots >= (1 << 23) || n_pos >= (1 << 23)) throw std::runtime_error("layout too large");
+        if (isz == 2 && (n_slots > 65535 || n_pos > 65535)) throw std::runtime_error("code too large for 16-bit indices");
+        for (int w = 0; w < warps; ++w)
+            for (const Seg &sg : csegs[w])
+            {
+                const int stride = idx_stride(sg.deg, isz);
+                for (int t = 0; t < sg.ntasks; ++t)
+                {
+                    const Group &g = cs[w][sg.first + t];
+                    for (int j = 0; j < (int)g.nodes.size(); ++j)
+                    {
+                        const int row = g.nodes[j];
+                        for (int k = 0; k < sg.deg; ++k)
+                        {
+                            const int e = code.row_edge[code.row_ptr[row] + k];
+                            edge_slot[e] = (int)(sg.base + ((size_t)t * sg.deg + k) * npw + j);
+                            put(cn_idx, sg.idx + ((size_t)t * npw + j) * stride + (size_t)k * isz, var_pos[code.e_col[e]]);
+                        }
+                    }
+                }
+            }
+        for (int w = 0; w < warps; ++w)
+            for (const Seg &sg : vsegs[w])
+            {
+                const int stride = idx_stride(sg.deg, isz);
+                for (int t = 0; t < sg.ntasks; ++t)
+                {
+                    const Group &g = vs[w][sg.first + t];
+                    for (int j = 0; j < (int)g.nodes.size(); ++j)
+                    {
+                        const int col = g.nodes[j];
+                        for (int k = 0; k < sg.deg; ++k)
+                            put(vn_idx, sg.idx + ((size_t)t * npw + j) * stride + (size_t)k * isz,
+                                (uint32_t)edge_slot[code.col_edge[code.col_ptr[col] + k]]);
+                    }
+                }
+            }
+        flatten(csegs, cn_max_segs, cn_seg);
+        flatten(vsegs, vn_max_segs, vn_seg);
+    }
 } // namespace b200

@@ -89,4 +89,38 @@ namespace b200
 
         void build(const HostCode &code, int lanes, int threads);
     };
+    // Segment mapping (tile4.cuh).  Same vector-tile idea as TaskLayout — one thread owns ONE 16-byte
+    // vector of adjacent frame lanes of one node, `lanes` warp lanes per node, npw = 32/lanes nodes per
+    // warp task — but each warp's task list is stored run-length encoded as SEGMENTS (runs of tasks of
+    // one degree), and message slots, variable positions and index entries are numbered warp-major in
+    // list order.  Inside a segment a warp therefore only advances three pointers by compile-time
+    // strides: no per-task descriptor, no per-task dispatch.
+    //
+    //   message slot  = seg.slot_base + (t*deg + k)*npw + j      (task t of the segment, edge k, node j)
+    //   position      = seg.pos_base + t*npw + j                 (variable side)
+    //   index entries = seg.idx_base + (t*npw + j)*stride + k*isz bytes: the deg entries of a node are
+    //                   contiguous and padded to `stride` = idx_stride(deg, isz) bytes, so a thread
+    //                   fetches all (or 16 bytes' worth) of its node's indices with one vector load.
+    //                   Check side: entry = position gathered by edge k; variable side: entry = message
+    //                   slot of edge k (both in file order).
+    struct SegLayout
+    {
+        int lanes = 0, threads = 0, warps = 0, npw = 0, isz = 0; // isz = bytes per index entry (2 or 4)
+        int n_slots = 0, n_pos = 0;
+        int cn_max_segs = 0, vn_max_segs = 0;
+        // segment s of warp w at 4*(w*max_segs + s): {degree | nodes per task << 8 | tasks << 16,
+        //   slot base (check side) / position base (variable side), idx byte offset, 0}; first word 0 terminates
+        std::vector<uint32_t> cn_seg, vn_seg;
+        std::vector<uint8_t> cn_idx, vn_idx; // packed index entries (isz bytes each), 16-byte aligned per segment
+        std::vector<uint32_t> var_pos;       // [nc] variable id -> position
+        std::vector<int> edge_slot;          // [nnz] file-order edge -> message slot
+        long cn_path = 0, vn_path = 0, cn_work = 0, vn_work = 0; // longest warp list / total, in edge steps (diagnostics)
+
+        static int idx_stride(int deg, int isz)
+        {
+            const int b = deg * isz;
+            return b <= 2 ? 2 : b <= 4 ? 4 : b <= 8 ? 8 : (b + 15) & ~15;
+        }
+        void build(const HostCode &code, int lanes, int threads, int isz);
+    };
 } // namespace b200

@@ -12,6 +12,13 @@ G_FILE = os.path.join(ROOT, "codes", "ref_g_k128_n1152.txt")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def large_code_files():
+    """BASELINE configs 3/4 code files, generated deterministically on first use (codes/gen_codes.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "codes"))
+    import gen_codes
+    return gen_codes.ensure()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 

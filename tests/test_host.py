@@ -135,3 +135,21 @@ def test_python_wrapper_is_api_compatible():
     for m in ("encode", "decode", "simulate", "stop_simulation", "get_results", "rank", "syndrome"):
         assert callable(getattr(ldpc.LDPC, m))
     assert ldpc.LIB_PATH.endswith("libldpc.so")
+
+
+@pytest.mark.parametrize("which", ["bg1", "dvbs2"])
+def test_large_code_files_and_layout(built_lib, which):
+    """BASELINE configs 3/4: generated code files have the sizes SURVEY.md §8 lists and map onto a valid
+    global-residency layout (every edge gets its own message slot)."""
+    from conftest import large_code_files
+    from libldpc_b200 import api
+    c = api.Context(large_code_files()[which], "", device=-1)
+    want = {"bg1": (26112, 17664, 121344, 25344), "dvbs2": (64800, 32400, 226799, 64800)}[which]
+    assert (c.nc, c.mc, c.nnz, c.nct) == want
+    for precision in (0, 1):
+        c.set_tuning(precision=precision, residency=api.AUTO, frames_per_cta=0)
+        lay = c.layout()
+        es = lay["edge_slot"]
+        assert lay["residency"] == api.GLOBAL
+        assert len(np.unique(es)) == c.nnz and es.min() >= 0 and es.max() < lay["n_slots"]
+    c.close()
