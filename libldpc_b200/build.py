@@ -14,7 +14,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
 SOURCES = ["tile_ms_f64.cu", "tile_ms_f32.cu", "tile_bp_f64.cu", "tile_bp_f32.cu", "engine.cu", "code.cpp", "sim_driver.cpp", "shim.cpp"]
-HEADERS = ["engine.hpp", "code.hpp", "kernels.cuh", "tile3.cuh", "tile_launch.cuh", "bec_kernel.cuh", "../../include/ldpc_b200.h"]
+HEADERS = ["engine.hpp", "code.hpp", "kernels.cuh", "tile4.cuh", "tile_launch.cuh", "bec_kernel.cuh", "../../include/ldpc_b200.h"]
 OBJDIR = os.path.join(HERE, "build")
 
 

@@ -377,8 +377,11 @@ namespace b200
                 i += n;
             }
         };
+        // entries are stored pre-scaled: byte offset of the record (index * 16 * lanes) as uint32, or that offset
+        // in 16-byte units (index * lanes) as uint16
         auto put = [&](std::vector<uint8_t> &buf, size_t off, uint32_t v)
         {
+            v *= (uint32_t)(isz == 2 ? lanes : 16 * lanes);
             if (isz == 2)
             {
                 if (v > 0xFFFFu) throw std::runtime_error("index does not fit 16 bits");
@@ -401,7 +404,7 @@ namespace b200
                     const Seg &g = segs[w][s];
                     uint32_t *d = &out[4 * ((size_t)w * max_segs + s)];
                     d[0] = (uint32_t)g.deg | ((uint32_t)g.cnt << 8) | ((uint32_t)g.ntasks << 16);
-                    d[1] = g.base;
+                    d[1] = g.base * (uint32_t)(16 * lanes); // byte offset of the first record
                     d[2] = g.idx;
                 }
         };
@@ -461,7 +464,7 @@ namespace b200
         n_slots = (int)sbase;
         cn_idx.assign(ibase + 16, 0);
         if (n_slots >= (1 << 23) || n_pos >= (1 << 23)) throw std::runtime_error("layout too large");
-        if (isz == 2 && (n_slots > 65535 || n_pos > 65535)) throw std::runtime_error("code too large for 16-bit indices");
+        if (isz == 2 && ((size_t)n_slots * lanes > 65535 || (size_t)n_pos * lanes > 65535)) throw std::runtime_error("code too large for 16-bit indices");
         for (int w = 0; w < warps; ++w)
             for (const Seg &sg : csegs[w])
             {

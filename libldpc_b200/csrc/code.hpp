@@ -102,14 +102,16 @@ namespace b200
     //                   contiguous and padded to `stride` = idx_stride(deg, isz) bytes, so a thread
     //                   fetches all (or 16 bytes' worth) of its node's indices with one vector load.
     //                   Check side: entry = position gathered by edge k; variable side: entry = message
-    //                   slot of edge k (both in file order).
+    //                   slot of edge k (both in file order).  Entries are stored PRE-SCALED to the byte
+    //                   offset of the record they name (index * 16 * lanes; in 16-byte units when isz = 2).
     struct SegLayout
     {
         int lanes = 0, threads = 0, warps = 0, npw = 0, isz = 0; // isz = bytes per index entry (2 or 4)
         int n_slots = 0, n_pos = 0;
         int cn_max_segs = 0, vn_max_segs = 0;
         // segment s of warp w at 4*(w*max_segs + s): {degree | nodes per task << 8 | tasks << 16,
-        //   slot base (check side) / position base (variable side), idx byte offset, 0}; first word 0 terminates
+        //   byte offset of the first message slot (check side) / first position (variable side) record,
+        //   idx byte offset, 0}; first word 0 terminates
         std::vector<uint32_t> cn_seg, vn_seg;
         std::vector<uint8_t> cn_idx, vn_idx; // packed index entries (isz bytes each), 16-byte aligned per segment
         std::vector<uint32_t> var_pos;       // [nc] variable id -> position

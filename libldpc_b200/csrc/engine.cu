@@ -31,15 +31,15 @@ namespace b200
         }
     };
 
-    struct DeviceTaskLayout
+    struct DeviceSegLayout
     {
-        uint32_t *cn_task = nullptr, *vn_task = nullptr, *var_pos = nullptr;
-        void *cn_col = nullptr, *vn_slot = nullptr;
+        uint32_t *cn_seg = nullptr, *vn_seg = nullptr, *var_pos = nullptr;
+        uint8_t *cn_idx = nullptr, *vn_idx = nullptr;
         int32_t *tx_pos = nullptr, *punct_pos = nullptr, *short_pos = nullptr;
-        const TaskLayout *host = nullptr;
-        ~DeviceTaskLayout()
+        const SegLayout *host = nullptr;
+        ~DeviceSegLayout()
         {
-            cudaFree(cn_task); cudaFree(vn_task); cudaFree(var_pos); cudaFree(cn_col); cudaFree(vn_slot);
+            cudaFree(cn_seg); cudaFree(vn_seg); cudaFree(var_pos); cudaFree(cn_idx); cudaFree(vn_idx);
             cudaFree(tx_pos); cudaFree(punct_pos); cudaFree(short_pos);
         }
     };
@@ -75,23 +75,22 @@ namespace b200
             return b + 16;
         }
 
-        size_t task_smem_bytes(const TaskLayout &l, bool idx16)
+        size_t seg_smem_bytes(const SegLayout &l)
         {
-            const size_t idx = idx16 ? 2 : 4, rs = 16 * (size_t)l.lanes;
+            const size_t rs = 16 * (size_t)l.lanes;
             size_t b = rs * ((size_t)l.n_slots + 2 * (size_t)l.n_pos);
-            b += 8 * ((size_t)l.cn_rounds + l.vn_rounds) * l.warps;
-            b += (idx * (size_t)l.n_slots + 15) & ~(size_t)15;
-            b += idx * (size_t)l.n_vslots;
+            b += 16 * ((size_t)l.cn_max_segs + l.vn_max_segs) * l.warps;
+            b += l.cn_idx.size() + l.vn_idx.size(); // both multiples of 16
             return b + 16;
         }
 
-        int family_occupancy(int precision, int alg, bool smem, int lanes, int threads, size_t smem_bytes)
+        int family_occupancy(int precision, int alg, bool smem, bool idx16, int lanes, int threads, size_t smem_bytes)
         {
             if (precision == LDPC_B200_F32)
-                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, lanes, threads, smem_bytes)
-                                     : tile_family_occupancy<float, ALG_BP>(smem, lanes, threads, smem_bytes);
-            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, lanes, threads, smem_bytes)
-                                 : tile_family_occupancy<double, ALG_BP>(smem, lanes, threads, smem_bytes);
+                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, idx16, lanes, threads, smem_bytes)
+                                     : tile_family_occupancy<float, ALG_BP>(smem, idx16, lanes, threads, smem_bytes);
+            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, idx16, lanes, threads, smem_bytes)
+                                 : tile_family_occupancy<double, ALG_BP>(smem, idx16, lanes, threads, smem_bytes);
         }
     } // namespace
 
@@ -115,7 +114,7 @@ namespace b200
         if (!cuda_ready_) return;
         cudaSetDevice(device);
         dev_layouts_.clear();
-        dev_task_layouts_.clear();
+        dev_seg_layouts_.clear();
         cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
         if (ev0_) cudaEventDestroy((cudaEvent_t)ev0_);
         if (ev1_) cudaEventDestroy((cudaEvent_t)ev1_);
@@ -157,15 +156,15 @@ namespace b200
         cuda_ready_ = true;
     }
 
-    const TaskLayout &Engine::get_task_layout(int lanes, int threads)
+    const SegLayout &Engine::get_seg_layout(int lanes, int threads, int isz)
     {
-        auto key = std::make_pair(lanes, threads);
-        auto it = task_layouts_.find(key);
-        if (it == task_layouts_.end())
+        auto key = std::make_tuple(lanes, threads, isz);
+        auto it = seg_layouts_.find(key);
+        if (it == seg_layouts_.end())
         {
-            auto l = std::make_unique<TaskLayout>();
-            l->build(H, lanes, threads);
-            it = task_layouts_.emplace(key, std::move(l)).first;
+            auto l = std::make_unique<SegLayout>();
+            l->build(H, lanes, threads, isz);
+            it = seg_layouts_.emplace(key, std::move(l)).first;
         }
         return *it->second;
     }
@@ -174,7 +173,7 @@ namespace b200
     // vector).  Shared-memory residency is used whenever the code fits: the widest tile that fits
     // with the default thread count wins (it shares every index load / address computation between
     // the most frames); otherwise messages live in global memory (L2 / HBM).
-    const TaskLayout &Engine::layout_for(int precision, int alg, int *residency, size_t *smem_bytes)
+    const SegLayout &Engine::layout_for(int precision, int alg, int *residency, size_t *smem_bytes)
     {
         const int vec = precision == LDPC_B200_F32 ? 4 : 2;
         const int max_threads = alg == ALG_MS ? 1024 : 512;
@@ -193,21 +192,25 @@ namespace b200
             for (int lanes = 8; lanes >= 1; lanes >>= 1)
             {
                 if (want_lanes && lanes != want_lanes) continue;
-                const TaskLayout &l = get_task_layout(lanes, threads);
-                if (std::max({l.n_slots, l.n_vslots, l.n_pos}) > 65535) continue;
-                const size_t need = task_smem_bytes(l, true);
-                if (need <= limit)
+                // 32-bit index entries (ready-made byte offsets) when the tables still fit, else 16-bit
+                for (int isz = 4; isz >= 2; isz -= 2)
                 {
-                    *residency = LDPC_B200_SMEM;
-                    *smem_bytes = need;
-                    return l;
+                    if (isz == 2 && (size_t)lanes * (size_t)std::max(H.nnz, H.nc) > 60000) continue;
+                    const SegLayout &l = get_seg_layout(lanes, threads, isz);
+                    const size_t need = seg_smem_bytes(l);
+                    if (need <= limit)
+                    {
+                        *residency = LDPC_B200_SMEM;
+                        *smem_bytes = need;
+                        return l;
+                    }
                 }
             }
             if (tuning.residency == LDPC_B200_SMEM) throw std::runtime_error("code does not fit shared-memory residency with this tuning");
         }
         *residency = LDPC_B200_GLOBAL;
         *smem_bytes = 0;
-        return get_task_layout(want_lanes ? want_lanes : 2, threads);
+        return get_seg_layout(want_lanes ? want_lanes : 1, threads, 4);
     }
 
     Engine::Config Engine::choose(int precision, int alg, uint64_t n_frames)
@@ -215,18 +218,18 @@ namespace b200
         Config c{};
         c.precision = precision;
         c.alg = alg;
-        const TaskLayout &l = layout_for(precision, alg, &c.residency, &c.smem_bytes);
+        const SegLayout &l = layout_for(precision, alg, &c.residency, &c.smem_bytes);
         c.lanes = l.lanes;
         c.fpc = l.lanes * (precision == LDPC_B200_F32 ? 4 : 2);
         c.threads = l.threads;
-        c.idx16 = (c.residency == LDPC_B200_SMEM); // shared-memory residency: 16-bit tables; global: 32-bit
+        c.idx16 = (l.isz == 2);
         int ctas = tuning.ctas;
         if (ctas <= 0)
         { // persistent grid: every SM gets as many CTAs as the runtime keeps resident
-            auto key = std::make_tuple(precision, alg, c.residency, c.lanes, c.threads, c.smem_bytes);
+            auto key = std::make_tuple(precision, alg, c.residency * 2 + (c.idx16 ? 1 : 0), c.lanes, c.threads, c.smem_bytes);
             auto it = occupancy_.find(key);
             if (it == occupancy_.end())
-                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.idx16, c.lanes, c.threads, c.smem_bytes)).first;
+                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.idx16, c.lanes, c.threads, c.smem_bytes)).first;
             if (it->second < 1) throw std::runtime_error("tile kernel does not fit on this device with the current tuning");
             ctas = sm_count_ * it->second;
         }
@@ -236,27 +239,19 @@ namespace b200
         return c;
     }
 
-    DeviceTaskLayout &Engine::device_task_layout(int lanes, int threads, bool idx16)
+    DeviceSegLayout &Engine::device_seg_layout(int lanes, int threads, bool idx16)
     {
         auto key = std::make_tuple(lanes, threads, idx16);
-        auto it = dev_task_layouts_.find(key);
-        if (it != dev_task_layouts_.end()) return *it->second;
-        const TaskLayout &l = get_task_layout(lanes, threads);
-        auto d = std::make_unique<DeviceTaskLayout>();
+        auto it = dev_seg_layouts_.find(key);
+        if (it != dev_seg_layouts_.end()) return *it->second;
+        const SegLayout &l = get_seg_layout(lanes, threads, idx16 ? 2 : 4);
+        auto d = std::make_unique<DeviceSegLayout>();
         d->host = &l;
-        d->cn_task = upload(l.cn_task);
-        d->vn_task = upload(l.vn_task);
+        d->cn_seg = upload(l.cn_seg);
+        d->vn_seg = upload(l.vn_seg);
         d->var_pos = upload(l.var_pos);
-        if (idx16)
-        {
-            d->cn_col = upload_idx<uint16_t>(l.cn_col);
-            d->vn_slot = upload_idx<uint16_t>(l.vn_slot);
-        }
-        else
-        {
-            d->cn_col = upload_idx<uint32_t>(l.cn_col);
-            d->vn_slot = upload_idx<uint32_t>(l.vn_slot);
-        }
+        d->cn_idx = upload(l.cn_idx);
+        d->vn_idx = upload(l.vn_idx);
         std::vector<int32_t> tx, pu, sh;
         for (int v : H.bit_pos) tx.push_back((int32_t)l.var_pos[v]);
         for (int v : H.puncture) if (v >= 0 && v < H.nc) pu.push_back((int32_t)l.var_pos[v]);
@@ -264,7 +259,7 @@ namespace b200
         d->tx_pos = upload(tx);
         d->punct_pos = upload(pu);
         d->short_pos = upload(sh);
-        return *dev_task_layouts_.emplace(key, std::move(d)).first->second;
+        return *dev_seg_layouts_.emplace(key, std::move(d)).first->second;
     }
 
     const TileLayout &Engine::get_layout(int fpc, int threads)
@@ -340,14 +335,16 @@ namespace b200
 
         const int alg = minsum ? ALG_MS : ALG_BP;
         const Config c = choose(tuning.precision, alg, n_frames);
-        DeviceTaskLayout &dl = device_task_layout(c.lanes, c.threads, c.idx16);
-        const TaskLayout &l = *dl.host;
+        DeviceSegLayout &dl = device_seg_layout(c.lanes, c.threads, c.idx16);
+        const SegLayout &l = *dl.host;
 
-        K3Params kp{};
-        kp.cn_task = dl.cn_task; kp.vn_task = dl.vn_task;
-        kp.cn_col = dl.cn_col; kp.vn_slot = dl.vn_slot; kp.var_pos = dl.var_pos;
+        K4Params kp{};
+        kp.cn_seg = dl.cn_seg; kp.vn_seg = dl.vn_seg;
+        kp.cn_idx = dl.cn_idx; kp.vn_idx = dl.vn_idx; kp.var_pos = dl.var_pos;
+        kp.cn_idx_bytes = (uint32_t)l.cn_idx.size(); kp.vn_idx_bytes = (uint32_t)l.vn_idx.size();
+        kp.cn_max_segs = l.cn_max_segs; kp.vn_max_segs = l.vn_max_segs;
         kp.tx_pos = dl.tx_pos; kp.punct_pos = dl.punct_pos; kp.short_pos = dl.short_pos;
-        kp.cn_rounds = l.cn_rounds; kp.vn_rounds = l.vn_rounds; kp.n_slots = l.n_slots; kp.n_vslots = l.n_vslots; kp.n_pos = l.n_pos;
+        kp.n_slots = l.n_slots; kp.n_pos = l.n_pos;
         kp.nc = H.nc; kp.nct = H.nct();
         kp.n_punct = 0; kp.n_short = 0;
         for (int v : H.puncture) if (v >= 0 && v < H.nc) ++kp.n_punct;
@@ -379,13 +376,13 @@ namespace b200
         const bool smem = c.residency == LDPC_B200_SMEM;
         if (c.precision == LDPC_B200_F32)
         {
-            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<float, ALG_BP>(kp, smem, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<float, ALG_BP>(kp, smem, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         else
         {
-            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<double, ALG_BP>(kp, smem, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<double, ALG_BP>(kp, smem, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         stats.launches += 1;
         stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;

@@ -15,7 +15,7 @@
 namespace b200
 {
     struct DeviceLayout;     // device-resident TileLayout (engine.cu; erasure decoder)
-    struct DeviceTaskLayout; // device-resident TaskLayout (engine.cu; tile3 kernel)
+    struct DeviceSegLayout;  // device-resident SegLayout (engine.cu; tile4 kernel)
 
     struct FrameSource
     {
@@ -50,7 +50,7 @@ namespace b200
         ldpc_b200_stats stats{};
 
         // Chooses / builds the layout for (precision, algorithm) under the current tuning (host only).
-        const TaskLayout &layout_for(int precision, int alg, int *residency, size_t *smem_bytes);
+        const SegLayout &layout_for(int precision, int alg, int *residency, size_t *smem_bytes);
 
         // Launches the tile kernel over n_frames frames on `stream` (0 = engine stream). Asynchronous.
         void launch(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
@@ -76,8 +76,8 @@ namespace b200
             bool idx16;
         };
         Config choose(int precision, int alg, uint64_t n_frames);
-        const TaskLayout &get_task_layout(int lanes, int threads);
-        DeviceTaskLayout &device_task_layout(int lanes, int threads, bool idx16);
+        const SegLayout &get_seg_layout(int lanes, int threads, int isz);
+        DeviceSegLayout &device_seg_layout(int lanes, int threads, bool idx16);
         const TileLayout &get_layout(int fpc, int threads);
         void launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
         DeviceLayout &device_layout(int fpc, int threads, bool idx16);
@@ -91,8 +91,8 @@ namespace b200
         void *ev0_ = nullptr, *ev1_ = nullptr;
         std::map<std::pair<int, int>, std::unique_ptr<TileLayout>> layouts_;
         std::map<std::tuple<int, int, bool>, std::unique_ptr<DeviceLayout>> dev_layouts_;
-        std::map<std::pair<int, int>, std::unique_ptr<TaskLayout>> task_layouts_;
-        std::map<std::tuple<int, int, bool>, std::unique_ptr<DeviceTaskLayout>> dev_task_layouts_;
+        std::map<std::tuple<int, int, int>, std::unique_ptr<SegLayout>> seg_layouts_;
+        std::map<std::tuple<int, int, bool>, std::unique_ptr<DeviceSegLayout>> dev_seg_layouts_;
         std::map<std::tuple<int, int, int, int, int, size_t>, int> occupancy_;
         int32_t *d_bit_pos_ = nullptr, *d_punct_ = nullptr, *d_short_ = nullptr;
         unsigned long long *d_counters_ = nullptr;

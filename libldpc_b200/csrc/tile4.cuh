@@ -1,0 +1,811 @@
+// sm_100a decode kernel, vector-tile mapping over run-length SEGMENTS: Philox channel -> flooding
+// min-sum / box-plus decode -> hard decision + error accounting, fused into ONE persistent kernel.
+//
+// Mapping.  A CTA keeps FPC = LANES * VEC frames in flight (VEC = 16/sizeof(T): 2 doubles or 4
+// floats).  Every per-frame array is stored as 16-byte vectors of VEC adjacent frame lanes,
+// [index][LANES] vectors per index ("records" of RS = 16*LANES bytes).  One thread owns ONE vector of
+// one node: warp lane l serves node l / LANES of the warp's current task and vector l % LANES, so a warp
+// walking the NPW = 32/LANES nodes of a task moves 512 contiguous bytes per access (conflict free in
+// shared memory, whole sectors in HBM/L2) with one LDS.128/STS.128 (LDG/STG.128) per VEC messages, and
+// every index load / address computation is shared by VEC frames.
+//
+// Work list (SegLayout, code.cpp).  Nodes of equal degree are packed NPW at a time into warp tasks and
+// the tasks of a warp are stored run-length encoded as segments; message slots, variable positions and
+// index entries are numbered in that order.  A warp therefore decodes one 16-byte descriptor per
+// SEGMENT, dispatches once on the (warp-uniform) degree to a fully unrolled body and then only advances
+// two pointers by compile-time strides per task.  A node's index entries are contiguous, pre-scaled to
+// byte offsets, and fetched with one vector load.
+//
+// State per frame lane: c2v per edge slot, posterior `out` and channel LLR per variable position.
+// v2c is never stored — it is recomputed as out - c2v, which is exactly the value the reference
+// stores (src/decoding/decoder.cpp:60-63), so results stay bit-identical while one of the
+// reference's two message arrays disappears.  A fresh frame starts with c2v = +0 and out = LLRin,
+// which makes its first check pass read LLRin exactly (x - (+0) == x for every x, -0 included),
+// i.e. decoder.cpp:16-19 without a special case.
+//
+// A frame lane that finishes (syndrome clear after an iteration, or iteration limit) is retired —
+// its bit errors are counted once, from the final posterior (src/sim/ldpcsim.cpp:184-190) — and
+// refilled at once with the next frame (LLRs regenerated from the counter-based Philox stream), so
+// early termination never leaves lanes idle waiting for the slowest frame of a batch.
+#pragma once
+#include <utility>
+
+#include "kernels.cuh"
+
+namespace b200
+{
+    // ------------------------------------------------------------------------------------------
+    // 16-byte vectors of frame lanes
+    // ------------------------------------------------------------------------------------------
+    template <typename T> struct Vec;
+    template <> struct __align__(16) Vec<double> { static constexpr int N = 2; double e[2]; };
+    template <> struct __align__(16) Vec<float> { static constexpr int N = 4; float e[4]; };
+
+    template <bool SMEM, typename T, int OFF> struct VAcc;
+    template <int OFF> struct VAcc<true, double, OFF>
+    {
+        static __device__ __forceinline__ Vec<double> ld(uint32_t a)
+        {
+            Vec<double> v;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.e[0]), "=d"(v.e[1]) : "r"(a), "n"(OFF));
+            return v;
+        }
+        static __device__ __forceinline__ void st(uint32_t a, const Vec<double> &v)
+        {
+            asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v.e[0]), "d"(v.e[1]) : "memory");
+        }
+    };
+    template <int OFF> struct VAcc<true, float, OFF>
+    {
+        static __device__ __forceinline__ Vec<float> ld(uint32_t a)
+        {
+            Vec<float> v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.e[0]), "=f"(v.e[1]), "=f"(v.e[2]), "=f"(v.e[3]) : "r"(a), "n"(OFF));
+            return v;
+        }
+        static __device__ __forceinline__ void st(uint32_t a, const Vec<float> &v)
+        {
+            asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(v.e[0]), "f"(v.e[1]), "f"(v.e[2]), "f"(v.e[3]) : "memory");
+        }
+    };
+    template <typename T, int OFF> struct VAcc<false, T, OFF>
+    {
+        static __device__ __forceinline__ Vec<T> ld(const unsigned char *a) { return *reinterpret_cast<const Vec<T> *>(a + OFF); }
+        static __device__ __forceinline__ void st(unsigned char *a, const Vec<T> &v) { *reinterpret_cast<Vec<T> *>(a + OFF) = v; }
+    };
+
+    // read-only words (tables): 4 / 8 / 16 bytes
+    template <bool SMEM, int OFF> struct WAcc;
+    template <int OFF> struct WAcc<true, OFF>
+    {
+        static __device__ __forceinline__ uint32_t ld1(uint32_t a) { return lds_u32<OFF>(a); }
+        static __device__ __forceinline__ uint2 ld2(uint32_t a)
+        {
+            uint2 v;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(a), "n"(OFF));
+            return v;
+        }
+        static __device__ __forceinline__ uint4 ld4(uint32_t a)
+        {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(OFF));
+            return v;
+        }
+    };
+    template <int OFF> struct WAcc<false, OFF>
+    {
+        static __device__ __forceinline__ uint32_t ld1(const unsigned char *a) { return __ldg(reinterpret_cast<const uint32_t *>(a + OFF)); }
+        static __device__ __forceinline__ uint2 ld2(const unsigned char *a) { return __ldg(reinterpret_cast<const uint2 *>(a + OFF)); }
+        static __device__ __forceinline__ uint4 ld4(const unsigned char *a) { return __ldg(reinterpret_cast<const uint4 *>(a + OFF)); }
+    };
+
+    // compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N-1>)
+    template <typename F, int... K>
+    __device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, K...>) { (f(std::integral_constant<int, K>{}), ...); }
+    template <int N, typename F>
+    __device__ __forceinline__ void static_for(F &&f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
+
+    // bytes between the index blocks of consecutive nodes (SegLayout::idx_stride)
+    __host__ __device__ constexpr int idx_stride_of(int deg, int isz)
+    {
+        const int b = deg * isz;
+        return b <= 2 ? 2 : b <= 4 ? 4 : b <= 8 ? 8 : (b + 15) & ~15;
+    }
+
+    // All D index entries of one node -> byte offsets.  Entries are uint32 byte offsets or uint16 offsets in
+    // 16-byte units (shared-memory residency of codes whose tables would not fit otherwise).
+    template <bool SMEM, typename IdxT, int D> struct IdxLoad
+    {
+        typedef typename PtrOf<SMEM>::type P;
+        static constexpr int ISZ = (int)sizeof(IdxT), STRIDE = idx_stride_of(D, ISZ), NW = (STRIDE + 3) / 4;
+        static __device__ __forceinline__ void load(P p, uint32_t (&e)[D])
+        {
+            uint32_t w[NW];
+            if constexpr (STRIDE == 2) w[0] = Acc<SMEM, uint16_t, 0>::ld(p);
+            else if constexpr (STRIDE == 4) w[0] = WAcc<SMEM, 0>::ld1(p);
+            else if constexpr (STRIDE == 8) { const uint2 t = WAcc<SMEM, 0>::ld2(p); w[0] = t.x; w[1] = t.y; }
+            else
+                static_for<STRIDE / 16>([&](auto q) {
+                    const uint4 t = WAcc<SMEM, q.value * 16>::ld4(p);
+                    w[4 * q.value] = t.x; w[4 * q.value + 1] = t.y; w[4 * q.value + 2] = t.z; w[4 * q.value + 3] = t.w;
+                });
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+            {
+                if constexpr (ISZ == 4) e[k] = w[k];
+                else e[k] = ((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xFFFFu)) << 4;
+            }
+        }
+    };
+    template <bool SMEM, typename IdxT> struct IdxOne
+    { // entry k of a node -> byte offset (generic-degree paths)
+        typedef typename PtrOf<SMEM>::type P;
+        static __device__ __forceinline__ uint32_t ld(P p, int k)
+        {
+            if constexpr (sizeof(IdxT) == 4) return Acc<SMEM, uint32_t, 0>::ld(p + 4 * k);
+            else return (uint32_t)Acc<SMEM, uint16_t, 0>::ld(p + 2 * k) << 4;
+        }
+    };
+
+    struct K4Params
+    {
+        // code tables (device global memory), SegLayout of code.hpp
+        const uint32_t *cn_seg, *vn_seg; // [warps][max_segs][4]
+        const unsigned char *cn_idx, *vn_idx;
+        uint32_t cn_idx_bytes, vn_idx_bytes; // multiples of 16
+        int cn_max_segs, vn_max_segs;
+        const uint32_t *var_pos;                       // [nc] variable id -> position
+        const int32_t *tx_pos, *punct_pos, *short_pos; // positions of transmitted (ascending id) / punctured / shortened variables
+        int n_slots, n_pos;
+        int nc, nct, n_punct, n_short;
+        // decoder
+        int max_iter, early_term;
+        // frame source
+        int kind;
+        const double *llr_in; // SRC_LLR: [n_frames][nc]
+        double sigma, sigma2, delta;
+        uint32_t thr;
+        uint64_t seed;
+        uint32_t point;
+        uint64_t frame0, n_frames;
+        // sinks (indexed by frame - frame0); any may be null
+        double *llr_out;
+        uint8_t *hard_out;
+        int32_t *iters_out;
+        unsigned long long *counters; // [5] fec, bec, frames, sum(ret iters), sum(executed iterations)
+        // global-memory residency: per-CTA state block
+        unsigned char *state;
+        size_t state_stride;
+    };
+
+    // raw value of smaller magnitude (min-sum keeps raw values; magnitude and sign are fixed at the store)
+    template <typename T> __device__ __forceinline__ T min_mag(T a, T b) { return (Num<T>::abs(b) < Num<T>::abs(a)) ? b : a; }
+    // |mag| with the sign bit of word s (bit 31)
+    __device__ __forceinline__ double mag_sign(double m, uint32_t s)
+    {
+        return __hiloint2double((int)(((uint32_t)__double2hiint(m) & 0x7FFFFFFFu) | (s & 0x80000000u)), __double2loint(m));
+    }
+    __device__ __forceinline__ float mag_sign(float m, uint32_t s) { return __uint_as_float((__float_as_uint(m) & 0x7FFFFFFFu) | (s & 0x80000000u)); }
+
+    // ------------------------------------------------------------------------------------------
+    // check-node update of one node, degree D (compile time).
+    //   out_sub : &out[0][sub]            gathered record at + index entry
+    //   c2v0    : &c2v[first slot][lane]  slot k at + k*512 (slots of a node are NPW records apart)
+    //   ip      : the node's index block
+    // Returns, per frame lane of the vector (bit e), the parity of the hard decisions of the check's
+    // variables (= the syndrome bit of the previous iteration's output, decoder.h:47-64), which comes for
+    // free with the gather.
+    // ------------------------------------------------------------------------------------------
+    template <typename T, typename IdxT, bool SMEM, int LANES, int ALG, int D>
+    struct Cn4
+    {
+        typedef typename PtrOf<SMEM>::type P;
+        typedef Vec<T> V;
+        static constexpr int VEC = V::N, CS = 512;
+
+        static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, P ip)
+        {
+            uint32_t eo[D];
+            IdxLoad<SMEM, IdxT, D>::load(ip, eo);
+            bool par[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) par[e] = false;
+
+            if constexpr (ALG == ALG_MS && D > 4)
+            {
+                // one pass: running smallest / second smallest raw values, position of the smallest, sign bits
+                T m1[VEC], m2[VEC];
+                uint32_t arg[VEC], sm[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { m1[e] = Num<T>::inf(); m2[e] = Num<T>::inf(); arg[e] = 0; sm[e] = 0; }
+                static_for<D>([&](auto k) {
+                    const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[k.value]);
+                    const V c = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e)
+                    {
+                        const T v = o.e[e] - c.e[e]; // == the reference's stored v2c (decoder.cpp:62); LLRin on a fresh frame (:18)
+                        par[e] ^= (o.e[e] <= T(0));
+                        sm[e] |= (Num<T>::hi(v) >> 31) << k.value;
+                        const bool lt1 = Num<T>::abs(v) < Num<T>::abs(m1[e]), lt2 = Num<T>::abs(v) < Num<T>::abs(m2[e]);
+                        m2[e] = lt1 ? m1[e] : (lt2 ? v : m2[e]);
+                        arg[e] = lt1 ? (uint32_t)k.value : arg[e];
+                        m1[e] = lt1 ? v : m1[e];
+                    }
+                });
+                // sign of message k = total sign ^ own sign: bit k of sm
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) sm[e] ^= (__popc(sm[e]) & 1u) ? ((D >= 32) ? 0xFFFFFFFFu : ((1u << D) - 1u)) : 0u;
+                static_for<D>([&](auto k) {
+                    V r;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) r.e[e] = mag_sign((arg[e] == (uint32_t)k.value) ? m2[e] : m1[e], sm[e] << (31 - k.value));
+                    VAcc<SMEM, T, k.value * CS>::st(c2v0, r);
+                });
+            }
+            else
+            {
+                V v[D], r[D];
+                static_for<D>([&](auto k) {
+                    const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[k.value]);
+                    const V c = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e)
+                    {
+                        v[k.value].e[e] = o.e[e] - c.e[e];
+                        par[e] ^= (o.e[e] <= T(0));
+                    }
+                });
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                {
+                    if constexpr (ALG == ALG_MS)
+                    {
+                        // min-sum: f = sign*sign*min (decoder.h:17-20) through the forward/backward recursion of
+                        // decoder.cpp:30-44.  Magnitude: exact minimum over the other edges; sign: XOR of sign BITS
+                        // (std::signbit semantics, -0.0 is negative).
+                        if constexpr (D == 2) { r[0].e[e] = v[1].e[e]; r[1].e[e] = v[0].e[e]; }
+                        else
+                        {
+                            uint32_t sx = 0;
+#pragma unroll
+                            for (int k = 0; k < D; ++k) sx ^= Num<T>::hi(v[k].e[e]);
+                            T m[D];
+                            if constexpr (D == 3)
+                            {
+                                m[0] = min_mag(v[1].e[e], v[2].e[e]); m[1] = min_mag(v[0].e[e], v[2].e[e]); m[2] = min_mag(v[0].e[e], v[1].e[e]);
+                            }
+                            else
+                            {
+                                const T m01 = min_mag(v[0].e[e], v[1].e[e]), m23 = min_mag(v[2].e[e], v[3].e[e]);
+                                m[0] = min_mag(v[1].e[e], m23); m[1] = min_mag(v[0].e[e], m23);
+                                m[2] = min_mag(m01, v[3].e[e]); m[3] = min_mag(m01, v[2].e[e]);
+                            }
+#pragma unroll
+                            for (int k = 0; k < D; ++k) r[k].e[e] = mag_sign(m[k], sx ^ Num<T>::hi(v[k].e[e]));
+                        }
+                    }
+                    else
+                    {
+                        // sum-product: the reference's forward/backward box-plus recursion, file order
+                        T F[D];
+                        F[0] = v[0].e[e];
+#pragma unroll
+                        for (int k = 1; k < D; ++k) F[k] = boxplus(F[k - 1], v[k].e[e]);
+                        T B = v[D - 1].e[e];
+                        r[D - 1].e[e] = F[D - 2];
+#pragma unroll
+                        for (int k = D - 2; k >= 1; --k) { r[k].e[e] = boxplus(F[k - 1], B); B = boxplus(B, v[k].e[e]); }
+                        r[0].e[e] = B;
+                    }
+                }
+                static_for<D>([&](auto k) { VAcc<SMEM, T, k.value * CS>::st(c2v0, r[k.value]); });
+            }
+            uint32_t bits = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) bits |= par[e] ? (1u << e) : 0u;
+            return bits;
+        }
+    };
+
+    // arbitrary degree (<= 64): running min1/min2 + sign mask for min-sum, parked forward values for box-plus
+    template <typename T, typename IdxT, bool SMEM, int LANES, int ALG>
+    __device__ __noinline__ uint32_t cn4_any(typename PtrOf<SMEM>::type out_sub, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type ip, int deg)
+    {
+        typedef Vec<T> V;
+        constexpr int VEC = V::N, CS = 512;
+        uint32_t par = 0;
+        if (ALG == ALG_MS)
+        {
+            T m1[VEC], m2[VEC];
+            int arg[VEC];
+            unsigned long long smask[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { m1[e] = Num<T>::inf(); m2[e] = Num<T>::inf(); arg[e] = 0; smask[e] = 0; }
+            for (int k = 0; k < deg; ++k)
+            {
+                const V o = VAcc<SMEM, T, 0>::ld(out_sub + IdxOne<SMEM, IdxT>::ld(ip, k));
+                const V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                {
+                    const T v = o.e[e] - c.e[e];
+                    par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u;
+                    smask[e] |= (unsigned long long)(Num<T>::hi(v) >> 31) << k;
+                    const bool lt1 = Num<T>::abs(v) < Num<T>::abs(m1[e]), lt2 = Num<T>::abs(v) < Num<T>::abs(m2[e]);
+                    m2[e] = lt1 ? m1[e] : (lt2 ? v : m2[e]);
+                    arg[e] = lt1 ? k : arg[e];
+                    m1[e] = lt1 ? v : m1[e];
+                }
+            }
+            uint32_t tot[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) tot[e] = (uint32_t)__popcll(smask[e]) & 1u;
+            for (int k = 0; k < deg; ++k)
+            {
+                V r;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                {
+                    const uint32_t s = tot[e] ^ (uint32_t)((smask[e] >> k) & 1ull);
+                    r.e[e] = mag_sign((k == arg[e]) ? m2[e] : m1[e], s << 31);
+                }
+                VAcc<SMEM, T, 0>::st(c2v0 + k * CS, r);
+            }
+        }
+        else
+        {
+            // box-plus forward/backward with the forward values parked in the output slots: slot k first
+            // receives F[k-1]; the backward sweep turns it into f(F[k-1], B[k+1]) (decoder.cpp:33-44).
+            // v[k] is needed again by the backward sweep (out and the old c2v are gone by then).
+            V Fp, B, vk;
+            V v[64];
+            {
+                const V o = VAcc<SMEM, T, 0>::ld(out_sub + IdxOne<SMEM, IdxT>::ld(ip, 0));
+                const V c = VAcc<SMEM, T, 0>::ld(c2v0);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { Fp.e[e] = o.e[e] - c.e[e]; par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u; }
+            }
+            v[0] = Fp;
+            for (int k = 1; k < deg; ++k)
+            {
+                const V o = VAcc<SMEM, T, 0>::ld(out_sub + IdxOne<SMEM, IdxT>::ld(ip, k));
+                const V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { vk.e[e] = o.e[e] - c.e[e]; par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u; }
+                v[k] = vk;
+                VAcc<SMEM, T, 0>::st(c2v0 + k * CS, Fp); // F[k-1] (slot deg-1 thereby gets its final value)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) Fp.e[e] = boxplus(Fp.e[e], vk.e[e]);
+            }
+            B = v[deg - 1];
+            for (int k = deg - 2; k >= 1; --k)
+            {
+                const V f = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                V r;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { r.e[e] = boxplus(f.e[e], B.e[e]); B.e[e] = boxplus(B.e[e], v[k].e[e]); }
+                VAcc<SMEM, T, 0>::st(c2v0 + k * CS, r);
+            }
+            VAcc<SMEM, T, 0>::st(c2v0, B);
+        }
+        return par;
+    }
+
+    // variable node: posterior = LLRin + sum of incoming c2v, strictly in file order (decoder.cpp:50-56)
+    template <typename T, typename IdxT, bool SMEM, int D>
+    struct Vn4
+    {
+        typedef typename PtrOf<SMEM>::type P;
+        typedef Vec<T> V;
+        static __device__ __forceinline__ V run(P c2v_sub, P ip, V acc)
+        {
+            uint32_t eo[D];
+            IdxLoad<SMEM, IdxT, D>::load(ip, eo);
+            V m[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) m[k] = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[k]);
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+            {
+#pragma unroll
+                for (int e = 0; e < V::N; ++e) acc.e[e] += m[k].e[e];
+            }
+            return acc;
+        }
+    };
+    // arbitrary degree: chunks of 4 entries (the index block of a node of degree > 8/sizeof(IdxT) is padded to 16 bytes)
+    template <typename T, typename IdxT, bool SMEM>
+    __device__ __forceinline__ Vec<T> vn4_any(typename PtrOf<SMEM>::type c2v_sub, typename PtrOf<SMEM>::type ip, int deg, Vec<T> acc)
+    {
+        typedef Vec<T> V;
+        int k = 0;
+        for (; k + 4 <= deg; k += 4)
+        {
+            uint32_t eo[4];
+            IdxLoad<SMEM, IdxT, 4>::load(ip + k * (int)sizeof(IdxT), eo);
+            const V m0 = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[0]), m1 = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[1]);
+            const V m2 = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[2]), m3 = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[3]);
+#pragma unroll
+            for (int e = 0; e < V::N; ++e) { acc.e[e] += m0.e[e]; acc.e[e] += m1.e[e]; acc.e[e] += m2.e[e]; acc.e[e] += m3.e[e]; }
+        }
+        for (; k < deg; ++k)
+        {
+            const V m = VAcc<SMEM, T, 0>::ld(c2v_sub + IdxOne<SMEM, IdxT>::ld(ip, k));
+#pragma unroll
+            for (int e = 0; e < V::N; ++e) acc.e[e] += m.e[e];
+        }
+        return acc;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // the persistent kernel
+    // ------------------------------------------------------------------------------------------
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES>
+    __global__ void __launch_bounds__(ALG == ALG_MS ? 1024 : 512, 1) tile4_kernel(const K4Params p)
+    {
+        typedef typename PtrOf<SMEM>::type P;
+        typedef Vec<T> V;
+        constexpr int VEC = V::N, FPC = LANES * VEC, NPW = 32 / LANES;
+        constexpr int TS = (int)sizeof(T), RS = 16 * LANES, ISZ = (int)sizeof(IdxT);
+        constexpr uint32_t ALL = (FPC == 32) ? 0xFFFFFFFFu : ((1u << FPC) - 1u), VMASK = (1u << VEC) - 1u;
+        extern __shared__ __align__(16) unsigned char dyn_smem[];
+        __shared__ unsigned long long s_frame[FPC], s_old[FPC];
+        __shared__ unsigned long long s_cnt[5];
+        __shared__ uint32_t s_err[FPC];
+        __shared__ uint32_t s_synd[2];
+        __shared__ uint2 s_ctrl[2]; // {frames at the iteration limit, frames with >= 1 completed iteration}
+        __shared__ int s_ret[FPC];
+        __shared__ uint32_t s_active, s_skip, s_next;
+
+        const int tid = threadIdx.x, nthreads = blockDim.x;
+        const int lane = tid & 31, warp = tid >> 5, warps = nthreads >> 5;
+        const int sub = lane & (LANES - 1), j = lane / LANES;
+
+        // ---- carve state and tables --------------------------------------------------------
+        P c2v, out, llr, cn_seg, vn_seg, cn_idx, vn_idx;
+        if constexpr (SMEM)
+        {
+            uint32_t q = (uint32_t)__cvta_generic_to_shared(dyn_smem);
+            const uint32_t a_c2v = q; q += RS * p.n_slots;
+            const uint32_t a_out = q; q += RS * p.n_pos;
+            const uint32_t a_llr = q; q += RS * p.n_pos;
+            const uint32_t a_cs = q; q += 16 * p.cn_max_segs * warps;
+            const uint32_t a_vs = q; q += 16 * p.vn_max_segs * warps;
+            const uint32_t a_ci = q; q += p.cn_idx_bytes;
+            const uint32_t a_vi = q;
+            for (int i = tid; i < 4 * p.cn_max_segs * warps; i += nthreads) sts_u32<0>(a_cs + 4 * i, p.cn_seg[i]);
+            for (int i = tid; i < 4 * p.vn_max_segs * warps; i += nthreads) sts_u32<0>(a_vs + 4 * i, p.vn_seg[i]);
+            for (int i = tid; i < (int)(p.cn_idx_bytes >> 2); i += nthreads) sts_u32<0>(a_ci + 4 * i, reinterpret_cast<const uint32_t *>(p.cn_idx)[i]);
+            for (int i = tid; i < (int)(p.vn_idx_bytes >> 2); i += nthreads) sts_u32<0>(a_vi + 4 * i, reinterpret_cast<const uint32_t *>(p.vn_idx)[i]);
+            c2v = a_c2v; out = a_out; llr = a_llr; cn_seg = a_cs; vn_seg = a_vs; cn_idx = a_ci; vn_idx = a_vi;
+        }
+        else
+        {
+            unsigned char *q = p.state + p.state_stride * blockIdx.x;
+            unsigned char *g_c2v = q; q += (size_t)RS * p.n_slots;
+            unsigned char *g_out = q; q += (size_t)RS * p.n_pos;
+            unsigned char *g_llr = q;
+            c2v = g_c2v; out = g_out; llr = g_llr;
+            cn_seg = (unsigned char *)p.cn_seg; vn_seg = (unsigned char *)p.vn_seg;
+            cn_idx = (unsigned char *)p.cn_idx; vn_idx = (unsigned char *)p.vn_idx;
+        }
+        if (tid < 5) s_cnt[tid] = 0;
+        if (tid < FPC) { s_err[tid] = 0; s_frame[tid] = 0; s_old[tid] = 0; s_ret[tid] = 0; }
+        if (tid == 0)
+        {
+            s_next = 0; s_active = 0; s_skip = 0; s_synd[0] = 0; s_synd[1] = 0;
+            s_ctrl[0] = make_uint2(0, 0); s_ctrl[1] = make_uint2(0, 0);
+        }
+        __syncthreads();
+
+        // per-frame iteration counter: lane g of warp 0 owns frame lane g
+        int it = 0;
+        uint32_t active = 0, skip = 0; // CTA-uniform copies of s_active / s_skip
+
+        // Writes the decoder input of global frame gf into frame lane g (all threads of the CTA
+        // cooperate), with the fresh-frame state: out = LLRin, c2v = +0.
+        auto generate = [&](int g, unsigned long long gf)
+        {
+            const int eo = (g / VEC) * 16 + (g % VEC) * TS; // byte offset of lane g inside a record
+            const P dl = llr + eo, dout = out + eo, dc = c2v + eo;
+            for (int i = tid; i < p.n_slots; i += nthreads) Acc<SMEM, T, 0>::st(dc + i * RS, T(0));
+            auto put = [&](int pos, T v)
+            {
+                Acc<SMEM, T, 0>::st(dl + pos * RS, v);
+                Acc<SMEM, T, 0>::st(dout + pos * RS, v);
+            };
+            if (p.kind == SRC_LLR)
+            {
+                const double *src = p.llr_in + (size_t)gf * p.nc;
+                for (int i = tid; i < p.nc; i += nthreads) put((int)p.var_pos[i], (T)src[i]);
+                return;
+            }
+            const unsigned long long frame = p.frame0 + gf;
+            if (p.kind == SRC_AWGN)
+            { // y = sigma*z + 1 (all-zero codeword, BPSK +1), LLR = 2y/sigma^2 (src/sim/channel.cpp:62-68,88-92)
+                const int npairs = (p.nct + 1) >> 1;
+                for (int q = tid; q < npairs; q += nthreads)
+                {
+                    const u32x4 r = channel_block(p.seed, p.point, 0, frame, (uint32_t)q);
+                    const double u1 = ((double)((((uint64_t)r.y << 32) | r.x) >> 11) + 1.0) * 0x1p-53;
+                    const double u2 = (double)((((uint64_t)r.w << 32) | r.z) >> 11) * 0x1p-53;
+                    const double rad = sqrt(-2.0 * log(u1));
+                    double sn, cs;
+                    sincos(6.283185307179586 * u2, &sn, &cs);
+                    const double y0 = __dadd_rn(__dmul_rn(rad * cs, p.sigma), 1.0);
+                    const double y1 = __dadd_rn(__dmul_rn(rad * sn, p.sigma), 1.0);
+                    const int t = 2 * q;
+                    put(p.tx_pos[t], (T)(__dmul_rn(2.0, y0) / p.sigma2));
+                    if (t + 1 < p.nct) put(p.tx_pos[t + 1], (T)(__dmul_rn(2.0, y1) / p.sigma2));
+                }
+                for (int i = tid; i < p.n_punct; i += nthreads) put(p.punct_pos[i], T(0));
+                for (int i = tid; i < p.n_short; i += nthreads) put(p.short_pos[i], (T)99999.9);
+            }
+            else
+            { // BSC: y = x ^ Bernoulli(eps), LLR = delta*(1-2y) (src/sim/channel.cpp:123-162)
+                const int nblk = (p.nct + 3) >> 2;
+                for (int q = tid; q < nblk; q += nthreads)
+                {
+                    const u32x4 r = channel_block(p.seed, p.point, 0, frame, (uint32_t)q);
+                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const int t = 4 * q + k;
+                        if (t < p.nct) put(p.tx_pos[t], (T)((w[k] < p.thr) ? -p.delta : p.delta));
+                    }
+                }
+                for (int i = tid; i < p.n_punct; i += nthreads) put(p.punct_pos[i], T(0));
+                for (int i = tid; i < p.n_short; i += nthreads) put(p.short_pos[i], (T)p.delta);
+            }
+        };
+
+        // Retires the frame lanes in `mask` and hands each a new frame if any is left.
+        //   synd / started : syndrome flags and ">= 1 iteration done" flags valid for this decision
+        //   as_skip        : the new frames must sit out the variable phase that follows
+        auto retire_and_refill = [&](uint32_t mask, uint32_t synd, uint32_t started, bool as_skip, bool first_fill)
+        {
+            if (!first_fill)
+            { // bit errors of the final decisions over the transmitted positions, all-zero codeword (ldpcsim.cpp:184-190)
+                for (int g = 0; g < FPC; ++g)
+                    if ((mask >> g) & 1u)
+                    {
+                        const P src = out + (g / VEC) * 16 + (g % VEC) * TS;
+                        uint32_t n = 0;
+                        for (int i = tid; i < p.nct; i += nthreads) n += (Acc<SMEM, T, 0>::ld(src + p.tx_pos[i] * RS) <= T(0)) ? 1u : 0u;
+                        n = __reduce_add_sync(0xffffffffu, n);
+                        if (lane == 0 && n) atomicAdd(&s_err[g], n);
+                    }
+                __syncthreads();
+            }
+            if (warp == 0)
+            {
+                bool got = false;
+                const bool mine = lane < FPC && ((mask >> lane) & 1u);
+                if (mine && !first_fill)
+                {
+                    const bool conv = p.early_term && ((started >> lane) & 1u) && !((synd >> lane) & 1u);
+                    const int ret = conv ? it - 1 : p.max_iter; // the reference breaks before ++I (decoder.cpp:66-77)
+                    const uint32_t e = s_err[lane];
+                    s_err[lane] = 0;
+                    atomicAdd(&s_cnt[0], (unsigned long long)(e ? 1 : 0));
+                    atomicAdd(&s_cnt[1], (unsigned long long)e);
+                    atomicAdd(&s_cnt[2], 1ull);
+                    atomicAdd(&s_cnt[3], (unsigned long long)ret);
+                    atomicAdd(&s_cnt[4], (unsigned long long)it);
+                    s_ret[lane] = ret;
+                    s_old[lane] = s_frame[lane];
+                }
+                if (mine)
+                {
+                    const uint32_t k = s_next + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                    const unsigned long long gf = (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * k;
+                    got = gf < p.n_frames; // frame indices grow with k: the lanes that get one form a prefix of `mask`
+                    if (got) s_frame[lane] = gf;
+                    it = 0;
+                }
+                const uint32_t gm = __ballot_sync(0xffffffffu, got);
+                if (lane == 0)
+                {
+                    s_next += (uint32_t)__popc(gm);
+                    s_active = (active & ~mask) | gm;
+                    s_skip = as_skip ? gm : 0u;
+                }
+            }
+            __syncthreads();
+            const uint32_t new_active = s_active;
+            if (!first_fill && (p.llr_out || p.hard_out || p.iters_out))
+            {
+                for (int g = 0; g < FPC; ++g)
+                    if ((mask >> g) & 1u)
+                    {
+                        const int eo = (g / VEC) * 16 + (g % VEC) * TS;
+                        const size_t o = (size_t)s_old[g] * p.nc;
+                        for (int i = tid; i < p.nc; i += nthreads)
+                        {
+                            const T v = Acc<SMEM, T, 0>::ld(out + eo + p.var_pos[i] * RS);
+                            if (p.llr_out) p.llr_out[o + i] = (double)v;
+                            if (p.hard_out) p.hard_out[o + i] = (v <= T(0)) ? 1 : 0; // decoder.cpp:58
+                        }
+                        if (tid == 0 && p.iters_out) p.iters_out[s_old[g]] = s_ret[g];
+                    }
+                __syncthreads();
+            }
+            for (int g = 0; g < FPC; ++g)
+                if (((mask & new_active) >> g) & 1u) generate(g, s_frame[g]);
+            __syncthreads();
+            active = new_active;
+            skip = s_skip;
+        };
+
+        retire_and_refill(ALL, 0, 0, false, true);
+
+        const P c2v_lane = c2v + lane * 16, c2v_sub = c2v + sub * 16, out_sub = out + sub * 16;
+        const P out_lane = out + lane * 16, llr_lane = llr + lane * 16;
+        const P cn_seg_w = cn_seg + 16 * p.cn_max_segs * warp, vn_seg_w = vn_seg + 16 * p.vn_max_segs * warp;
+
+        for (uint32_t L = 0;; ++L)
+        {
+            const int par_i = (int)(L & 1u);
+            if (!active) break; // CTA-uniform
+
+            // ---- without early termination a frame at the iteration limit retires here, before a
+            //      check phase is spent on it (its result is fixed: decoder.cpp:22,74-77)
+            if (!p.early_term)
+            {
+                const uint32_t lim = s_ctrl[par_i].x & active;
+                if (lim)
+                {
+                    retire_and_refill(lim, 0, 0, false, false);
+                    if (warp == 0 && lane == 0) s_ctrl[par_i].x &= ~lim;
+                    if (!active) break;
+                }
+            }
+
+            // ---- check-node phase (+ syndrome of the previous iteration's decisions) ----------
+            uint32_t bad = 0;
+            for (P sp = cn_seg_w;; sp += 16)
+            {
+                const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
+                if (sg.x == 0) break;
+                const int deg = (int)(sg.x & 0xFFu), cnt = (int)((sg.x >> 8) & 0xFFu);
+                int nt = (int)(sg.x >> 16);
+                if (j >= cnt) continue;
+                P c2v0 = c2v_lane + sg.y;
+                const P ib = cn_idx + sg.z;
+#define B200_CN_CASE(D)                                                                                      \
+    case D:                                                                                                  \
+    {                                                                                                        \
+        constexpr int ST = idx_stride_of(D, ISZ);                                                            \
+        P ip = ib + j * ST;                                                                                  \
+        _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
+        {                                                                                                    \
+            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::run(out_sub, c2v0, ip);                                \
+            c2v0 += D * 512;                                                                                 \
+            ip += NPW * ST;                                                                                  \
+        }                                                                                                    \
+        break;                                                                                               \
+    }
+                switch (deg) // warp-uniform
+                {
+                    B200_CN_CASE(2)
+                    B200_CN_CASE(3)
+                    B200_CN_CASE(4)
+                    B200_CN_CASE(5)
+                    B200_CN_CASE(6)
+                    B200_CN_CASE(7)
+                    B200_CN_CASE(8)
+                default:
+                {
+                    const int st = idx_stride_of(deg, ISZ);
+                    P ip = ib + j * st;
+                    for (; nt > 0; --nt)
+                    {
+                        bad |= cn4_any<T, IdxT, SMEM, LANES, ALG>(out_sub, c2v0, ip, deg);
+                        c2v0 += deg * 512;
+                        ip += NPW * st;
+                    }
+                    break;
+                }
+                }
+#undef B200_CN_CASE
+            }
+            // syndrome flags per frame lane: frame = sub*VEC + e
+            {
+                const uint32_t m = __reduce_or_sync(0xffffffffu, bad << (sub * VEC));
+                if (lane == 0 && m) atomicOr(&s_synd[par_i], m);
+            }
+            __syncthreads(); // B
+
+            // ---- decision: converged (decoder.cpp:66-72) or out of iterations ---------------------
+            {
+                const uint32_t synd = s_synd[par_i];
+                const uint2 ctrl = s_ctrl[par_i];
+                const uint32_t done = active & ((p.early_term ? (~synd & ctrl.y) : 0u) | ctrl.x);
+                if (done) retire_and_refill(done, synd, ctrl.y, true, false);
+            }
+            // bookkeeping for the variable phase that follows and the next decision
+            const uint32_t live = active & ~skip;
+            if (warp == 0)
+            {
+                if (lane < FPC && ((live >> lane) & 1u)) ++it;
+                const bool act = lane < FPC && ((active >> lane) & 1u);
+                const uint32_t started = __ballot_sync(0xffffffffu, act && it >= 1);
+                const uint32_t limit = __ballot_sync(0xffffffffu, act && it >= p.max_iter);
+                if (lane == 0) { s_ctrl[par_i ^ 1] = make_uint2(limit, started); s_synd[par_i ^ 1] = 0; }
+            }
+
+            // ---- variable-node phase: posterior (hard decision = its sign, taken where it is consumed) ----
+            const uint32_t mylive = (live >> (sub * VEC)) & VMASK;
+            if (live)
+            {
+                for (P sp = vn_seg_w;; sp += 16)
+                {
+                    const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
+                    if (sg.x == 0) break;
+                    const int deg = (int)(sg.x & 0xFFu), cnt = (int)((sg.x >> 8) & 0xFFu);
+                    int nt = (int)(sg.x >> 16);
+                    if (j >= cnt) continue;
+                    P lp = llr_lane + sg.y, op = out_lane + sg.y;
+                    const P ib = vn_idx + sg.z;
+                    auto finish = [&](const V &acc)
+                    {
+                        if (mylive == VMASK) VAcc<SMEM, T, 0>::st(op, acc);
+                        else
+                        {
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e)
+                                if ((mylive >> e) & 1u) Acc<SMEM, T, 0>::st(op + e * TS, acc.e[e]);
+                        }
+                        lp += 512;
+                        op += 512;
+                    };
+#define B200_VN_CASE(D)                                                                                      \
+    case D:                                                                                                  \
+    {                                                                                                        \
+        constexpr int ST = idx_stride_of(D, ISZ);                                                            \
+        P ip = ib + j * ST;                                                                                  \
+        _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
+        {                                                                                                    \
+            finish(Vn4<T, IdxT, SMEM, D>::run(c2v_sub, ip, VAcc<SMEM, T, 0>::ld(lp))); /* decoder.cpp:50 */ \
+            ip += NPW * ST;                                                                                  \
+        }                                                                                                    \
+        break;                                                                                               \
+    }
+                    switch (deg)
+                    {
+                    case 0:
+                        for (; nt > 0; --nt) finish(VAcc<SMEM, T, 0>::ld(lp));
+                        break;
+                        B200_VN_CASE(1)
+                        B200_VN_CASE(2)
+                        B200_VN_CASE(3)
+                        B200_VN_CASE(4)
+                        B200_VN_CASE(5)
+                        B200_VN_CASE(6)
+                        B200_VN_CASE(7)
+                        B200_VN_CASE(8)
+                    default:
+                    {
+                        const int st = idx_stride_of(deg, ISZ);
+                        P ip = ib + j * st;
+                        for (; nt > 0; --nt)
+                        {
+                            finish(vn4_any<T, IdxT, SMEM>(c2v_sub, ip, deg, VAcc<SMEM, T, 0>::ld(lp)));
+                            ip += NPW * st;
+                        }
+                        break;
+                    }
+                    }
+#undef B200_VN_CASE
+                }
+            }
+            skip = 0;
+            __syncthreads(); // A: variable-phase writes visible to the next check phase
+        }
+
+        __syncthreads();
+        if (tid < 5 && s_cnt[tid]) atomicAdd(&p.counters[tid], s_cnt[tid]);
+    }
+} // namespace b200
