@@ -393,6 +393,15 @@ namespace b200
                 buf[off + 2] = (uint8_t)((v >> 16) & 0xFF); buf[off + 3] = (uint8_t)(v >> 24);
             }
         };
+        // byte offset of entry k of node j of task t inside a segment's index block: node-major while a node's
+        // entries fit 8 bytes, else 16-byte chunks stored chunk-major ([task][chunk][node]) so that the
+        // vector load of a chunk is contiguous over the nodes of a warp task (bank-conflict free)
+        auto idx_offset = [&](int t, int j, int k, int stride) -> size_t
+        {
+            if (stride < 16) return ((size_t)t * npw + j) * stride + (size_t)k * isz;
+            const int epc = 16 / isz;
+            return (size_t)t * npw * stride + (size_t)(k / epc) * npw * 16 + (size_t)j * 16 + (size_t)(k % epc) * isz;
+        };
         auto flatten = [&](const std::vector<std::vector<Seg>> &segs, int &max_segs, std::vector<uint32_t> &out)
         {
             max_segs = 1;
@@ -479,7 +488,7 @@ namespace b200
                         {
                             const int e = code.row_edge[code.row_ptr[row] + k];
                             edge_slot[e] = (int)(sg.base + ((size_t)t * sg.deg + k) * npw + j);
-                            put(cn_idx, sg.idx + ((size_t)t * npw + j) * stride + (size_t)k * isz, var_pos[code.e_col[e]]);
+                            put(cn_idx, sg.idx + idx_offset(t, j, k, stride), var_pos[code.e_col[e]]);
                         }
                     }
                 }
@@ -495,8 +504,7 @@ namespace b200
                     {
                         const int col = g.nodes[j];
                         for (int k = 0; k < sg.deg; ++k)
-                            put(vn_idx, sg.idx + ((size_t)t * npw + j) * stride + (size_t)k * isz,
-                                (uint32_t)edge_slot[code.col_edge[code.col_ptr[col] + k]]);
+                            put(vn_idx, sg.idx + idx_offset(t, j, k, stride), (uint32_t)edge_slot[code.col_edge[code.col_ptr[col] + k]]);
                     }
                 }
             }

@@ -98,9 +98,13 @@ namespace b200
     //
     //   message slot  = seg.slot_base + (t*deg + k)*npw + j      (task t of the segment, edge k, node j)
     //   position      = seg.pos_base + t*npw + j                 (variable side)
-    //   index entries = seg.idx_base + (t*npw + j)*stride + k*isz bytes: the deg entries of a node are
-    //                   contiguous and padded to `stride` = idx_stride(deg, isz) bytes, so a thread
-    //                   fetches all (or 16 bytes' worth) of its node's indices with one vector load.
+    //   index entries = seg.idx_base + (t*npw + j)*stride + k*isz bytes while a node's deg entries fit 8
+    //                   bytes (`stride` = idx_stride(deg, isz)); longer blocks are cut into 16-byte chunks
+    //                   stored chunk-major, seg.idx_base + t*npw*stride + (k/epc)*npw*16 + j*16 + (k%epc)*isz
+    //                   with epc = 16/isz, so a thread fetches 16 bytes' worth of its node's indices with one
+    //                   vector load and a warp's load of a chunk is contiguous (bank-conflict free).
+    //                   Nodes missing from a ragged last task keep all-zero entries and own padded slots /
+    //                   positions, so their threads can run the node update unconditionally.
     //                   Check side: entry = position gathered by edge k; variable side: entry = message
     //                   slot of edge k (both in file order).  Entries are stored PRE-SCALED to the byte
     //                   offset of the record they name (index * 16 * lanes; in 16-byte units when isz = 2).

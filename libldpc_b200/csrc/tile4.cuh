@@ -113,11 +113,14 @@ namespace b200
     }
 
     // All D index entries of one node -> byte offsets.  Entries are uint32 byte offsets or uint16 offsets in
-    // 16-byte units (shared-memory residency of codes whose tables would not fit otherwise).
-    template <bool SMEM, typename IdxT, int D> struct IdxLoad
+    // 16-byte units (shared-memory residency of codes whose tables would not fit otherwise).  Blocks of up
+    // to 8 bytes are node-major; longer ones are 16-byte chunks, chunk-major (SegLayout, code.hpp): chunk q of
+    // node j at + q*NPW*16 + j*16.
+    template <bool SMEM, typename IdxT, int LANES, int D> struct IdxLoad
     {
         typedef typename PtrOf<SMEM>::type P;
         static constexpr int ISZ = (int)sizeof(IdxT), STRIDE = idx_stride_of(D, ISZ), NW = (STRIDE + 3) / 4;
+        static constexpr int CH = STRIDE < 16 ? STRIDE : 16, CSTEP = (32 / LANES) * 16;
         static __device__ __forceinline__ void load(P p, uint32_t (&e)[D])
         {
             uint32_t w[NW];
@@ -126,7 +129,7 @@ namespace b200
             else if constexpr (STRIDE == 8) { const uint2 t = WAcc<SMEM, 0>::ld2(p); w[0] = t.x; w[1] = t.y; }
             else
                 static_for<STRIDE / 16>([&](auto q) {
-                    const uint4 t = WAcc<SMEM, q.value * 16>::ld4(p);
+                    const uint4 t = WAcc<SMEM, q.value * CSTEP>::ld4(p);
                     w[4 * q.value] = t.x; w[4 * q.value + 1] = t.y; w[4 * q.value + 2] = t.z; w[4 * q.value + 3] = t.w;
                 });
 #pragma unroll
@@ -137,13 +140,21 @@ namespace b200
             }
         }
     };
-    template <bool SMEM, typename IdxT> struct IdxOne
-    { // entry k of a node -> byte offset (generic-degree paths)
+    // one 16-byte chunk (EPC = 16/sizeof(IdxT) entries) of a long index block -> byte offsets (generic-degree paths)
+    template <bool SMEM, typename IdxT> struct IdxChunk
+    {
         typedef typename PtrOf<SMEM>::type P;
-        static __device__ __forceinline__ uint32_t ld(P p, int k)
+        static constexpr int EPC = 16 / (int)sizeof(IdxT);
+        static __device__ __forceinline__ void load(P p, uint32_t (&e)[EPC])
         {
-            if constexpr (sizeof(IdxT) == 4) return Acc<SMEM, uint32_t, 0>::ld(p + 4 * k);
-            else return (uint32_t)Acc<SMEM, uint16_t, 0>::ld(p + 2 * k) << 4;
+            const uint4 t = WAcc<SMEM, 0>::ld4(p);
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < EPC; ++k)
+            {
+                if constexpr (sizeof(IdxT) == 4) e[k] = w[k];
+                else e[k] = ((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xFFFFu)) << 4;
+            }
         }
     };
 
@@ -206,7 +217,7 @@ namespace b200
         static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, P ip)
         {
             uint32_t eo[D];
-            IdxLoad<SMEM, IdxT, D>::load(ip, eo);
+            IdxLoad<SMEM, IdxT, LANES, D>::load(ip, eo);
             bool par[VEC];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) par[e] = false;
@@ -308,12 +319,14 @@ namespace b200
         }
     };
 
-    // arbitrary degree (<= 64): running min1/min2 + sign mask for min-sum, parked forward values for box-plus
+    // arbitrary degree (9..64): running min1/min2 + sign mask for min-sum, parked forward values for box-plus.
+    // The index block is walked in 16-byte chunks (chunk q at ip + q*NPW*16).
     template <typename T, typename IdxT, bool SMEM, int LANES, int ALG>
     __device__ __noinline__ uint32_t cn4_any(typename PtrOf<SMEM>::type out_sub, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type ip, int deg)
     {
         typedef Vec<T> V;
-        constexpr int VEC = V::N, CS = 512;
+        typedef IdxChunk<SMEM, IdxT> IC;
+        constexpr int VEC = V::N, CS = 512, EPC = IC::EPC, CSTEP = (32 / LANES) * 16;
         uint32_t par = 0;
         if (ALG == ALG_MS)
         {
@@ -322,20 +335,30 @@ namespace b200
             unsigned long long smask[VEC];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) { m1[e] = Num<T>::inf(); m2[e] = Num<T>::inf(); arg[e] = 0; smask[e] = 0; }
-            for (int k = 0; k < deg; ++k)
+            for (int k0 = 0; k0 < deg; k0 += EPC, ip += CSTEP)
             {
-                const V o = VAcc<SMEM, T, 0>::ld(out_sub + IdxOne<SMEM, IdxT>::ld(ip, k));
-                const V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                uint32_t eo[EPC];
+                IC::load(ip, eo);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e)
+                for (int q = 0; q < EPC; ++q)
                 {
-                    const T v = o.e[e] - c.e[e];
-                    par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u;
-                    smask[e] |= (unsigned long long)(Num<T>::hi(v) >> 31) << k;
-                    const bool lt1 = Num<T>::abs(v) < Num<T>::abs(m1[e]), lt2 = Num<T>::abs(v) < Num<T>::abs(m2[e]);
-                    m2[e] = lt1 ? m1[e] : (lt2 ? v : m2[e]);
-                    arg[e] = lt1 ? k : arg[e];
-                    m1[e] = lt1 ? v : m1[e];
+                    const int k = k0 + q;
+                    if (k < deg)
+                    {
+                        const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[q]);
+                        const V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e)
+                        {
+                            const T v = o.e[e] - c.e[e];
+                            par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u;
+                            smask[e] |= (unsigned long long)(Num<T>::hi(v) >> 31) << k;
+                            const bool lt1 = Num<T>::abs(v) < Num<T>::abs(m1[e]), lt2 = Num<T>::abs(v) < Num<T>::abs(m2[e]);
+                            m2[e] = lt1 ? m1[e] : (lt2 ? v : m2[e]);
+                            arg[e] = lt1 ? k : arg[e];
+                            m1[e] = lt1 ? v : m1[e];
+                        }
+                    }
                 }
             }
             uint32_t tot[VEC];
@@ -358,25 +381,33 @@ namespace b200
             // box-plus forward/backward with the forward values parked in the output slots: slot k first
             // receives F[k-1]; the backward sweep turns it into f(F[k-1], B[k+1]) (decoder.cpp:33-44).
             // v[k] is needed again by the backward sweep (out and the old c2v are gone by then).
-            V Fp, B, vk;
+            V Fp, B;
             V v[64];
+            for (int k0 = 0; k0 < deg; k0 += EPC, ip += CSTEP)
             {
-                const V o = VAcc<SMEM, T, 0>::ld(out_sub + IdxOne<SMEM, IdxT>::ld(ip, 0));
-                const V c = VAcc<SMEM, T, 0>::ld(c2v0);
+                uint32_t eo[EPC];
+                IC::load(ip, eo);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) { Fp.e[e] = o.e[e] - c.e[e]; par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u; }
-            }
-            v[0] = Fp;
-            for (int k = 1; k < deg; ++k)
-            {
-                const V o = VAcc<SMEM, T, 0>::ld(out_sub + IdxOne<SMEM, IdxT>::ld(ip, k));
-                const V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                for (int q = 0; q < EPC; ++q)
+                {
+                    const int k = k0 + q;
+                    if (k < deg)
+                    {
+                        const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[q]);
+                        const V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                        V vk;
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) { vk.e[e] = o.e[e] - c.e[e]; par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u; }
-                v[k] = vk;
-                VAcc<SMEM, T, 0>::st(c2v0 + k * CS, Fp); // F[k-1] (slot deg-1 thereby gets its final value)
+                        for (int e = 0; e < VEC; ++e) { vk.e[e] = o.e[e] - c.e[e]; par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u; }
+                        v[k] = vk;
+                        if (k == 0) Fp = vk;
+                        else
+                        {
+                            VAcc<SMEM, T, 0>::st(c2v0 + k * CS, Fp); // F[k-1] (slot deg-1 thereby gets its final value)
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) Fp.e[e] = boxplus(Fp.e[e], vk.e[e]);
+                            for (int e = 0; e < VEC; ++e) Fp.e[e] = boxplus(Fp.e[e], vk.e[e]);
+                        }
+                    }
+                }
             }
             B = v[deg - 1];
             for (int k = deg - 2; k >= 1; --k)
@@ -393,7 +424,7 @@ namespace b200
     }
 
     // variable node: posterior = LLRin + sum of incoming c2v, strictly in file order (decoder.cpp:50-56)
-    template <typename T, typename IdxT, bool SMEM, int D>
+    template <typename T, typename IdxT, bool SMEM, int LANES, int D>
     struct Vn4
     {
         typedef typename PtrOf<SMEM>::type P;
@@ -401,7 +432,7 @@ namespace b200
         static __device__ __forceinline__ V run(P c2v_sub, P ip, V acc)
         {
             uint32_t eo[D];
-            IdxLoad<SMEM, IdxT, D>::load(ip, eo);
+            IdxLoad<SMEM, IdxT, LANES, D>::load(ip, eo);
             V m[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) m[k] = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[k]);
@@ -414,26 +445,40 @@ namespace b200
             return acc;
         }
     };
-    // arbitrary degree: chunks of 4 entries (the index block of a node of degree > 8/sizeof(IdxT) is padded to 16 bytes)
-    template <typename T, typename IdxT, bool SMEM>
+    // arbitrary degree (> 8): 16-byte index chunks (chunk q at ip + q*NPW*16)
+    template <typename T, typename IdxT, bool SMEM, int LANES>
     __device__ __forceinline__ Vec<T> vn4_any(typename PtrOf<SMEM>::type c2v_sub, typename PtrOf<SMEM>::type ip, int deg, Vec<T> acc)
     {
         typedef Vec<T> V;
-        int k = 0;
-        for (; k + 4 <= deg; k += 4)
+        typedef IdxChunk<SMEM, IdxT> IC;
+        constexpr int EPC = IC::EPC, CSTEP = (32 / LANES) * 16;
+        for (int k0 = 0; k0 < deg; k0 += EPC, ip += CSTEP)
         {
-            uint32_t eo[4];
-            IdxLoad<SMEM, IdxT, 4>::load(ip + k * (int)sizeof(IdxT), eo);
-            const V m0 = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[0]), m1 = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[1]);
-            const V m2 = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[2]), m3 = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[3]);
+            uint32_t eo[EPC];
+            IC::load(ip, eo);
+            if (k0 + EPC <= deg)
+            {
+                V m[EPC];
 #pragma unroll
-            for (int e = 0; e < V::N; ++e) { acc.e[e] += m0.e[e]; acc.e[e] += m1.e[e]; acc.e[e] += m2.e[e]; acc.e[e] += m3.e[e]; }
-        }
-        for (; k < deg; ++k)
-        {
-            const V m = VAcc<SMEM, T, 0>::ld(c2v_sub + IdxOne<SMEM, IdxT>::ld(ip, k));
+                for (int q = 0; q < EPC; ++q) m[q] = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[q]);
 #pragma unroll
-            for (int e = 0; e < V::N; ++e) acc.e[e] += m.e[e];
+                for (int q = 0; q < EPC; ++q)
+                {
+#pragma unroll
+                    for (int e = 0; e < V::N; ++e) acc.e[e] += m[q].e[e];
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int q = 0; q < EPC; ++q)
+                    if (k0 + q < deg)
+                    {
+                        const V m = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[q]);
+#pragma unroll
+                        for (int e = 0; e < V::N; ++e) acc.e[e] += m.e[e];
+                    }
+            }
         }
         return acc;
     }
@@ -669,19 +714,20 @@ namespace b200
             {
                 const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
                 if (sg.x == 0) break;
-                const int deg = (int)(sg.x & 0xFFu), cnt = (int)((sg.x >> 8) & 0xFFu);
+                // threads of nodes missing from a ragged task run along on padded slots / zero index entries
+                const int deg = (int)(sg.x & 0xFFu);
+                const uint32_t keep = (j < (int)((sg.x >> 8) & 0xFFu)) ? 0xFFFFFFFFu : 0u;
                 int nt = (int)(sg.x >> 16);
-                if (j >= cnt) continue;
                 P c2v0 = c2v_lane + sg.y;
                 const P ib = cn_idx + sg.z;
 #define B200_CN_CASE(D)                                                                                      \
     case D:                                                                                                  \
     {                                                                                                        \
         constexpr int ST = idx_stride_of(D, ISZ);                                                            \
-        P ip = ib + j * ST;                                                                                  \
+        P ip = ib + j * (ST < 16 ? ST : 16);                                                                 \
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
-            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::run(out_sub, c2v0, ip);                                \
+            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::run(out_sub, c2v0, ip) & keep;                         \
             c2v0 += D * 512;                                                                                 \
             ip += NPW * ST;                                                                                  \
         }                                                                                                    \
@@ -699,10 +745,10 @@ namespace b200
                 default:
                 {
                     const int st = idx_stride_of(deg, ISZ);
-                    P ip = ib + j * st;
+                    P ip = ib + j * 16;
                     for (; nt > 0; --nt)
                     {
-                        bad |= cn4_any<T, IdxT, SMEM, LANES, ALG>(out_sub, c2v0, ip, deg);
+                        bad |= cn4_any<T, IdxT, SMEM, LANES, ALG>(out_sub, c2v0, ip, deg) & keep;
                         c2v0 += deg * 512;
                         ip += NPW * st;
                     }
@@ -744,9 +790,8 @@ namespace b200
                 {
                     const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
                     if (sg.x == 0) break;
-                    const int deg = (int)(sg.x & 0xFFu), cnt = (int)((sg.x >> 8) & 0xFFu);
+                    const int deg = (int)(sg.x & 0xFFu);
                     int nt = (int)(sg.x >> 16);
-                    if (j >= cnt) continue;
                     P lp = llr_lane + sg.y, op = out_lane + sg.y;
                     const P ib = vn_idx + sg.z;
                     auto finish = [&](const V &acc)
@@ -765,10 +810,10 @@ namespace b200
     case D:                                                                                                  \
     {                                                                                                        \
         constexpr int ST = idx_stride_of(D, ISZ);                                                            \
-        P ip = ib + j * ST;                                                                                  \
+        P ip = ib + j * (ST < 16 ? ST : 16);                                                                 \
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
-            finish(Vn4<T, IdxT, SMEM, D>::run(c2v_sub, ip, VAcc<SMEM, T, 0>::ld(lp))); /* decoder.cpp:50 */ \
+            finish(Vn4<T, IdxT, SMEM, LANES, D>::run(c2v_sub, ip, VAcc<SMEM, T, 0>::ld(lp))); /* decoder.cpp:50 */ \
             ip += NPW * ST;                                                                                  \
         }                                                                                                    \
         break;                                                                                               \
@@ -789,10 +834,10 @@ namespace b200
                     default:
                     {
                         const int st = idx_stride_of(deg, ISZ);
-                        P ip = ib + j * st;
+                        P ip = ib + j * 16;
                         for (; nt > 0; --nt)
                         {
-                            finish(vn4_any<T, IdxT, SMEM>(c2v_sub, ip, deg, VAcc<SMEM, T, 0>::ld(lp)));
+                            finish(vn4_any<T, IdxT, SMEM, LANES>(c2v_sub, ip, deg, VAcc<SMEM, T, 0>::ld(lp)));
                             ip += NPW * st;
                         }
                         break;
