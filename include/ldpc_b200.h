@@ -109,6 +109,7 @@ typedef struct
     int threads_per_cta;  /* 0 = auto */
     int ctas;             /* 0 = auto (148 x resident CTAs) */
     int bec_deg1_compat;  /* 1 (default) = erased degree-1 variable nodes send 0 like the reference's UB outcome */
+    int tmem;             /* 0 = auto (Tensor-Memory mirror of thread-private state when it fits), 1 = off */
 } ldpc_b200_tuning;
 
 const char *ldpc_b200_last_error(void);

@@ -84,13 +84,13 @@ namespace b200
             return b + 16;
         }
 
-        int family_occupancy(int precision, int alg, bool smem, bool idx16, int lanes, int threads, size_t smem_bytes)
+        int family_occupancy(int precision, int alg, bool smem, bool tm, int lanes, int threads, size_t smem_bytes)
         {
             if (precision == LDPC_B200_F32)
-                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, idx16, lanes, threads, smem_bytes)
-                                     : tile_family_occupancy<float, ALG_BP>(smem, idx16, lanes, threads, smem_bytes);
-            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, idx16, lanes, threads, smem_bytes)
-                                 : tile_family_occupancy<double, ALG_BP>(smem, idx16, lanes, threads, smem_bytes);
+                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, tm, lanes, threads, smem_bytes)
+                                     : tile_family_occupancy<float, ALG_BP>(smem, tm, lanes, threads, smem_bytes);
+            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, tm, lanes, threads, smem_bytes)
+                                 : tile_family_occupancy<double, ALG_BP>(smem, tm, lanes, threads, smem_bytes);
         }
     } // namespace
 
@@ -156,14 +156,14 @@ namespace b200
         cuda_ready_ = true;
     }
 
-    const SegLayout &Engine::get_seg_layout(int lanes, int threads, int isz)
+    const SegLayout &Engine::get_seg_layout(int lanes, int threads)
     {
-        auto key = std::make_tuple(lanes, threads, isz);
+        auto key = std::make_pair(lanes, threads);
         auto it = seg_layouts_.find(key);
         if (it == seg_layouts_.end())
         {
             auto l = std::make_unique<SegLayout>();
-            l->build(H, lanes, threads, isz);
+            l->build(H, lanes, threads, 4);
             it = seg_layouts_.emplace(key, std::move(l)).first;
         }
         return *it->second;
@@ -176,7 +176,8 @@ namespace b200
     const SegLayout &Engine::layout_for(int precision, int alg, int *residency, size_t *smem_bytes)
     {
         const int vec = precision == LDPC_B200_F32 ? 4 : 2;
-        const int max_threads = alg == ALG_MS ? 1024 : 512;
+        (void)alg;
+        const int max_threads = 512; // the kernels are compiled for <= 512 threads (128 registers/thread at one CTA per SM)
         const int threads = tuning.threads_per_cta > 0 ? std::min(tuning.threads_per_cta, max_threads) : max_threads;
         int want_lanes = 0;
         if (tuning.frames_per_cta > 0)
@@ -192,25 +193,20 @@ namespace b200
             for (int lanes = 8; lanes >= 1; lanes >>= 1)
             {
                 if (want_lanes && lanes != want_lanes) continue;
-                // 32-bit index entries (ready-made byte offsets) when the tables still fit, else 16-bit
-                for (int isz = 4; isz >= 2; isz -= 2)
+                const SegLayout &l = get_seg_layout(lanes, threads);
+                const size_t need = seg_smem_bytes(l);
+                if (need <= limit)
                 {
-                    if (isz == 2 && (size_t)lanes * (size_t)std::max(H.nnz, H.nc) > 60000) continue;
-                    const SegLayout &l = get_seg_layout(lanes, threads, isz);
-                    const size_t need = seg_smem_bytes(l);
-                    if (need <= limit)
-                    {
-                        *residency = LDPC_B200_SMEM;
-                        *smem_bytes = need;
-                        return l;
-                    }
+                    *residency = LDPC_B200_SMEM;
+                    *smem_bytes = need;
+                    return l;
                 }
             }
             if (tuning.residency == LDPC_B200_SMEM) throw std::runtime_error("code does not fit shared-memory residency with this tuning");
         }
         *residency = LDPC_B200_GLOBAL;
         *smem_bytes = 0;
-        return get_seg_layout(want_lanes ? want_lanes : 1, threads, 4);
+        return get_seg_layout(want_lanes ? want_lanes : 1, threads);
     }
 
     Engine::Config Engine::choose(int precision, int alg, uint64_t n_frames)
@@ -222,14 +218,48 @@ namespace b200
         c.lanes = l.lanes;
         c.fpc = l.lanes * (precision == LDPC_B200_F32 ? 4 : 2);
         c.threads = l.threads;
-        c.idx16 = (l.isz == 2);
+        // Tensor-Memory mirror (shared-memory residency): every warp gets a window of 4 columns per mirrored 16-byte
+        // vector (its check tasks' c2v slots, then its variable tasks' channel LLRs); the windows of the warps that
+        // share a TMEM lane partition (warp % 4) lie side by side in the 512 columns.
+        c.tm = false;
+        c.tm_alloc_cols = c.tm_cols_per_warp = c.tm_vn_off = 0;
+        if (c.residency == LDPC_B200_SMEM && tuning.tmem == 0)
+        {
+            uint32_t cn_max = 0, vn_max = 0;
+            for (int w = 0; w < l.warps; ++w)
+            {
+                uint32_t cn = 0, vn = 0;
+                for (int sgi = 0; sgi < l.cn_max_segs; ++sgi)
+                {
+                    const uint32_t d = l.cn_seg[4 * ((size_t)w * l.cn_max_segs + sgi)];
+                    if (!d) break;
+                    cn += (d & 0xFFu) * (d >> 16);
+                }
+                for (int sgi = 0; sgi < l.vn_max_segs; ++sgi)
+                {
+                    const uint32_t d = l.vn_seg[4 * ((size_t)w * l.vn_max_segs + sgi)];
+                    if (!d) break;
+                    vn += d >> 16;
+                }
+                cn_max = std::max(cn_max, cn);
+                vn_max = std::max(vn_max, vn);
+            }
+            const uint32_t per_warp = 4 * (cn_max + vn_max), total = per_warp * (uint32_t)((l.warps + 3) / 4);
+            if (total <= 512)
+            {
+                uint32_t cols = 32;
+                while (cols < total) cols <<= 1;
+                c.tm = true;
+                c.tm_alloc_cols = cols; c.tm_cols_per_warp = per_warp; c.tm_vn_off = 4 * cn_max;
+            }
+        }
         int ctas = tuning.ctas;
         if (ctas <= 0)
         { // persistent grid: every SM gets as many CTAs as the runtime keeps resident
-            auto key = std::make_tuple(precision, alg, c.residency * 2 + (c.idx16 ? 1 : 0), c.lanes, c.threads, c.smem_bytes);
+            auto key = std::make_tuple(precision, alg, c.residency * 2 + (c.tm ? 1 : 0), c.lanes, c.threads, c.smem_bytes);
             auto it = occupancy_.find(key);
             if (it == occupancy_.end())
-                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.idx16, c.lanes, c.threads, c.smem_bytes)).first;
+                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.tm, c.lanes, c.threads, c.smem_bytes)).first;
             if (it->second < 1) throw std::runtime_error("tile kernel does not fit on this device with the current tuning");
             ctas = sm_count_ * it->second;
         }
@@ -239,12 +269,12 @@ namespace b200
         return c;
     }
 
-    DeviceSegLayout &Engine::device_seg_layout(int lanes, int threads, bool idx16)
+    DeviceSegLayout &Engine::device_seg_layout(int lanes, int threads)
     {
-        auto key = std::make_tuple(lanes, threads, idx16);
+        auto key = std::make_pair(lanes, threads);
         auto it = dev_seg_layouts_.find(key);
         if (it != dev_seg_layouts_.end()) return *it->second;
-        const SegLayout &l = get_seg_layout(lanes, threads, idx16 ? 2 : 4);
+        const SegLayout &l = get_seg_layout(lanes, threads);
         auto d = std::make_unique<DeviceSegLayout>();
         d->host = &l;
         d->cn_seg = upload(l.cn_seg);
@@ -335,7 +365,7 @@ namespace b200
 
         const int alg = minsum ? ALG_MS : ALG_BP;
         const Config c = choose(tuning.precision, alg, n_frames);
-        DeviceSegLayout &dl = device_seg_layout(c.lanes, c.threads, c.idx16);
+        DeviceSegLayout &dl = device_seg_layout(c.lanes, c.threads);
         const SegLayout &l = *dl.host;
 
         K4Params kp{};
@@ -373,16 +403,17 @@ namespace b200
             ensure_state(kp.state_stride * c.ctas);
             kp.state = d_state_;
         }
+        kp.tm_alloc_cols = c.tm_alloc_cols; kp.tm_cols_per_warp = c.tm_cols_per_warp; kp.tm_vn_off = c.tm_vn_off;
         const bool smem = c.residency == LDPC_B200_SMEM;
         if (c.precision == LDPC_B200_F32)
         {
-            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<float, ALG_BP>(kp, smem, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.tm, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<float, ALG_BP>(kp, smem, c.tm, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         else
         {
-            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<double, ALG_BP>(kp, smem, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.tm, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<double, ALG_BP>(kp, smem, c.tm, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         stats.launches += 1;
         stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;

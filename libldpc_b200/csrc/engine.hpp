@@ -73,11 +73,12 @@ namespace b200
         {
             int precision, alg, residency, lanes, fpc, threads, ctas;
             size_t smem_bytes;
-            bool idx16;
+            bool tm;                                  // TMEM mirror in use
+            uint32_t tm_alloc_cols, tm_cols_per_warp, tm_vn_off;
         };
         Config choose(int precision, int alg, uint64_t n_frames);
-        const SegLayout &get_seg_layout(int lanes, int threads, int isz);
-        DeviceSegLayout &device_seg_layout(int lanes, int threads, bool idx16);
+        const SegLayout &get_seg_layout(int lanes, int threads);
+        DeviceSegLayout &device_seg_layout(int lanes, int threads);
         const TileLayout &get_layout(int fpc, int threads);
         void launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
         DeviceLayout &device_layout(int fpc, int threads, bool idx16);
@@ -91,8 +92,8 @@ namespace b200
         void *ev0_ = nullptr, *ev1_ = nullptr;
         std::map<std::pair<int, int>, std::unique_ptr<TileLayout>> layouts_;
         std::map<std::tuple<int, int, bool>, std::unique_ptr<DeviceLayout>> dev_layouts_;
-        std::map<std::tuple<int, int, int>, std::unique_ptr<SegLayout>> seg_layouts_;
-        std::map<std::tuple<int, int, bool>, std::unique_ptr<DeviceSegLayout>> dev_seg_layouts_;
+        std::map<std::pair<int, int>, std::unique_ptr<SegLayout>> seg_layouts_;
+        std::map<std::pair<int, int>, std::unique_ptr<DeviceSegLayout>> dev_seg_layouts_;
         std::map<std::tuple<int, int, int, int, int, size_t>, int> occupancy_;
         int32_t *d_bit_pos_ = nullptr, *d_punct_ = nullptr, *d_short_ = nullptr;
         unsigned long long *d_counters_ = nullptr;

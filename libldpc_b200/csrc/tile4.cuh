@@ -99,6 +99,48 @@ namespace b200
         static __device__ __forceinline__ uint4 ld4(const unsigned char *a) { return __ldg(reinterpret_cast<const uint4 *>(a + OFF)); }
     };
 
+    // ------------------------------------------------------------------------------------------
+    // Tensor Memory as thread-private scratch.  tcgen05.ld/st with shape 32x32b.x4: thread i of a warp
+    // moves four 32-bit columns of TMEM lane (warp % 4) * 32 + i, i.e. one 16-byte vector per thread and
+    // instruction, on a data path separate from shared memory (LDTM / STTM).  Used as a write-through
+    // mirror of the two arrays only their owning thread ever reads back (a check task's own c2v slots, a
+    // variable task's channel LLR), which takes those reads off the shared-memory pipe that bounds the kernel.
+    // ------------------------------------------------------------------------------------------
+    template <typename T> struct TmAcc;
+    template <> struct TmAcc<double>
+    {
+        static __device__ __forceinline__ Vec<double> ld(uint32_t taddr)
+        {
+            uint32_t a, b, c, d;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
+            Vec<double> v;
+            v.e[0] = __hiloint2double((int)b, (int)a);
+            v.e[1] = __hiloint2double((int)d, (int)c);
+            return v;
+        }
+        static __device__ __forceinline__ void st(uint32_t taddr, const Vec<double> &v)
+        {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__double2loint(v.e[0])), "r"(__double2hiint(v.e[0])),
+                         "r"(__double2loint(v.e[1])), "r"(__double2hiint(v.e[1]))
+                         : "memory");
+        }
+    };
+    template <> struct TmAcc<float>
+    {
+        static __device__ __forceinline__ Vec<float> ld(uint32_t taddr)
+        {
+            Vec<float> v;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(v.e[0]), "=f"(v.e[1]), "=f"(v.e[2]), "=f"(v.e[3]) : "r"(taddr) : "memory");
+            return v;
+        }
+        static __device__ __forceinline__ void st(uint32_t taddr, const Vec<float> &v)
+        {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(v.e[0]), "f"(v.e[1]), "f"(v.e[2]), "f"(v.e[3]) : "memory");
+        }
+    };
+    __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+    __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
     // compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N-1>)
     template <typename F, int... K>
     __device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, K...>) { (f(std::integral_constant<int, K>{}), ...); }
@@ -187,6 +229,9 @@ namespace b200
         // global-memory residency: per-CTA state block
         unsigned char *state;
         size_t state_stride;
+        // TMEM mirror (TM kernels): columns allocated per CTA (power of two >= 32), columns per warp window,
+        // column offset of the variable-side (channel LLR) part inside a warp window
+        uint32_t tm_alloc_cols, tm_cols_per_warp, tm_vn_off;
     };
 
     // raw value of smaller magnitude (min-sum keeps raw values; magnitude and sign are fixed at the store)
@@ -214,7 +259,10 @@ namespace b200
         typedef Vec<T> V;
         static constexpr int VEC = V::N, CS = 512;
 
-        static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, P ip)
+        // CSRC: the old c2v values come from shared/global memory (0) or from the thread's TMEM mirror at
+        // columns tc + 4k (1); TMW: new values are also written to that mirror.
+        template <int CSRC, bool TMW>
+        static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, P ip, uint32_t tc)
         {
             uint32_t eo[D];
             IdxLoad<SMEM, IdxT, LANES, D>::load(ip, eo);
@@ -231,7 +279,9 @@ namespace b200
                 for (int e = 0; e < VEC; ++e) { m1[e] = Num<T>::inf(); m2[e] = Num<T>::inf(); arg[e] = 0; sm[e] = 0; }
                 static_for<D>([&](auto k) {
                     const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[k.value]);
-                    const V c = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
+                    V c;
+                    if constexpr (CSRC == 1) { c = TmAcc<T>::ld(tc + 4 * k.value); tm_wait_ld(); }
+                    else c = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
 #pragma unroll
                     for (int e = 0; e < VEC; ++e)
                     {
@@ -252,18 +302,23 @@ namespace b200
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) r.e[e] = mag_sign((arg[e] == (uint32_t)k.value) ? m2[e] : m1[e], sm[e] << (31 - k.value));
                     VAcc<SMEM, T, k.value * CS>::st(c2v0, r);
+                    if constexpr (TMW) TmAcc<T>::st(tc + 4 * k.value, r);
                 });
             }
             else
             {
-                V v[D], r[D];
+                V v[D], r[D], c[D];
+                static_for<D>([&](auto k) {
+                    if constexpr (CSRC == 1) c[k.value] = TmAcc<T>::ld(tc + 4 * k.value);
+                    else c[k.value] = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
+                });
+                if constexpr (CSRC == 1) tm_wait_ld();
                 static_for<D>([&](auto k) {
                     const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[k.value]);
-                    const V c = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
 #pragma unroll
                     for (int e = 0; e < VEC; ++e)
                     {
-                        v[k.value].e[e] = o.e[e] - c.e[e];
+                        v[k.value].e[e] = o.e[e] - c[k.value].e[e];
                         par[e] ^= (o.e[e] <= T(0));
                     }
                 });
@@ -310,7 +365,10 @@ namespace b200
                         r[0].e[e] = B;
                     }
                 }
-                static_for<D>([&](auto k) { VAcc<SMEM, T, k.value * CS>::st(c2v0, r[k.value]); });
+                static_for<D>([&](auto k) {
+                    VAcc<SMEM, T, k.value * CS>::st(c2v0, r[k.value]);
+                    if constexpr (TMW) TmAcc<T>::st(tc + 4 * k.value, r[k.value]);
+                });
             }
             uint32_t bits = 0;
 #pragma unroll
@@ -486,9 +544,11 @@ namespace b200
     // ------------------------------------------------------------------------------------------
     // the persistent kernel
     // ------------------------------------------------------------------------------------------
-    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES>
-    __global__ void __launch_bounds__(ALG == ALG_MS ? 1024 : 512, 1) tile4_kernel(const K4Params p)
+    // TM: keep the write-through TMEM mirror (K4Params::tm_*; shared-memory residency only).
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM>
+    __global__ void __launch_bounds__(512, (SMEM || ALG == ALG_BP) ? 1 : 2) tile4_kernel(const K4Params p)
     {
+        static_assert(SMEM || !TM, "the TMEM mirror belongs to shared-memory residency");
         typedef typename PtrOf<SMEM>::type P;
         typedef Vec<T> V;
         constexpr int VEC = V::N, FPC = LANES * VEC, NPW = 32 / LANES;
@@ -501,7 +561,7 @@ namespace b200
         __shared__ uint32_t s_synd[2];
         __shared__ uint2 s_ctrl[2]; // {frames at the iteration limit, frames with >= 1 completed iteration}
         __shared__ int s_ret[FPC];
-        __shared__ uint32_t s_active, s_skip, s_next;
+        __shared__ uint32_t s_active, s_skip, s_next, s_tmem;
 
         const int tid = threadIdx.x, nthreads = blockDim.x;
         const int lane = tid & 31, warp = tid >> 5, warps = nthreads >> 5;
@@ -535,6 +595,19 @@ namespace b200
             cn_seg = (unsigned char *)p.cn_seg; vn_seg = (unsigned char *)p.vn_seg;
             cn_idx = (unsigned char *)p.cn_idx; vn_idx = (unsigned char *)p.vn_idx;
         }
+        uint32_t tm_w = 0; // this warp's TMEM window: lane partition (warp % 4), columns (warp / 4) * tm_cols_per_warp ...
+        if constexpr (TM)
+        {
+            if (warp == 0)
+            {
+                asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "r"(p.tm_alloc_cols) : "memory");
+                asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tm_w = s_tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * p.tm_cols_per_warp;
+        }
         if (tid < 5) s_cnt[tid] = 0;
         if (tid < FPC) { s_err[tid] = 0; s_frame[tid] = 0; s_old[tid] = 0; s_ret[tid] = 0; }
         if (tid == 0)
@@ -547,6 +620,9 @@ namespace b200
         // per-frame iteration counter: lane g of warp 0 owns frame lane g
         int it = 0;
         uint32_t active = 0, skip = 0; // CTA-uniform copies of s_active / s_skip
+        // A refill rewrites c2v / llr in shared memory behind the TMEM mirror's back: the next check phase and the
+        // next variable phase read shared memory (and refresh the mirror).  CTA-uniform.
+        bool cn_stale = true, vn_stale = true;
 
         // Writes the decoder input of global frame gf into frame lane g (all threads of the CTA
         // cooperate), with the fresh-frame state: out = LLRin, c2v = +0.
@@ -682,6 +758,8 @@ namespace b200
             __syncthreads();
             active = new_active;
             skip = s_skip;
+            cn_stale = true;
+            vn_stale = true;
         };
 
         retire_and_refill(ALL, 0, 0, false, true);
@@ -710,16 +788,20 @@ namespace b200
 
             // ---- check-node phase (+ syndrome of the previous iteration's decisions) ----------
             uint32_t bad = 0;
-            for (P sp = cn_seg_w;; sp += 16)
+            auto cn_phase = [&](auto csrc)
             {
-                const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
-                if (sg.x == 0) break;
-                // threads of nodes missing from a ragged task run along on padded slots / zero index entries
-                const int deg = (int)(sg.x & 0xFFu);
-                const uint32_t keep = (j < (int)((sg.x >> 8) & 0xFFu)) ? 0xFFFFFFFFu : 0u;
-                int nt = (int)(sg.x >> 16);
-                P c2v0 = c2v_lane + sg.y;
-                const P ib = cn_idx + sg.z;
+                constexpr int CSRC = decltype(csrc)::value;
+                uint32_t tc = tm_w;
+                for (P sp = cn_seg_w;; sp += 16)
+                {
+                    const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
+                    if (sg.x == 0) break;
+                    // threads of nodes missing from a ragged task run along on padded slots / zero index entries
+                    const int deg = (int)(sg.x & 0xFFu);
+                    const uint32_t keep = (j < (int)((sg.x >> 8) & 0xFFu)) ? 0xFFFFFFFFu : 0u;
+                    int nt = (int)(sg.x >> 16);
+                    P c2v0 = c2v_lane + sg.y;
+                    const P ib = cn_idx + sg.z;
 #define B200_CN_CASE(D)                                                                                      \
     case D:                                                                                                  \
     {                                                                                                        \
@@ -727,36 +809,42 @@ namespace b200
         P ip = ib + j * (ST < 16 ? ST : 16);                                                                 \
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
-            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::run(out_sub, c2v0, ip) & keep;                         \
+            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM>(out_sub, c2v0, ip, tc) & keep;  \
             c2v0 += D * 512;                                                                                 \
             ip += NPW * ST;                                                                                  \
+            if constexpr (TM) tc += 4 * D;                                                                   \
         }                                                                                                    \
         break;                                                                                               \
     }
-                switch (deg) // warp-uniform
-                {
-                    B200_CN_CASE(2)
-                    B200_CN_CASE(3)
-                    B200_CN_CASE(4)
-                    B200_CN_CASE(5)
-                    B200_CN_CASE(6)
-                    B200_CN_CASE(7)
-                    B200_CN_CASE(8)
-                default:
-                {
-                    const int st = idx_stride_of(deg, ISZ);
-                    P ip = ib + j * 16;
-                    for (; nt > 0; --nt)
+                    switch (deg) // warp-uniform
                     {
-                        bad |= cn4_any<T, IdxT, SMEM, LANES, ALG>(out_sub, c2v0, ip, deg) & keep;
-                        c2v0 += deg * 512;
-                        ip += NPW * st;
+                        B200_CN_CASE(2)
+                        B200_CN_CASE(3)
+                        B200_CN_CASE(4)
+                        B200_CN_CASE(5)
+                        B200_CN_CASE(6)
+                        B200_CN_CASE(7)
+                        B200_CN_CASE(8)
+                    default: // not mirrored: always served from shared / global memory
+                    {
+                        const int st = idx_stride_of(deg, ISZ);
+                        P ip = ib + j * 16;
+                        for (; nt > 0; --nt)
+                        {
+                            bad |= cn4_any<T, IdxT, SMEM, LANES, ALG>(out_sub, c2v0, ip, deg) & keep;
+                            c2v0 += deg * 512;
+                            ip += NPW * st;
+                        }
+                        break;
                     }
-                    break;
-                }
-                }
+                    }
 #undef B200_CN_CASE
-            }
+                }
+                if constexpr (TM) tm_wait_st();
+            };
+            if (TM && !cn_stale) cn_phase(std::integral_constant<int, TM ? 1 : 0>{});
+            else cn_phase(std::integral_constant<int, 0>{});
+            cn_stale = false;
             // syndrome flags per frame lane: frame = sub*VEC + e
             {
                 const uint32_t m = __reduce_or_sync(0xffffffffu, bad << (sub * VEC));
@@ -784,8 +872,10 @@ namespace b200
 
             // ---- variable-node phase: posterior (hard decision = its sign, taken where it is consumed) ----
             const uint32_t mylive = (live >> (sub * VEC)) & VMASK;
-            if (live)
+            auto vn_phase = [&](auto lsrc)
             {
+                constexpr int LSRC = decltype(lsrc)::value;
+                uint32_t tl = tm_w + p.tm_vn_off;
                 for (P sp = vn_seg_w;; sp += 16)
                 {
                     const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
@@ -794,6 +884,17 @@ namespace b200
                     int nt = (int)(sg.x >> 16);
                     P lp = llr_lane + sg.y, op = out_lane + sg.y;
                     const P ib = vn_idx + sg.z;
+                    auto channel_llr = [&]() -> V // decoder.cpp:50
+                    {
+                        V a;
+                        if constexpr (LSRC == 1) { a = TmAcc<T>::ld(tl); tm_wait_ld(); }
+                        else
+                        {
+                            a = VAcc<SMEM, T, 0>::ld(lp);
+                            if constexpr (TM) TmAcc<T>::st(tl, a);
+                        }
+                        return a;
+                    };
                     auto finish = [&](const V &acc)
                     {
                         if (mylive == VMASK) VAcc<SMEM, T, 0>::st(op, acc);
@@ -805,6 +906,7 @@ namespace b200
                         }
                         lp += 512;
                         op += 512;
+                        if constexpr (TM) tl += 4;
                     };
 #define B200_VN_CASE(D)                                                                                      \
     case D:                                                                                                  \
@@ -813,7 +915,7 @@ namespace b200
         P ip = ib + j * (ST < 16 ? ST : 16);                                                                 \
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
-            finish(Vn4<T, IdxT, SMEM, LANES, D>::run(c2v_sub, ip, VAcc<SMEM, T, 0>::ld(lp))); /* decoder.cpp:50 */ \
+            finish(Vn4<T, IdxT, SMEM, LANES, D>::run(c2v_sub, ip, channel_llr()));                           \
             ip += NPW * ST;                                                                                  \
         }                                                                                                    \
         break;                                                                                               \
@@ -821,7 +923,7 @@ namespace b200
                     switch (deg)
                     {
                     case 0:
-                        for (; nt > 0; --nt) finish(VAcc<SMEM, T, 0>::ld(lp));
+                        for (; nt > 0; --nt) finish(channel_llr());
                         break;
                         B200_VN_CASE(1)
                         B200_VN_CASE(2)
@@ -837,7 +939,7 @@ namespace b200
                         P ip = ib + j * 16;
                         for (; nt > 0; --nt)
                         {
-                            finish(vn4_any<T, IdxT, SMEM, LANES>(c2v_sub, ip, deg, VAcc<SMEM, T, 0>::ld(lp)));
+                            finish(vn4_any<T, IdxT, SMEM, LANES>(c2v_sub, ip, deg, channel_llr()));
                             ip += NPW * st;
                         }
                         break;
@@ -845,6 +947,13 @@ namespace b200
                     }
 #undef B200_VN_CASE
                 }
+                if constexpr (TM && LSRC == 0) tm_wait_st();
+            };
+            if (live)
+            {
+                if (TM && !vn_stale) vn_phase(std::integral_constant<int, TM ? 1 : 0>{});
+                else vn_phase(std::integral_constant<int, 0>{});
+                vn_stale = false;
             }
             skip = 0;
             __syncthreads(); // A: variable-phase writes visible to the next check phase
@@ -852,5 +961,9 @@ namespace b200
 
         __syncthreads();
         if (tid < 5 && s_cnt[tid]) atomicAdd(&p.counters[tid], s_cnt[tid]);
+        if constexpr (TM)
+        {
+            if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(p.tm_alloc_cols) : "memory");
+        }
     }
 } // namespace b200

@@ -9,51 +9,52 @@
 
 namespace b200
 {
-    // Index entries: 32-bit byte offsets, or (shared-memory residency only) 16-bit offsets in 16-byte units.
+    // Three variants per (T, ALG, lanes): shared-memory residency with / without the TMEM mirror, global
+    // residency.  Index entries are 32-bit byte offsets.
     // lanes = warp lanes per node (frames per CTA = lanes * 16/sizeof(T)).
     template <typename T, int ALG>
-    void launch_tile_family(const K4Params &kp, bool smem, bool idx16, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
+    void launch_tile_family(const K4Params &kp, bool smem, bool tm, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
 
     // resident CTAs per SM the runtime grants this configuration (occupancy query; 0 = does not fit)
     template <typename T, int ALG>
-    int tile_family_occupancy(bool smem, bool idx16, int lanes, int threads, size_t smem_bytes);
+    int tile_family_occupancy(bool smem, bool tm, int lanes, int threads, size_t smem_bytes);
 
     constexpr int TILE_SMEM_OPTIN = 232448 - 1024; // 227 KB minus the kernel's static shared memory
 
-    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES>
+    template <typename T, int ALG, bool SMEM, int LANES, bool TM>
     void prepare_tile_one()
     {
         static bool attr_set = false;
         if (SMEM && !attr_set)
         {
-            cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, IdxT, ALG, SMEM, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
+            cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
             if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
             attr_set = true;
         }
     }
 
-    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES>
+    template <typename T, int ALG, bool SMEM, int LANES, bool TM>
     void launch_tile_one(const K4Params &kp, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
     {
-        prepare_tile_one<T, IdxT, ALG, SMEM, LANES>();
-        tile4_kernel<T, IdxT, ALG, SMEM, LANES><<<ctas, threads, SMEM ? smem_bytes : 0, s>>>(kp);
+        prepare_tile_one<T, ALG, SMEM, LANES, TM>();
+        tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM><<<ctas, threads, SMEM ? smem_bytes : 0, s>>>(kp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " (tile kernel launch)");
     }
 
-    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES>
+    template <typename T, int ALG, bool SMEM, int LANES, bool TM>
     int occupancy_tile_one(int threads, size_t smem_bytes)
     {
-        prepare_tile_one<T, IdxT, ALG, SMEM, LANES>();
+        prepare_tile_one<T, ALG, SMEM, LANES, TM>();
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile4_kernel<T, IdxT, ALG, SMEM, LANES>, threads, SMEM ? smem_bytes : 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM>, threads, SMEM ? smem_bytes : 0);
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
         return n;
     }
 
 #define B200_DEFINE_TILE_FAMILY(T, ALG)                                                                                \
     template <>                                                                                                        \
-    void launch_tile_family<T, ALG>(const K4Params &kp, bool smem, bool idx16, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
+    void launch_tile_family<T, ALG>(const K4Params &kp, bool smem, bool tm, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
     {                                                                                                                  \
         switch (lanes)                                                                                                 \
         {                                                                                                              \
@@ -62,7 +63,7 @@ namespace b200
         }                                                                                                              \
     }                                                                                                                  \
     template <>                                                                                                        \
-    int tile_family_occupancy<T, ALG>(bool smem, bool idx16, int lanes, int threads, size_t smem_bytes)                \
+    int tile_family_occupancy<T, ALG>(bool smem, bool tm, int lanes, int threads, size_t smem_bytes)                \
     {                                                                                                                  \
         switch (lanes)                                                                                                 \
         {                                                                                                              \
@@ -74,15 +75,15 @@ namespace b200
 
 #define B200_LAUNCH_CASE(T, ALG, L)                                                                                    \
     case L:                                                                                                            \
-        if (smem && idx16) launch_tile_one<T, uint16_t, ALG, true, L>(kp, ctas, threads, smem_bytes, s);               \
-        else if (smem) launch_tile_one<T, uint32_t, ALG, true, L>(kp, ctas, threads, smem_bytes, s);                   \
-        else launch_tile_one<T, uint32_t, ALG, false, L>(kp, ctas, threads, 0, s);                                     \
+        if (smem && tm) launch_tile_one<T, ALG, true, L, true>(kp, ctas, threads, smem_bytes, s);                      \
+        else if (smem) launch_tile_one<T, ALG, true, L, false>(kp, ctas, threads, smem_bytes, s);                      \
+        else launch_tile_one<T, ALG, false, L, false>(kp, ctas, threads, 0, s);                                        \
         return;
 #define B200_OCC_CASE(T, ALG, L)                                                                                       \
     case L:                                                                                                            \
-        return (smem && idx16) ? occupancy_tile_one<T, uint16_t, ALG, true, L>(threads, smem_bytes)                    \
-               : smem          ? occupancy_tile_one<T, uint32_t, ALG, true, L>(threads, smem_bytes)                    \
-                               : occupancy_tile_one<T, uint32_t, ALG, false, L>(threads, 0);
+        return (smem && tm) ? occupancy_tile_one<T, ALG, true, L, true>(threads, smem_bytes)                           \
+               : smem       ? occupancy_tile_one<T, ALG, true, L, false>(threads, smem_bytes)                          \
+                            : occupancy_tile_one<T, ALG, false, L, false>(threads, 0);
 #define B200_TILE_LAUNCH_CASES(T, ALG) B200_LAUNCH_CASE(T, ALG, 1) B200_LAUNCH_CASE(T, ALG, 2) B200_LAUNCH_CASE(T, ALG, 4) B200_LAUNCH_CASE(T, ALG, 8)
 #define B200_TILE_OCC_CASES(T, ALG) B200_OCC_CASE(T, ALG, 1) B200_OCC_CASE(T, ALG, 2) B200_OCC_CASE(T, ALG, 4) B200_OCC_CASE(T, ALG, 8)
 } // namespace b200
