@@ -16,6 +16,10 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", "/usr/bin/g++", "-Xcompile
 SOURCES = ["tile_ms_f64.cu", "tile_ms_f32.cu", "tile_bp_f64.cu", "tile_bp_f32.cu", "engine.cu", "code.cpp", "sim_driver.cpp", "shim.cpp"]
 HEADERS = ["engine.hpp", "code.hpp", "kernels.cuh", "tile4.cuh", "tile_launch.cuh", "bec_kernel.cuh", "../../include/ldpc_b200.h"]
 OBJDIR = os.path.join(HERE, "build")
+if os.environ.get("B200_PHASE_TIMING"):  # debug: per-warp phase cycle counts printed by CTA 0
+    COMMON = COMMON + ["-DB200_PHASE_TIMING=1"]
+if os.environ.get("B200_TILE_MAX_THREADS"):  # tuning experiments only; the default lives in csrc/tile4.cuh
+    COMMON = COMMON + ["-DB200_TILE_MAX_THREADS=" + os.environ["B200_TILE_MAX_THREADS"]]
 
 
 def _stale(target, deps):

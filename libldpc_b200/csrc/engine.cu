@@ -177,7 +177,7 @@ namespace b200
     {
         const int vec = precision == LDPC_B200_F32 ? 4 : 2;
         (void)alg;
-        const int max_threads = 512; // the kernels are compiled for <= 512 threads (128 registers/thread at one CTA per SM)
+        const int max_threads = B200_TILE_MAX_THREADS; // compile-time cap of the kernels (tile4.cuh)
         const int threads = tuning.threads_per_cta > 0 ? std::min(tuning.threads_per_cta, max_threads) : max_threads;
         int want_lanes = 0;
         if (tuning.frames_per_cta > 0)

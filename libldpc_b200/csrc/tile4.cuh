@@ -28,6 +28,7 @@
 // refilled at once with the next frame (LLRs regenerated from the counter-based Philox stream), so
 // early termination never leaves lanes idle waiting for the slowest frame of a batch.
 #pragma once
+#include <cstdio>
 #include <utility>
 
 #include "kernels.cuh"
@@ -544,9 +545,12 @@ namespace b200
     // ------------------------------------------------------------------------------------------
     // the persistent kernel
     // ------------------------------------------------------------------------------------------
+#ifndef B200_TILE_MAX_THREADS
+#define B200_TILE_MAX_THREADS 512 // compile-time cap of threads per CTA (register budget = 65536 / cap)
+#endif
     // TM: keep the write-through TMEM mirror (K4Params::tm_*; shared-memory residency only).
     template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM>
-    __global__ void __launch_bounds__(512, (SMEM || ALG == ALG_BP) ? 1 : 2) tile4_kernel(const K4Params p)
+    __global__ void __launch_bounds__(B200_TILE_MAX_THREADS, (SMEM || ALG == ALG_BP) ? 1 : (1024 / B200_TILE_MAX_THREADS)) tile4_kernel(const K4Params p)
     {
         static_assert(SMEM || !TM, "the TMEM mirror belongs to shared-memory residency");
         typedef typename PtrOf<SMEM>::type P;
@@ -768,6 +772,9 @@ namespace b200
         const P out_lane = out + lane * 16, llr_lane = llr + lane * 16;
         const P cn_seg_w = cn_seg + 16 * p.cn_max_segs * warp, vn_seg_w = vn_seg + 16 * p.vn_max_segs * warp;
 
+#ifdef B200_PHASE_TIMING
+        long long pt_cn = 0, pt_wb = 0, pt_vn = 0, pt_wa = 0, pt_n = 0, pt_hdr = 0, pt_nseg = 0, pt_ntask = 0;
+#endif
         for (uint32_t L = 0;; ++L)
         {
             const int par_i = (int)(L & 1u);
@@ -787,6 +794,9 @@ namespace b200
             }
 
             // ---- check-node phase (+ syndrome of the previous iteration's decisions) ----------
+#ifdef B200_PHASE_TIMING
+            const long long pt0 = clock64();
+#endif
             uint32_t bad = 0;
             auto cn_phase = [&](auto csrc)
             {
@@ -794,6 +804,9 @@ namespace b200
                 uint32_t tc = tm_w;
                 for (P sp = cn_seg_w;; sp += 16)
                 {
+#ifdef B200_PHASE_TIMING
+                    const long long ph0 = clock64();
+#endif
                     const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
                     if (sg.x == 0) break;
                     // threads of nodes missing from a ragged task run along on padded slots / zero index entries
@@ -802,11 +815,17 @@ namespace b200
                     int nt = (int)(sg.x >> 16);
                     P c2v0 = c2v_lane + sg.y;
                     const P ib = cn_idx + sg.z;
+#ifdef B200_PHASE_TIMING
+#define B200_PT_HDR pt_hdr += clock64() - ph0; pt_nseg += 1; pt_ntask += nt;
+#else
+#define B200_PT_HDR
+#endif
 #define B200_CN_CASE(D)                                                                                      \
     case D:                                                                                                  \
     {                                                                                                        \
         constexpr int ST = idx_stride_of(D, ISZ);                                                            \
         P ip = ib + j * (ST < 16 ? ST : 16);                                                                 \
+        B200_PT_HDR                                                                                          \
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
             bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM>(out_sub, c2v0, ip, tc) & keep;  \
@@ -850,7 +869,13 @@ namespace b200
                 const uint32_t m = __reduce_or_sync(0xffffffffu, bad << (sub * VEC));
                 if (lane == 0 && m) atomicOr(&s_synd[par_i], m);
             }
+#ifdef B200_PHASE_TIMING
+            const long long pt1 = clock64();
+#endif
             __syncthreads(); // B
+#ifdef B200_PHASE_TIMING
+            const long long pt2 = clock64();
+#endif
 
             // ---- decision: converged (decoder.cpp:66-72) or out of iterations ---------------------
             {
@@ -956,8 +981,20 @@ namespace b200
                 vn_stale = false;
             }
             skip = 0;
+#ifdef B200_PHASE_TIMING
+            const long long pt3 = clock64();
+#endif
             __syncthreads(); // A: variable-phase writes visible to the next check phase
+#ifdef B200_PHASE_TIMING
+            const long long pt4 = clock64();
+            pt_cn += pt1 - pt0; pt_wb += pt2 - pt1; pt_vn += pt3 - pt2; pt_wa += pt4 - pt3; ++pt_n;
+#endif
         }
+#ifdef B200_PHASE_TIMING
+        if (blockIdx.x == 0 && lane == 0)
+            printf("warp %2d: iterations %lld  check %lld  wait-B %lld  decision+variable %lld  wait-A %lld  (cycles per iteration); check segments/it %lld tasks/it %lld header cycles/seg %lld\n", warp, pt_n,
+                   pt_cn / pt_n, pt_wb / pt_n, pt_vn / pt_n, pt_wa / pt_n, pt_nseg / pt_n, pt_ntask / pt_n, pt_hdr / (pt_nseg ? pt_nseg : 1));
+#endif
 
         __syncthreads();
         if (tid < 5 && s_cnt[tid]) atomicAdd(&p.counters[tid], s_cnt[tid]);

@@ -12,10 +12,10 @@ dec = sys.argv[1] if len(sys.argv) > 1 else "BP_MS"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 4 * 128
 ctx = api.Context(os.path.join(ROOT, "codes", "ref_h_n1152_m1024.txt"), "", device=0)
 for prec, pname, vec in ((api.F64, "f64", 2), (api.F32, "f32", 4)):
-    for lanes in (1, 2):
-        for threads in (256, 512):
+    for lanes in [int(t) for t in os.environ.get('AB_LANES', '1,2').split(',')]:
+        for threads in [int(t) for t in os.environ.get('AB_THREADS', '256,512').split(',')]:
             for tmem in (1, 0):
-                for et in (False, True):
+                for et in ((False, True) if os.environ.get('AB_ET', '1') == '1' else (False,)):
                     try:
                         ctx.set_tuning(precision=prec, residency=api.SMEM, frames_per_cta=lanes * vec, threads_per_cta=threads, ctas=0, tmem=tmem)
                         ctx.sim_point("AWGN", -4.5, nframes=2000, decoding=dec, iterations=50, early_term=et)
