@@ -203,6 +203,9 @@ typedef struct
     size_t smem_bytes;
 } ldpc_b200_stats;
 int ldpc_b200_get_stats(const ldpc_b200_ctx *ctx, ldpc_b200_stats *s);
+/* Measurement aid: sustained shared-memory read bandwidth of the context's device in GB/s (a conflict-free
+ * LDS.128 streaming kernel on every SM) — the roofline that bounds the shared-memory-resident decode kernel. */
+int ldpc_b200_smem_probe(ldpc_b200_ctx *ctx, double *gb_per_s);
 int ldpc_b200_reset_stats(ldpc_b200_ctx *ctx);
 
 #ifdef __cplusplus

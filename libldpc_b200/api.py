@@ -58,7 +58,7 @@ HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device
                   "ldpc_b200_get_puncture", "ldpc_b200_get_layout", "ldpc_b200_rank", "ldpc_b200_encode", "ldpc_b200_syndrome",
                   "ldpc_b200_decode_batch", "ldpc_b200_decode_batch_device", "ldpc_b200_decode_bec_batch", "ldpc_b200_channel",
                   "ldpc_b200_sim_point", "ldpc_b200_sim_point_async", "ldpc_b200_simulate", "ldpc_b200_simulate_ex", "ldpc_b200_get_stats",
-                  "ldpc_b200_reset_stats")
+                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe")
 
 _lib = None
 
@@ -102,6 +102,7 @@ def load_library(path=None):
                                         ct.c_int, ct.c_int, ALLREDUCE_FN, ROUND_FN, vp, ct.c_int]
     L.ldpc_b200_get_stats.argtypes = [vp, ct.POINTER(stats)]
     L.ldpc_b200_reset_stats.argtypes = [vp]
+    L.ldpc_b200_smem_probe.argtypes = [vp, ct.POINTER(ct.c_double)]
     if path is None:
         _lib = L
     return L
@@ -190,13 +191,20 @@ class Context:
     def _dp(decoding, iterations, early_term):
         return decoder_param(bool(early_term), int(iterations), decoding.encode())
 
-    def decode_batch(self, llr, decoding="BP", iterations=50, early_term=True, want_llr=True, want_hard=True):
-        """llr [n, nc] float64 (full length) -> (llr_out [n,nc], hard [n,nc] u8, iters [n] i32)."""
+    def decode_batch(self, llr, decoding="BP", iterations=50, early_term=True, want_llr=True, want_hard=True, out=None, hard=None, its=None):
+        """llr [n, nc] float64 (full length) -> (llr_out [n,nc], hard [n,nc] u8, iters [n] i32).
+        out / hard / its may be caller-provided C-contiguous arrays (e.g. views of pinned host memory)."""
         llr = np.ascontiguousarray(llr, np.float64).reshape(-1, self.nc)
         n = llr.shape[0]
-        out = np.empty_like(llr) if want_llr else None
-        hard = np.empty((n, self.nc), np.uint8) if want_hard else None
-        its = np.empty(n, np.int32)
+        if out is None and want_llr:
+            out = np.empty_like(llr)
+        if hard is None and want_hard:
+            hard = np.empty((n, self.nc), np.uint8)
+        if its is None:
+            its = np.empty(n, np.int32)
+        assert out is None or (out.dtype == np.float64 and out.size == n * self.nc and out.flags.c_contiguous)
+        assert hard is None or (hard.dtype == np.uint8 and hard.size == n * self.nc and hard.flags.c_contiguous)
+        assert its.dtype == np.int32 and its.size == n and its.flags.c_contiguous
         self._check(self.lib.ldpc_b200_decode_batch(self._h, self._dp(decoding, iterations, early_term), _p(llr, ct.c_double), n,
                                                     _p(out, ct.c_double), _p(hard, ct.c_uint8), _p(its, ct.c_int32)))
         return out, hard, its
@@ -254,6 +262,12 @@ class Context:
                                                    int(rank), int(world), cb, rf, None, int(bool(quiet))))
         n = int(np.sum(np.array(res.frames[0:max_points]) > 0))
         return {k: np.array(getattr(res, k)[0:n]) for k, _ in sim_results_t._fields_}
+
+    def smem_probe(self):
+        """Sustained shared-memory read bandwidth of this device, GB/s."""
+        v = ct.c_double()
+        self._check(self.lib.ldpc_b200_smem_probe(self._h, ct.byref(v)))
+        return float(v.value)
 
     def stats(self, reset=False):
         s = stats()

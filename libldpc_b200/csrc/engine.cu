@@ -116,6 +116,15 @@ namespace b200
         dev_layouts_.clear();
         dev_seg_layouts_.clear();
         cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
+        for (int b = 0; b < 2; ++b)
+        {
+            cudaFree(db_in_[b]); cudaFree(db_out_[b]); cudaFree(db_hard_[b]); cudaFree(db_it_[b]);
+            if (ev_in_[b]) cudaEventDestroy((cudaEvent_t)ev_in_[b]);
+            if (ev_k_[b]) cudaEventDestroy((cudaEvent_t)ev_k_[b]);
+            if (ev_out_[b]) cudaEventDestroy((cudaEvent_t)ev_out_[b]);
+        }
+        if (copy_in_) cudaStreamDestroy((cudaStream_t)copy_in_);
+        if (copy_out_) cudaStreamDestroy((cudaStream_t)copy_out_);
         if (ev0_) cudaEventDestroy((cudaEvent_t)ev0_);
         if (ev1_) cudaEventDestroy((cudaEvent_t)ev1_);
         if (stream_) cudaStreamDestroy((cudaStream_t)stream_);
@@ -341,6 +350,62 @@ namespace b200
         state_bytes_ = bytes;
     }
 
+    // Shared-memory streaming probe: every CTA (1024 threads, one per SM) reads a 128 KB window with
+    // conflict-free LDS.128 (each warp 512 contiguous bytes per instruction), 8 loads in flight per thread.
+    // Gives the sustained shared-memory read bandwidth of this device under load — the roofline that applies
+    // to the shared-memory-resident decode kernel.
+    __global__ void __launch_bounds__(1024, 1) smem_probe_kernel(int iters, uint32_t stride, const uint32_t *__restrict__ offs, uint32_t *sink)
+    {
+        extern __shared__ __align__(16) unsigned char probe_smem[];
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(probe_smem) + threadIdx.x * 16u;
+        for (int i = threadIdx.x; i < 8 * 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(probe_smem)[i] = i;
+        uint32_t o[8]; // run-time block offsets (u * 16 KB): keeps the address stream opaque to the compiler
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = offs[u];
+        __syncthreads();
+        uint32_t acc = 0, off = 0;
+        for (int i = 0; i < iters; ++i)
+        {
+            uint32_t v[8][4];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "r"(base + ((off + o[u]) & 0x1FFFFu)) : "memory");
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u][0] ^ v[u][1] ^ v[u][2] ^ v[u][3];
+            off += stride;
+        }
+        sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    }
+
+    double Engine::smem_probe()
+    {
+        ensure_cuda();
+        const int iters = 4096, threads = 1024, smem = 8 * 16384;
+        CUDA_OK(cudaFuncSetAttribute(smem_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        uint32_t *sink = nullptr, *offs = nullptr;
+        CUDA_OK(cudaMalloc(&sink, (size_t)sm_count_ * threads * sizeof(uint32_t)));
+        CUDA_OK(cudaMalloc(&offs, 8 * sizeof(uint32_t)));
+        uint32_t h[8];
+        for (int u = 0; u < 8; ++u) h[u] = (uint32_t)u * 16384u;
+        CUDA_OK(cudaMemcpy(offs, h, sizeof(h), cudaMemcpyHostToDevice));
+        cudaStream_t s = (cudaStream_t)stream_;
+        double best = 0;
+        for (int rep = 0; rep < 4; ++rep)
+        {
+            CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
+            smem_probe_kernel<<<sm_count_, threads, smem, s>>>(iters, 16384u, offs, sink);
+            CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));
+            CUDA_OK(cudaEventSynchronize((cudaEvent_t)ev1_));
+            float ms = 0;
+            CUDA_OK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
+            const double gbs = (double)sm_count_ * threads * 16.0 * 8.0 * iters / (ms * 1e-3) / 1e9;
+            if (rep > 0) best = std::max(best, gbs);
+        }
+        cudaFree(sink);
+        cudaFree(offs);
+        return best;
+    }
+
     int Engine::channel_kind(const std::string &name)
     {
         if (name == "AWGN") return SRC_AWGN;
@@ -493,54 +558,82 @@ namespace b200
         stats.edge_iterations += h[4] * (uint64_t)H.nnz;
     }
 
+    // Host-buffer batch decode: a double-buffered pipeline over three streams — H2D of chunk k+1, the decode
+    // kernel of chunk k and D2H of chunk k-1 overlap (kernels stay on ONE stream, so the per-CTA state block of
+    // global residency is never shared by two launches).  Device buffers are cached in the engine.  With pinned
+    // caller buffers the copies run at full PCIe rate; pageable buffers work too (the driver stages them).
     void Engine::decode_batch_host(const decoder_param &dp, const double *llr, int64_t n, double *llr_out, uint8_t *hard, int32_t *iters)
     {
         if (n <= 0) return;
         ensure_cuda();
-        cudaStream_t s = (cudaStream_t)stream_;
+        cudaStream_t sk = (cudaStream_t)stream_;
         const size_t nc = H.nc;
-        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((512ull << 20) / (nc * sizeof(double)))));
-        double *d_in = nullptr, *d_out = nullptr;
-        uint8_t *d_hard = nullptr;
-        int32_t *d_it = nullptr;
-        CUDA_OK(cudaMalloc(&d_in, chunk * nc * sizeof(double)));
-        if (llr_out) CUDA_OK(cudaMalloc(&d_out, chunk * nc * sizeof(double)));
-        if (hard) CUDA_OK(cudaMalloc(&d_hard, chunk * nc));
-        if (iters) CUDA_OK(cudaMalloc(&d_it, chunk * sizeof(int32_t)));
-        try
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, std::max<int64_t>((int64_t)((48ull << 20) / (nc * sizeof(double))), 1184)));
+        if (!copy_in_)
         {
-            for (int64_t o = 0; o < n; o += chunk)
+            CUDA_OK(cudaStreamCreateWithFlags((cudaStream_t *)&copy_in_, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags((cudaStream_t *)&copy_out_, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b)
             {
-                const int64_t m = std::min(chunk, n - o);
-                CUDA_OK(cudaMemcpyAsync(d_in, llr + o * nc, m * nc * sizeof(double), cudaMemcpyHostToDevice, s));
-                CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), s));
-                FrameSource src;
-                src.kind = SRC_LLR;
-                src.d_llr = d_in;
-                FrameSink sink;
-                sink.d_llr_out = d_out; sink.d_hard = d_hard; sink.d_iters = d_it;
-                CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
-                launch(dp, src, sink, (uint64_t)m, s);
-                CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));
-                if (llr_out) CUDA_OK(cudaMemcpyAsync(llr_out + o * nc, d_out, m * nc * sizeof(double), cudaMemcpyDeviceToHost, s));
-                if (hard) CUDA_OK(cudaMemcpyAsync(hard + o * nc, d_hard, m * nc, cudaMemcpyDeviceToHost, s));
-                if (iters) CUDA_OK(cudaMemcpyAsync(iters + o, d_it, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-                unsigned long long h[5];
-                CUDA_OK(cudaMemcpyAsync(h, d_counters_, sizeof(h), cudaMemcpyDeviceToHost, s));
-                CUDA_OK(cudaStreamSynchronize(s));
-                float ms = 0;
-                CUDA_OK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
-                stats.device_ms += ms;
-                stats.frames += h[2];
-                stats.edge_iterations += h[4] * (uint64_t)H.nnz;
+                CUDA_OK(cudaEventCreateWithFlags((cudaEvent_t *)&ev_in_[b], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags((cudaEvent_t *)&ev_k_[b], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags((cudaEvent_t *)&ev_out_[b], cudaEventDisableTiming));
             }
         }
-        catch (...)
+        cudaStream_t si = (cudaStream_t)copy_in_, so = (cudaStream_t)copy_out_;
+        auto grow = [&](void *&ptr, size_t &cap, size_t need)
         {
-            cudaFree(d_in); cudaFree(d_out); cudaFree(d_hard); cudaFree(d_it);
-            throw;
+            if (need <= cap) return;
+            CUDA_OK(cudaDeviceSynchronize());
+            cudaFree(ptr);
+            ptr = nullptr; cap = 0;
+            CUDA_OK(cudaMalloc(&ptr, need));
+            cap = need;
+        };
+        for (int b = 0; b < 2; ++b)
+        {
+            grow(db_in_[b], db_in_cap_[b], (size_t)chunk * nc * sizeof(double));
+            if (llr_out) grow(db_out_[b], db_out_cap_[b], (size_t)chunk * nc * sizeof(double));
+            if (hard) grow(db_hard_[b], db_hard_cap_[b], (size_t)chunk * nc);
+            if (iters) grow(db_it_[b], db_it_cap_[b], (size_t)chunk * sizeof(int32_t));
         }
-        cudaFree(d_in); cudaFree(d_out); cudaFree(d_hard); cudaFree(d_it);
+        CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), sk));
+        CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, sk));
+        int64_t k = 0;
+        for (int64_t o = 0; o < n; o += chunk, ++k)
+        {
+            const int b = (int)(k & 1);
+            const int64_t m = std::min(chunk, n - o);
+            if (k >= 2) CUDA_OK(cudaStreamWaitEvent(si, (cudaEvent_t)ev_k_[b], 0)); // the kernel that read this input buffer is done
+            CUDA_OK(cudaMemcpyAsync(db_in_[b], llr + o * nc, m * nc * sizeof(double), cudaMemcpyHostToDevice, si));
+            CUDA_OK(cudaEventRecord((cudaEvent_t)ev_in_[b], si));
+            CUDA_OK(cudaStreamWaitEvent(sk, (cudaEvent_t)ev_in_[b], 0));
+            if (k >= 2) CUDA_OK(cudaStreamWaitEvent(sk, (cudaEvent_t)ev_out_[b], 0)); // the copy-out of this output buffer is done
+            FrameSource src;
+            src.kind = SRC_LLR;
+            src.d_llr = (const double *)db_in_[b];
+            FrameSink sink;
+            sink.d_llr_out = llr_out ? (double *)db_out_[b] : nullptr;
+            sink.d_hard = hard ? (uint8_t *)db_hard_[b] : nullptr;
+            sink.d_iters = iters ? (int32_t *)db_it_[b] : nullptr;
+            launch(dp, src, sink, (uint64_t)m, sk);
+            CUDA_OK(cudaEventRecord((cudaEvent_t)ev_k_[b], sk));
+            CUDA_OK(cudaStreamWaitEvent(so, (cudaEvent_t)ev_k_[b], 0));
+            if (llr_out) CUDA_OK(cudaMemcpyAsync(llr_out + o * nc, db_out_[b], m * nc * sizeof(double), cudaMemcpyDeviceToHost, so));
+            if (hard) CUDA_OK(cudaMemcpyAsync(hard + o * nc, db_hard_[b], m * nc, cudaMemcpyDeviceToHost, so));
+            if (iters) CUDA_OK(cudaMemcpyAsync(iters + o, db_it_[b], m * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
+            CUDA_OK(cudaEventRecord((cudaEvent_t)ev_out_[b], so));
+        }
+        CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, sk));
+        unsigned long long h[5];
+        CUDA_OK(cudaMemcpyAsync(h, d_counters_, sizeof(h), cudaMemcpyDeviceToHost, sk));
+        CUDA_OK(cudaStreamSynchronize(sk));
+        CUDA_OK(cudaStreamSynchronize(so));
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
+        stats.device_ms += ms;
+        stats.frames += h[2];
+        stats.edge_iterations += h[4] * (uint64_t)H.nnz;
     }
 
     void Engine::decode_bec_host(const decoder_param &dp, const uint8_t *in, const uint8_t *cw, int64_t n, uint8_t *out, uint8_t *hard, int32_t *iters)

@@ -65,6 +65,9 @@ namespace b200
         void sim_point_async(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
                              uint64_t frame0, uint64_t n_frames, unsigned long long *d_counters, void *stream);
 
+        // sustained shared-memory read bandwidth of the device in GB/s (LDS.128 streaming from every SM)
+        double smem_probe();
+
         void ensure_cuda();
         void *engine_stream() const { return stream_; }
 
@@ -99,6 +102,11 @@ namespace b200
         unsigned long long *d_counters_ = nullptr;
         unsigned char *d_state_ = nullptr;
         size_t state_bytes_ = 0;
+        // host-buffer batch decode pipeline (decode_batch_host): copy streams, per-buffer events, cached device buffers
+        void *copy_in_ = nullptr, *copy_out_ = nullptr;
+        void *ev_in_[2] = {nullptr, nullptr}, *ev_k_[2] = {nullptr, nullptr}, *ev_out_[2] = {nullptr, nullptr};
+        void *db_in_[2] = {nullptr, nullptr}, *db_out_[2] = {nullptr, nullptr}, *db_hard_[2] = {nullptr, nullptr}, *db_it_[2] = {nullptr, nullptr};
+        size_t db_in_cap_[2] = {0, 0}, db_out_cap_[2] = {0, 0}, db_hard_cap_[2] = {0, 0}, db_it_cap_[2] = {0, 0};
     };
 
     // reference-semantics sweep driver (sim_driver.cpp)

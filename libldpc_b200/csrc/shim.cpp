@@ -367,6 +367,14 @@ extern "C"
         });
     }
 
+    int ldpc_b200_smem_probe(ldpc_b200_ctx *ctx, double *gb_per_s)
+    {
+        return guarded([&] {
+            if (!ctx || !gb_per_s) throw std::runtime_error("null argument");
+            *gb_per_s = ctx->eng->smem_probe();
+        });
+    }
+
     int ldpc_b200_get_stats(const ldpc_b200_ctx *ctx, ldpc_b200_stats *s)
     {
         return guarded([&] {
