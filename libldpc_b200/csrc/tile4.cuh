@@ -262,11 +262,15 @@ namespace b200
 
         // CSRC: the old c2v values come from shared/global memory (0) or from the thread's TMEM mirror at
         // columns tc + 4k (1); TMW: new values are also written to that mirror.
+        // nx: in = this node's index entries (byte offsets), out = those of the node at ip_next when `more`
+        // (software prefetch: the load is in flight while this node is computed).
         template <int CSRC, bool TMW>
-        static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, P ip, uint32_t tc)
+        static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, uint32_t (&nx)[D], P ip_next, bool more, uint32_t tc)
         {
             uint32_t eo[D];
-            IdxLoad<SMEM, IdxT, LANES, D>::load(ip, eo);
+#pragma unroll
+            for (int k = 0; k < D; ++k) eo[k] = nx[k];
+            if (more) IdxLoad<SMEM, IdxT, LANES, D>::load(ip_next, nx);
             bool par[VEC];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) par[e] = false;
@@ -488,10 +492,12 @@ namespace b200
     {
         typedef typename PtrOf<SMEM>::type P;
         typedef Vec<T> V;
-        static __device__ __forceinline__ V run(P c2v_sub, P ip, V acc)
+        static __device__ __forceinline__ V run(P c2v_sub, uint32_t (&nx)[D], P ip_next, bool more, V acc)
         {
             uint32_t eo[D];
-            IdxLoad<SMEM, IdxT, LANES, D>::load(ip, eo);
+#pragma unroll
+            for (int k = 0; k < D; ++k) eo[k] = nx[k];
+            if (more) IdxLoad<SMEM, IdxT, LANES, D>::load(ip_next, nx);
             V m[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) m[k] = VAcc<SMEM, T, 0>::ld(c2v_sub + eo[k]);
@@ -802,13 +808,16 @@ namespace b200
             {
                 constexpr int CSRC = decltype(csrc)::value;
                 uint32_t tc = tm_w;
-                for (P sp = cn_seg_w;; sp += 16)
+                uint4 sg_next = WAcc<SMEM, 0>::ld4(cn_seg_w);
+                for (P sp = cn_seg_w;;)
                 {
 #ifdef B200_PHASE_TIMING
                     const long long ph0 = clock64();
 #endif
-                    const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
+                    const uint4 sg = sg_next;
                     if (sg.x == 0) break;
+                    sp += 16;
+                    sg_next = WAcc<SMEM, 0>::ld4(sp); // the next descriptor (or the terminator) is in flight while this segment runs
                     // threads of nodes missing from a ragged task run along on padded slots / zero index entries
                     const int deg = (int)(sg.x & 0xFFu);
                     const uint32_t keep = (j < (int)((sg.x >> 8) & 0xFFu)) ? 0xFFFFFFFFu : 0u;
@@ -825,12 +834,14 @@ namespace b200
     {                                                                                                        \
         constexpr int ST = idx_stride_of(D, ISZ);                                                            \
         P ip = ib + j * (ST < 16 ? ST : 16);                                                                 \
+        uint32_t nx[D];                                                                                      \
+        IdxLoad<SMEM, IdxT, LANES, D>::load(ip, nx);                                                         \
         B200_PT_HDR                                                                                          \
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
-            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM>(out_sub, c2v0, ip, tc) & keep;  \
-            c2v0 += D * 512;                                                                                 \
             ip += NPW * ST;                                                                                  \
+            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM>(out_sub, c2v0, nx, ip, nt > 1, tc) & keep; \
+            c2v0 += D * 512;                                                                                 \
             if constexpr (TM) tc += 4 * D;                                                                   \
         }                                                                                                    \
         break;                                                                                               \
@@ -901,10 +912,13 @@ namespace b200
             {
                 constexpr int LSRC = decltype(lsrc)::value;
                 uint32_t tl = tm_w + p.tm_vn_off;
-                for (P sp = vn_seg_w;; sp += 16)
+                uint4 sg_next = WAcc<SMEM, 0>::ld4(vn_seg_w);
+                for (P sp = vn_seg_w;;)
                 {
-                    const uint4 sg = WAcc<SMEM, 0>::ld4(sp);
+                    const uint4 sg = sg_next;
                     if (sg.x == 0) break;
+                    sp += 16;
+                    sg_next = WAcc<SMEM, 0>::ld4(sp);
                     const int deg = (int)(sg.x & 0xFFu);
                     int nt = (int)(sg.x >> 16);
                     P lp = llr_lane + sg.y, op = out_lane + sg.y;
@@ -938,10 +952,12 @@ namespace b200
     {                                                                                                        \
         constexpr int ST = idx_stride_of(D, ISZ);                                                            \
         P ip = ib + j * (ST < 16 ? ST : 16);                                                                 \
+        uint32_t nx[D];                                                                                      \
+        IdxLoad<SMEM, IdxT, LANES, D>::load(ip, nx);                                                         \
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
-            finish(Vn4<T, IdxT, SMEM, LANES, D>::run(c2v_sub, ip, channel_llr()));                           \
             ip += NPW * ST;                                                                                  \
+            finish(Vn4<T, IdxT, SMEM, LANES, D>::run(c2v_sub, nx, ip, nt > 1, channel_llr()));               \
         }                                                                                                    \
         break;                                                                                               \
     }
