@@ -116,6 +116,7 @@ namespace b200
         dev_layouts_.clear();
         dev_seg_layouts_.clear();
         cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
+        cudaFree(d_g_col_ptr_); cudaFree(d_g_row_);
         for (int b = 0; b < 2; ++b)
         {
             cudaFree(db_in_[b]); cudaFree(db_out_[b]); cudaFree(db_hard_[b]); cudaFree(db_it_[b]);
@@ -160,6 +161,13 @@ namespace b200
         d_bit_pos_ = upload(bp);
         d_punct_ = upload(pu);
         d_short_ = upload(sh);
+        if (has_gen)
+        { // generator matrix by column (= variable id), rows in file order
+            std::vector<int32_t> cp(G.col_ptr.begin(), G.col_ptr.end()), rows(G.nnz);
+            for (int q = 0; q < G.nnz; ++q) rows[q] = (int32_t)G.e_row[G.col_edge[q]];
+            d_g_col_ptr_ = upload(cp);
+            d_g_row_ = upload(rows);
+        }
         CUDA_OK(cudaMalloc(&d_counters_, 8 * sizeof(unsigned long long)));
         CUDA_OK(cudaMemset(d_counters_, 0, 8 * sizeof(unsigned long long)));
         cuda_ready_ = true;
@@ -197,13 +205,15 @@ namespace b200
                 throw std::runtime_error("frames_per_cta / vector width must be 1, 2, 4 or 8");
         }
         const size_t limit = std::min<size_t>(smem_optin_ > 1024 ? smem_optin_ - 1024 : 0, (size_t)TILE_SMEM_OPTIN);
+        // information words of the frames in flight (random codewords through the generator matrix), 16-byte rounded
+        auto u_bytes = [&](int lanes) -> size_t { return has_gen ? (((size_t)4 * lanes * vec * ((G.mc + 31) / 32)) + 15) & ~(size_t)15 : 0; };
         if (tuning.residency != LDPC_B200_GLOBAL)
         {
             for (int lanes = 8; lanes >= 1; lanes >>= 1)
             {
                 if (want_lanes && lanes != want_lanes) continue;
                 const SegLayout &l = get_seg_layout(lanes, threads);
-                const size_t need = seg_smem_bytes(l);
+                const size_t need = seg_smem_bytes(l) + u_bytes(lanes);
                 if (need <= limit)
                 {
                     *residency = LDPC_B200_SMEM;
@@ -214,7 +224,7 @@ namespace b200
             if (tuning.residency == LDPC_B200_SMEM) throw std::runtime_error("code does not fit shared-memory residency with this tuning");
         }
         *residency = LDPC_B200_GLOBAL;
-        *smem_bytes = 0;
+        *smem_bytes = u_bytes(want_lanes ? want_lanes : 1);
         return get_seg_layout(want_lanes ? want_lanes : 1, threads);
     }
 
@@ -469,6 +479,14 @@ namespace b200
             kp.state = d_state_;
         }
         kp.tm_alloc_cols = c.tm_alloc_cols; kp.tm_cols_per_warp = c.tm_cols_per_warp; kp.tm_vn_off = c.tm_vn_off;
+        // transmitted codewords: random information words through G when a generator matrix is loaded (the reference's -G,
+        // src/sim/ldpcsim.cpp:162-165); decoding caller-supplied LLRs has no transmitted word
+        kp.tx_var = d_bit_pos_;
+        if (has_gen && !tuning.zero_codeword && src.kind != SRC_LLR)
+        {
+            kp.g_col_ptr = d_g_col_ptr_; kp.g_row = d_g_row_;
+            kp.g_rows = G.mc; kp.g_cols = G.nc; kp.u_words = (G.mc + 31) / 32;
+        }
         const bool smem = c.residency == LDPC_B200_SMEM;
         if (c.precision == LDPC_B200_F32)
         {
@@ -676,8 +694,24 @@ namespace b200
     // Stand-alone channel kernel: the same generator code as the fused path, one thread per Philox block.
     __global__ void channel_kernel(int kind, int nc, int nct, const int32_t *__restrict__ bit_pos, const int32_t *__restrict__ punct, int n_punct,
                                    const int32_t *__restrict__ shorten, int n_short, double sigma, double sigma2, double delta, uint32_t thr,
-                                   uint64_t seed, uint32_t point, uint64_t frame0, int64_t n_frames, uint8_t *cw, double *llr, uint8_t *llr_u8)
+                                   uint64_t seed, uint32_t point, uint64_t frame0, int64_t n_frames, uint8_t *cw, double *llr, uint8_t *llr_u8,
+                                   const int32_t *__restrict__ g_col_ptr, const int32_t *__restrict__ g_row, int g_rows, int g_cols)
     {
+        // codeword bit of variable v in frame fr: parity of the Philox stream-1 information bits selected by column v of G
+        // (same rule as the fused kernel, tile4.cuh cw_bit); 0 without a generator matrix.  Used by AWGN / BSC only.
+        auto cw_bit = [&](int64_t fr, int v) -> uint32_t
+        {
+            if (g_rows <= 0 || v >= g_cols) return 0u;
+            uint32_t b = 0;
+            for (int q = g_col_ptr[v]; q < g_col_ptr[v + 1]; ++q)
+            {
+                const int r = g_row[q];
+                const u32x4 w = channel_block(seed, point, 1, frame0 + fr, (uint32_t)r >> 7);
+                const uint32_t q4[4] = {w.x, w.y, w.z, w.w};
+                b ^= q4[(r >> 5) & 3] >> (r & 31);
+            }
+            return b & 1u;
+        };
         const int per = (kind == SRC_AWGN) ? 2 : 4;
         const int nblk = (nct + per - 1) / per;
         const int64_t total = n_frames * (int64_t)nblk;
@@ -694,11 +728,18 @@ namespace b200
                 const double rad = sqrt(-2.0 * log(u1));
                 double sn, cs;
                 sincos(6.283185307179586 * u2, &sn, &cs);
-                const double y0 = __dadd_rn(__dmul_rn(rad * cs, sigma), 1.0);
-                const double y1 = __dadd_rn(__dmul_rn(rad * sn, sigma), 1.0);
                 const int t = 2 * j;
+                const uint32_t b0 = cw_bit(fr, bit_pos[t]);
+                const double y0 = __dadd_rn(__dmul_rn(rad * cs, sigma), b0 ? -1.0 : 1.0);
                 llr[base + bit_pos[t]] = __dmul_rn(2.0, y0) / sigma2;
-                if (t + 1 < nct) llr[base + bit_pos[t + 1]] = __dmul_rn(2.0, y1) / sigma2;
+                if (cw) cw[base + bit_pos[t]] = (uint8_t)b0;
+                if (t + 1 < nct)
+                {
+                    const uint32_t b1 = cw_bit(fr, bit_pos[t + 1]);
+                    const double y1 = __dadd_rn(__dmul_rn(rad * sn, sigma), b1 ? -1.0 : 1.0);
+                    llr[base + bit_pos[t + 1]] = __dmul_rn(2.0, y1) / sigma2;
+                    if (cw) cw[base + bit_pos[t + 1]] = (uint8_t)b1;
+                }
             }
             else
             {
@@ -708,8 +749,17 @@ namespace b200
                     const int t = 4 * j + q;
                     if (t >= nct) break;
                     const bool hit = w[q] < thr;
-                    if (kind == SRC_BSC) llr[base + bit_pos[t]] = hit ? -delta : delta;
-                    else llr_u8[base + bit_pos[t]] = hit ? (uint8_t)'E' : (uint8_t)0;
+                    if (kind == SRC_BSC)
+                    {
+                        const uint32_t b = cw_bit(fr, bit_pos[t]);
+                        llr[base + bit_pos[t]] = ((hit ? 1u : 0u) ^ b) ? -delta : delta;
+                        if (cw) cw[base + bit_pos[t]] = (uint8_t)b;
+                    }
+                    else
+                    {
+                        llr_u8[base + bit_pos[t]] = hit ? (uint8_t)'E' : (uint8_t)0;
+                        if (cw) cw[base + bit_pos[t]] = 0;
+                    }
                 }
             }
             if (j == 0)
@@ -724,7 +774,11 @@ namespace b200
                     if (kind == SRC_BEC) llr_u8[base + shorten[i]] = 0;
                     else llr[base + shorten[i]] = (kind == SRC_AWGN) ? 99999.9 : delta;
                 }
-                if (cw) for (int i = 0; i < nc; ++i) cw[base + i] = 0;
+                if (cw)
+                { // non-transmitted positions carry their codeword bit too (all-zero for the erasure channel)
+                    for (int i = 0; i < n_punct; ++i) cw[base + punct[i]] = (kind == SRC_BEC) ? 0 : (uint8_t)cw_bit(fr, punct[i]);
+                    for (int i = 0; i < n_short; ++i) cw[base + shorten[i]] = (kind == SRC_BEC) ? 0 : (uint8_t)cw_bit(fr, shorten[i]);
+                }
             }
         }
     }
@@ -752,7 +806,8 @@ namespace b200
             thr = t <= 0 ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
         }
         channel_kernel<<<sm_count_ * 4, 256, 0, s>>>(kind, (int)nc, H.nct(), d_bit_pos_, d_punct_, (int)H.puncture.size(), d_short_,
-                                                     (int)H.shorten.size(), sigma, sigma2, delta, thr, seed, point, frame0, n, d_cw, d_llr, d_u8);
+                                                     (int)H.shorten.size(), sigma, sigma2, delta, thr, seed, point, frame0, n, d_cw, d_llr, d_u8,
+                                                     d_g_col_ptr_, d_g_row_, (has_gen && !tuning.zero_codeword) ? G.mc : 0, has_gen ? G.nc : 0);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess && d_llr) e = cudaMemcpyAsync(llr, d_llr, n * nc * sizeof(double), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess && d_u8) e = cudaMemcpyAsync(llr_u8, d_u8, n * nc, cudaMemcpyDeviceToHost, s);

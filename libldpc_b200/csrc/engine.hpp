@@ -99,6 +99,7 @@ namespace b200
         std::map<std::pair<int, int>, std::unique_ptr<DeviceSegLayout>> dev_seg_layouts_;
         std::map<std::tuple<int, int, int, int, int, size_t>, int> occupancy_;
         int32_t *d_bit_pos_ = nullptr, *d_punct_ = nullptr, *d_short_ = nullptr;
+        int32_t *d_g_col_ptr_ = nullptr, *d_g_row_ = nullptr; // generator matrix by column (device)
         unsigned long long *d_counters_ = nullptr;
         unsigned char *d_state_ = nullptr;
         size_t state_bytes_ = 0;

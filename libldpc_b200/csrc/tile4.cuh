@@ -230,6 +230,11 @@ namespace b200
         // global-memory residency: per-CTA state block
         unsigned char *state;
         size_t state_stride;
+        // transmitted codewords (-G, src/sim/channel.cpp:44-60): generator matrix by column (variable id) and
+        // the variable id of every transmitted position; g_rows = 0 -> all-zero codeword
+        const int32_t *g_col_ptr, *g_row;
+        const int32_t *tx_var;
+        int g_rows, g_cols, u_words; // u_words = ceil(g_rows / 32)
         // TMEM mirror (TM kernels): columns allocated per CTA (power of two >= 32), columns per warp window,
         // column offset of the variable-side (channel LLR) part inside a warp window
         uint32_t tm_alloc_cols, tm_cols_per_warp, tm_vn_off;
@@ -579,6 +584,7 @@ namespace b200
 
         // ---- carve state and tables --------------------------------------------------------
         P c2v, out, llr, cn_seg, vn_seg, cn_idx, vn_idx;
+        uint32_t a_u = (uint32_t)__cvta_generic_to_shared(dyn_smem); // information words of the frames in flight: [FPC][u_words]
         if constexpr (SMEM)
         {
             uint32_t q = (uint32_t)__cvta_generic_to_shared(dyn_smem);
@@ -588,7 +594,8 @@ namespace b200
             const uint32_t a_cs = q; q += 16 * p.cn_max_segs * warps;
             const uint32_t a_vs = q; q += 16 * p.vn_max_segs * warps;
             const uint32_t a_ci = q; q += p.cn_idx_bytes;
-            const uint32_t a_vi = q;
+            const uint32_t a_vi = q; q += p.vn_idx_bytes;
+            a_u = q;
             for (int i = tid; i < 4 * p.cn_max_segs * warps; i += nthreads) sts_u32<0>(a_cs + 4 * i, p.cn_seg[i]);
             for (int i = tid; i < 4 * p.vn_max_segs * warps; i += nthreads) sts_u32<0>(a_vs + 4 * i, p.vn_seg[i]);
             for (int i = tid; i < (int)(p.cn_idx_bytes >> 2); i += nthreads) sts_u32<0>(a_ci + 4 * i, reinterpret_cast<const uint32_t *>(p.cn_idx)[i]);
@@ -634,6 +641,22 @@ namespace b200
         // next variable phase read shared memory (and refresh the mirror).  CTA-uniform.
         bool cn_stale = true, vn_stale = true;
 
+        // bit of the codeword of frame lane g at transmitted index t: parity of the information bits selected by
+        // column tx_var[t] of the generator matrix (src/core/sparse.h:162-187); 0 without a generator matrix
+        auto cw_bit = [&](int g, int t) -> uint32_t
+        {
+            if (p.g_rows <= 0) return 0u;
+            const int v = p.tx_var[t];
+            if (v >= p.g_cols) return 0u;
+            uint32_t b = 0;
+            for (int q = p.g_col_ptr[v]; q < p.g_col_ptr[v + 1]; ++q)
+            {
+                const int r = p.g_row[q];
+                b ^= lds_u32<0>(a_u + 4 * (g * p.u_words + (r >> 5))) >> (r & 31);
+            }
+            return b & 1u;
+        };
+
         // Writes the decoder input of global frame gf into frame lane g (all threads of the CTA
         // cooperate), with the fresh-frame state: out = LLRin, c2v = +0.
         auto generate = [&](int g, unsigned long long gf)
@@ -653,8 +676,20 @@ namespace b200
                 return;
             }
             const unsigned long long frame = p.frame0 + gf;
+            if (p.g_rows > 0)
+            { // fresh information word per frame from Philox stream 1 (bit k = bit k%32 of word k/32), cw = u*G
+                for (int w = tid; w < p.u_words; w += nthreads)
+                {
+                    const u32x4 r = channel_block(p.seed, p.point, 1, frame, (uint32_t)w >> 2);
+                    const uint32_t q4[4] = {r.x, r.y, r.z, r.w};
+                    uint32_t v = q4[w & 3];
+                    if (32 * w + 32 > p.g_rows) v &= (1u << (p.g_rows - 32 * w)) - 1u;
+                    sts_u32<0>(a_u + 4 * (g * p.u_words + w), v);
+                }
+                __syncthreads();
+            }
             if (p.kind == SRC_AWGN)
-            { // y = sigma*z + 1 (all-zero codeword, BPSK +1), LLR = 2y/sigma^2 (src/sim/channel.cpp:62-68,88-92)
+            { // y = sigma*z + x, x = 1 - 2*cw (BPSK), LLR = 2y/sigma^2 (src/sim/channel.cpp:56-68,88-92)
                 const int npairs = (p.nct + 1) >> 1;
                 for (int q = tid; q < npairs; q += nthreads)
                 {
@@ -664,11 +699,16 @@ namespace b200
                     const double rad = sqrt(-2.0 * log(u1));
                     double sn, cs;
                     sincos(6.283185307179586 * u2, &sn, &cs);
-                    const double y0 = __dadd_rn(__dmul_rn(rad * cs, p.sigma), 1.0);
-                    const double y1 = __dadd_rn(__dmul_rn(rad * sn, p.sigma), 1.0);
                     const int t = 2 * q;
+                    const double x0 = cw_bit(g, t) ? -1.0 : 1.0;
+                    const double y0 = __dadd_rn(__dmul_rn(rad * cs, p.sigma), x0);
                     put(p.tx_pos[t], (T)(__dmul_rn(2.0, y0) / p.sigma2));
-                    if (t + 1 < p.nct) put(p.tx_pos[t + 1], (T)(__dmul_rn(2.0, y1) / p.sigma2));
+                    if (t + 1 < p.nct)
+                    {
+                        const double x1 = cw_bit(g, t + 1) ? -1.0 : 1.0;
+                        const double y1 = __dadd_rn(__dmul_rn(rad * sn, p.sigma), x1);
+                        put(p.tx_pos[t + 1], (T)(__dmul_rn(2.0, y1) / p.sigma2));
+                    }
                 }
                 for (int i = tid; i < p.n_punct; i += nthreads) put(p.punct_pos[i], T(0));
                 for (int i = tid; i < p.n_short; i += nthreads) put(p.short_pos[i], (T)99999.9);
@@ -684,7 +724,7 @@ namespace b200
                     for (int k = 0; k < 4; ++k)
                     {
                         const int t = 4 * q + k;
-                        if (t < p.nct) put(p.tx_pos[t], (T)((w[k] < p.thr) ? -p.delta : p.delta));
+                        if (t < p.nct) put(p.tx_pos[t], (T)((((w[k] < p.thr) ? 1u : 0u) ^ cw_bit(g, t)) ? -p.delta : p.delta));
                     }
                 }
                 for (int i = tid; i < p.n_punct; i += nthreads) put(p.punct_pos[i], T(0));
@@ -698,13 +738,14 @@ namespace b200
         auto retire_and_refill = [&](uint32_t mask, uint32_t synd, uint32_t started, bool as_skip, bool first_fill)
         {
             if (!first_fill)
-            { // bit errors of the final decisions over the transmitted positions, all-zero codeword (ldpcsim.cpp:184-190)
+            { // bit errors of the final decisions over the transmitted positions vs the transmitted codeword (ldpcsim.cpp:184-190)
                 for (int g = 0; g < FPC; ++g)
                     if ((mask >> g) & 1u)
                     {
                         const P src = out + (g / VEC) * 16 + (g % VEC) * TS;
                         uint32_t n = 0;
-                        for (int i = tid; i < p.nct; i += nthreads) n += (Acc<SMEM, T, 0>::ld(src + p.tx_pos[i] * RS) <= T(0)) ? 1u : 0u;
+                        for (int i = tid; i < p.nct; i += nthreads)
+                            n += ((Acc<SMEM, T, 0>::ld(src + p.tx_pos[i] * RS) <= T(0)) ? 1u : 0u) ^ cw_bit(g, i);
                         n = __reduce_add_sync(0xffffffffu, n);
                         if (lane == 0 && n) atomicAdd(&s_err[g], n);
                     }

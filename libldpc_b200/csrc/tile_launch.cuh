@@ -25,7 +25,7 @@ namespace b200
     void prepare_tile_one()
     {
         static bool attr_set = false;
-        if (SMEM && !attr_set)
+        if (!attr_set)
         {
             cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
             if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
@@ -37,7 +37,7 @@ namespace b200
     void launch_tile_one(const K4Params &kp, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
     {
         prepare_tile_one<T, ALG, SMEM, LANES, TM>();
-        tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM><<<ctas, threads, SMEM ? smem_bytes : 0, s>>>(kp);
+        tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM><<<ctas, threads, smem_bytes, s>>>(kp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " (tile kernel launch)");
     }
@@ -77,7 +77,7 @@ namespace b200
     case L:                                                                                                            \
         if (smem && tm) launch_tile_one<T, ALG, true, L, true>(kp, ctas, threads, smem_bytes, s);                      \
         else if (smem) launch_tile_one<T, ALG, true, L, false>(kp, ctas, threads, smem_bytes, s);                      \
-        else launch_tile_one<T, ALG, false, L, false>(kp, ctas, threads, 0, s);                                        \
+        else launch_tile_one<T, ALG, false, L, false>(kp, ctas, threads, smem_bytes, s);                               \
         return;
 #define B200_OCC_CASE(T, ALG, L)                                                                                       \
     case L:                                                                                                            \

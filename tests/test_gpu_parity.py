@@ -107,29 +107,46 @@ def test_ragged_batches_and_refill(gpu_ctx, oracle_code):
     assert np.array_equal(full[2][:40], ri) and np.array_equal(full[1][:40], rc)
 
 
-def test_channel_kernel_vs_spec(gpu_ctx, oracle_code):
-    """Philox channel: BSC/BEC inputs bit-exact with the CPU specification, AWGN within 1e-12."""
+def test_channel_kernel_vs_spec(gpu_ctx, oracle_code, oracle_gen):
+    """Philox channel: BSC/BEC inputs bit-exact with the CPU specification, AWGN within 1e-12.  The context holds a
+    generator matrix, so AWGN/BSC frames carry random codewords u*G (the reference's -G); the erasure path transmits
+    the all-zero word."""
     for ch, x in (("BSC", 0.11), ("BEC", 0.45)):
         cw, llr = gpu_ctx.channel(ch, x, seed=9, point=3, frame0=1 << 33, n=17)
-        ocw, ollr = oracle_code.channel_frames(ch, x, 9, 3, 1 << 33, 17)
+        ocw, ollr = oracle_code.channel_frames(ch, x, 9, 3, 1 << 33, 17, gen=oracle_gen if ch == "BSC" else None)
         assert np.array_equal(cw, ocw)
         assert np.array_equal(llr, ollr)
+        if ch == "BSC":
+            assert 0.3 < cw.mean() < 0.7 and not oracle_code.syndrome(cw[0]).any()   # real, non-trivial codewords
     cw, llr = gpu_ctx.channel("AWGN", -4.5, seed=2, point=1, frame0=5, n=64)
-    ocw, ollr = oracle_code.channel_frames("AWGN", -4.5, 2, 1, 5, 64)
+    ocw, ollr = oracle_code.channel_frames("AWGN", -4.5, 2, 1, 5, 64, gen=oracle_gen)
+    assert np.array_equal(cw, ocw)
     assert np.allclose(llr, ollr, rtol=1e-12, atol=1e-12)
     tx = oracle_code.bit_pos
-    z = (llr[:, tx] * 10 ** (4.5 / 10) / 2 - 1) / np.sqrt(10 ** (4.5 / 10))  # back to standard normal
+    z = (llr[:, tx] * 10 ** (4.5 / 10) / 2 - (1 - 2.0 * cw[:, tx])) / np.sqrt(10 ** (4.5 / 10))  # back to standard normal
+    gpu_ctx.set_tuning(zero_codeword=1)
+    cw0, llr0 = gpu_ctx.channel("AWGN", -4.5, seed=2, point=1, frame0=5, n=8)
+    gpu_ctx.set_tuning(zero_codeword=0)
+    assert not cw0.any() and np.allclose(llr0, oracle_code.channel_frames("AWGN", -4.5, 2, 1, 5, 8)[1], rtol=1e-12, atol=1e-12)
     assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
     assert np.all(llr[:, oracle_code.puncture] == 0.0)
 
 
 @pytest.mark.parametrize("ch,x,dec", [("BSC", 0.21, "BP_MS"), ("BSC", 0.16, "BP_MS"), ("BEC", 0.9, "BP"), ("BEC", 0.6, "BP")])
-def test_sim_counters_bit_exact_integer_channels(gpu_ctx, oracle_code, ch, x, dec):
-    """Whole pipeline (channel -> decode -> accounting) on the GPU equals the oracle's frame loop."""
+def test_sim_counters_bit_exact_integer_channels(gpu_ctx, oracle_code, oracle_gen, ch, x, dec):
+    """Whole pipeline (encode -> channel -> decode -> accounting) on the GPU equals the oracle's frame loop; BSC frames
+    carry random codewords through the generator matrix, with and without (zero_codeword) it."""
     n = 600
     g = gpu_ctx.sim_point(ch, x, seed=5, point=2, frame0=100, nframes=n, decoding=dec, iterations=30, early_term=True)
-    o = oracle_code.sim_point(ch, x, seed=5, point=2, frame0=100, nframes=n, decoding=dec, iterations=30, early_term=True, threads=8)
+    o = oracle_code.sim_point(ch, x, seed=5, point=2, frame0=100, nframes=n, decoding=dec, iterations=30, early_term=True, threads=8,
+                              gen=oracle_gen if ch == "BSC" else None)
     assert {k: g[k] for k in ("fec", "bec", "frames", "iters")} == o
+    if ch == "BSC":
+        gpu_ctx.set_tuning(zero_codeword=1)
+        g0 = gpu_ctx.sim_point(ch, x, seed=5, point=2, frame0=100, nframes=n, decoding=dec, iterations=30, early_term=True)
+        gpu_ctx.set_tuning(zero_codeword=0)
+        o0 = oracle_code.sim_point(ch, x, seed=5, point=2, frame0=100, nframes=n, decoding=dec, iterations=30, early_term=True, threads=8)
+        assert {k: g0[k] for k in ("fec", "bec", "frames", "iters")} == o0
 
 
 def test_sim_awgn_minsum_matches_oracle_on_dumped_llrs(gpu_ctx, oracle_code):
@@ -137,8 +154,9 @@ def test_sim_awgn_minsum_matches_oracle_on_dumped_llrs(gpu_ctx, oracle_code):
     n, x = 400, -4.5
     g = gpu_ctx.sim_point("AWGN", x, seed=1, point=0, frame0=0, nframes=n, decoding="BP_MS", iterations=50, early_term=True)
     cw, llr = gpu_ctx.channel("AWGN", x, seed=1, point=0, frame0=0, n=n)
+    assert cw.any()                                                  # random codewords through G
     out, co, its = oracle_code.decode(llr, 50, True, True)
-    errs = (co[:, oracle_code.bit_pos] != 0).sum(1)
+    errs = (co[:, oracle_code.bit_pos] != cw[:, oracle_code.bit_pos]).sum(1)
     assert g["frames"] == n
     assert g["iters"] == int(its.sum())
     assert g["fec"] == int((errs > 0).sum())
