@@ -150,8 +150,17 @@ namespace b200
 
         // Same-degree nodes are packed npw at a time (one warp executes one group per round with all its
         // node threads on equal trip counts); groups are then spread over warps longest-first.
-        std::vector<std::vector<Group>> schedule(const std::vector<int> &degree, int npw, int warps)
+        // side: 0 = historical cost model (degree + 3); 1 = check tasks, 2 = variable tasks of the segment kernel, whose
+        // costs follow the measured instruction counts of the node bodies (a check update is 3*deg - 4 pairwise
+        // operations plus loads/stores, a variable update one gather + add per edge plus a fixed part).
+        std::vector<std::vector<Group>> schedule(const std::vector<int> &degree, int npw, int warps, int side = 0)
         {
+            auto cost = [side](int deg) -> long
+            {
+                if (side == 1) return 10L * std::max(3 * deg - 4, 1) + 20;
+                if (side == 2) return 4L * deg + 12;
+                return deg + 3;
+            };
             std::vector<int> order(degree.size());
             std::iota(order.begin(), order.end(), 0);
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return degree[a] > degree[b]; });
@@ -172,7 +181,7 @@ namespace b200
                 auto [load, w] = heap.top();
                 heap.pop();
                 per_warp[w].push_back(g);
-                heap.push({load + g.degree + 3, w});
+                heap.push({load + cost(g.degree), w});
             }
             return per_warp;
         }
@@ -348,7 +357,7 @@ namespace b200
     }
     void SegLayout::build(const HostCode &code, int lanes_, int threads_, int isz_)
     {
-        if (lanes_ < 1 || lanes_ > 8 || (lanes_ & (lanes_ - 1))) throw std::runtime_error("lanes per node must be 1, 2, 4 or 8");
+        if (lanes_ < 1 || lanes_ > 4 || (lanes_ & (lanes_ - 1))) throw std::runtime_error("lanes per node must be 1, 2 or 4");
         if (threads_ < 32 || threads_ > 1024 || threads_ % 32) throw std::runtime_error("threads_per_cta must be a multiple of 32 <= 1024");
         if (isz_ != 2 && isz_ != 4) throw std::runtime_error("index entries are 2 or 4 bytes");
         if (code.nnz >= (1 << 22)) throw std::runtime_error("code too large (nnz >= 2^22)");
@@ -419,7 +428,7 @@ namespace b200
         };
 
         // ---- variable side first: it defines the positions the check side gathers from -------------
-        auto vs = schedule(vdeg, npw, warps);
+        auto vs = schedule(vdeg, npw, warps, 2);
         std::vector<std::vector<Seg>> vsegs(warps), csegs(warps);
         var_pos.assign(code.nc, 0);
         size_t pbase = 0, ibase = 0;
@@ -449,7 +458,7 @@ namespace b200
         vn_idx.assign(ibase + 16, 0);
 
         // ---- check side ------------------------------------------------------------------------
-        auto cs = schedule(cdeg, npw, warps);
+        auto cs = schedule(cdeg, npw, warps, 1);
         edge_slot.assign(code.nnz, -1);
         size_t sbase = 0;
         ibase = 0;

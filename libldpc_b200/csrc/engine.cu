@@ -84,13 +84,13 @@ namespace b200
             return b + 16;
         }
 
-        int family_occupancy(int precision, int alg, bool smem, bool tm, int lanes, int threads, size_t smem_bytes)
+        int family_occupancy(int precision, int alg, bool smem, bool tm, bool et, int lanes, int threads, size_t smem_bytes)
         {
             if (precision == LDPC_B200_F32)
-                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, tm, lanes, threads, smem_bytes)
-                                     : tile_family_occupancy<float, ALG_BP>(smem, tm, lanes, threads, smem_bytes);
-            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, tm, lanes, threads, smem_bytes)
-                                 : tile_family_occupancy<double, ALG_BP>(smem, tm, lanes, threads, smem_bytes);
+                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, tm, et, lanes, threads, smem_bytes)
+                                     : tile_family_occupancy<float, ALG_BP>(smem, tm, et, lanes, threads, smem_bytes);
+            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, tm, et, lanes, threads, smem_bytes)
+                                 : tile_family_occupancy<double, ALG_BP>(smem, tm, et, lanes, threads, smem_bytes);
         }
     } // namespace
 
@@ -201,15 +201,15 @@ namespace b200
         {
             if (tuning.frames_per_cta % vec) throw std::runtime_error("frames_per_cta must be a multiple of the vector width (2 for f64, 4 for f32)");
             want_lanes = tuning.frames_per_cta / vec;
-            if (want_lanes != 1 && want_lanes != 2 && want_lanes != 4 && want_lanes != 8)
-                throw std::runtime_error("frames_per_cta / vector width must be 1, 2, 4 or 8");
+            if (want_lanes != 1 && want_lanes != 2 && want_lanes != 4)
+                throw std::runtime_error("frames_per_cta / vector width must be 1, 2 or 4");
         }
         const size_t limit = std::min<size_t>(smem_optin_ > 1024 ? smem_optin_ - 1024 : 0, (size_t)TILE_SMEM_OPTIN);
         // information words of the frames in flight (random codewords through the generator matrix), 16-byte rounded
         auto u_bytes = [&](int lanes) -> size_t { return has_gen ? (((size_t)4 * lanes * vec * ((G.mc + 31) / 32)) + 15) & ~(size_t)15 : 0; };
         if (tuning.residency != LDPC_B200_GLOBAL)
         {
-            for (int lanes = 8; lanes >= 1; lanes >>= 1)
+            for (int lanes = 4; lanes >= 1; lanes >>= 1)
             {
                 if (want_lanes && lanes != want_lanes) continue;
                 const SegLayout &l = get_seg_layout(lanes, threads);
@@ -278,7 +278,7 @@ namespace b200
             auto key = std::make_tuple(precision, alg, c.residency * 2 + (c.tm ? 1 : 0), c.lanes, c.threads, c.smem_bytes);
             auto it = occupancy_.find(key);
             if (it == occupancy_.end())
-                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.tm, c.lanes, c.threads, c.smem_bytes)).first;
+                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.tm, true, c.lanes, c.threads, c.smem_bytes)).first;
             if (it->second < 1) throw std::runtime_error("tile kernel does not fit on this device with the current tuning");
             ctas = sm_count_ * it->second;
         }
@@ -490,13 +490,13 @@ namespace b200
         const bool smem = c.residency == LDPC_B200_SMEM;
         if (c.precision == LDPC_B200_F32)
         {
-            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.tm, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<float, ALG_BP>(kp, smem, c.tm, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<float, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         else
         {
-            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.tm, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<double, ALG_BP>(kp, smem, c.tm, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<double, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         stats.launches += 1;
         stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;

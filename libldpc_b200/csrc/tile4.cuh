@@ -269,7 +269,8 @@ namespace b200
         // columns tc + 4k (1); TMW: new values are also written to that mirror.
         // nx: in = this node's index entries (byte offsets), out = those of the node at ip_next when `more`
         // (software prefetch: the load is in flight while this node is computed).
-        template <int CSRC, bool TMW>
+        // PAR: also return the syndrome bits (only early termination consumes them, decoder.cpp:66-72).
+        template <int CSRC, bool TMW, bool PAR>
         static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, uint32_t (&nx)[D], P ip_next, bool more, uint32_t tc)
         {
             uint32_t eo[D];
@@ -296,7 +297,7 @@ namespace b200
                     for (int e = 0; e < VEC; ++e)
                     {
                         const T v = o.e[e] - c.e[e]; // == the reference's stored v2c (decoder.cpp:62); LLRin on a fresh frame (:18)
-                        par[e] ^= (o.e[e] <= T(0));
+                        if constexpr (PAR) par[e] ^= (o.e[e] <= T(0));
                         sm[e] |= (Num<T>::hi(v) >> 31) << k.value;
                         const bool lt1 = Num<T>::abs(v) < Num<T>::abs(m1[e]), lt2 = Num<T>::abs(v) < Num<T>::abs(m2[e]);
                         m2[e] = lt1 ? m1[e] : (lt2 ? v : m2[e]);
@@ -329,7 +330,7 @@ namespace b200
                     for (int e = 0; e < VEC; ++e)
                     {
                         v[k.value].e[e] = o.e[e] - c[k.value].e[e];
-                        par[e] ^= (o.e[e] <= T(0));
+                        if constexpr (PAR) par[e] ^= (o.e[e] <= T(0));
                     }
                 });
 #pragma unroll
@@ -560,7 +561,8 @@ namespace b200
 #define B200_TILE_MAX_THREADS 512 // compile-time cap of threads per CTA (register budget = 65536 / cap)
 #endif
     // TM: keep the write-through TMEM mirror (K4Params::tm_*; shared-memory residency only).
-    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM>
+    // ET: compiled with early termination support (syndrome in the check phase); ET = false serves --no-early-term runs.
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM, bool ET>
     __global__ void __launch_bounds__(B200_TILE_MAX_THREADS, (SMEM || ALG == ALG_BP) ? 1 : (1024 / B200_TILE_MAX_THREADS)) tile4_kernel(const K4Params p)
     {
         static_assert(SMEM || !TM, "the TMEM mirror belongs to shared-memory residency");
@@ -757,7 +759,7 @@ namespace b200
                 const bool mine = lane < FPC && ((mask >> lane) & 1u);
                 if (mine && !first_fill)
                 {
-                    const bool conv = p.early_term && ((started >> lane) & 1u) && !((synd >> lane) & 1u);
+                    const bool conv = ET && p.early_term && ((started >> lane) & 1u) && !((synd >> lane) & 1u);
                     const int ret = conv ? it - 1 : p.max_iter; // the reference breaks before ++I (decoder.cpp:66-77)
                     const uint32_t e = s_err[lane];
                     s_err[lane] = 0;
@@ -829,7 +831,7 @@ namespace b200
 
             // ---- without early termination a frame at the iteration limit retires here, before a
             //      check phase is spent on it (its result is fixed: decoder.cpp:22,74-77)
-            if (!p.early_term)
+            if (!ET || !p.early_term)
             {
                 const uint32_t lim = s_ctrl[par_i].x & active;
                 if (lim)
@@ -881,7 +883,7 @@ namespace b200
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
             ip += NPW * ST;                                                                                  \
-            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM>(out_sub, c2v0, nx, ip, nt > 1, tc) & keep; \
+            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM, ET>(out_sub, c2v0, nx, ip, nt > 1, tc) & keep; \
             c2v0 += D * 512;                                                                                 \
             if constexpr (TM) tc += 4 * D;                                                                   \
         }                                                                                                    \
@@ -917,6 +919,7 @@ namespace b200
             else cn_phase(std::integral_constant<int, 0>{});
             cn_stale = false;
             // syndrome flags per frame lane: frame = sub*VEC + e
+            if constexpr (ET)
             {
                 const uint32_t m = __reduce_or_sync(0xffffffffu, bad << (sub * VEC));
                 if (lane == 0 && m) atomicOr(&s_synd[par_i], m);
@@ -933,7 +936,7 @@ namespace b200
             {
                 const uint32_t synd = s_synd[par_i];
                 const uint2 ctrl = s_ctrl[par_i];
-                const uint32_t done = active & ((p.early_term ? (~synd & ctrl.y) : 0u) | ctrl.x);
+                const uint32_t done = active & (((ET && p.early_term) ? (~synd & ctrl.y) : 0u) | ctrl.x);
                 if (done) retire_and_refill(done, synd, ctrl.y, true, false);
             }
             // bookkeeping for the variable phase that follows and the next decision

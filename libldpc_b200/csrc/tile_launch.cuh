@@ -9,81 +9,84 @@
 
 namespace b200
 {
-    // Three variants per (T, ALG, lanes): shared-memory residency with / without the TMEM mirror, global
-    // residency.  Index entries are 32-bit byte offsets.
+    // Four variants per (T, ALG, lanes): shared-memory residency with the TMEM mirror (with / without the
+    // early-termination syndrome: --no-early-term runs skip it), shared-memory residency without the mirror,
+    // global residency.  Index entries are 32-bit byte offsets.
     // lanes = warp lanes per node (frames per CTA = lanes * 16/sizeof(T)).
     template <typename T, int ALG>
-    void launch_tile_family(const K4Params &kp, bool smem, bool tm, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
+    void launch_tile_family(const K4Params &kp, bool smem, bool tm, bool et, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
 
     // resident CTAs per SM the runtime grants this configuration (occupancy query; 0 = does not fit)
     template <typename T, int ALG>
-    int tile_family_occupancy(bool smem, bool tm, int lanes, int threads, size_t smem_bytes);
+    int tile_family_occupancy(bool smem, bool tm, bool et, int lanes, int threads, size_t smem_bytes);
 
     constexpr int TILE_SMEM_OPTIN = 232448 - 1024; // 227 KB minus the kernel's static shared memory
 
-    template <typename T, int ALG, bool SMEM, int LANES, bool TM>
+    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET>
     void prepare_tile_one()
     {
         static bool attr_set = false;
         if (!attr_set)
         {
-            cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
+            cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
             if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
             attr_set = true;
         }
     }
 
-    template <typename T, int ALG, bool SMEM, int LANES, bool TM>
+    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET>
     void launch_tile_one(const K4Params &kp, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
     {
-        prepare_tile_one<T, ALG, SMEM, LANES, TM>();
-        tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM><<<ctas, threads, smem_bytes, s>>>(kp);
+        prepare_tile_one<T, ALG, SMEM, LANES, TM, ET>();
+        tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET><<<ctas, threads, smem_bytes, s>>>(kp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " (tile kernel launch)");
     }
 
-    template <typename T, int ALG, bool SMEM, int LANES, bool TM>
+    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET>
     int occupancy_tile_one(int threads, size_t smem_bytes)
     {
-        prepare_tile_one<T, ALG, SMEM, LANES, TM>();
+        prepare_tile_one<T, ALG, SMEM, LANES, TM, ET>();
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM>, threads, SMEM ? smem_bytes : 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET>, threads, smem_bytes);
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
         return n;
     }
 
 #define B200_DEFINE_TILE_FAMILY(T, ALG)                                                                                \
     template <>                                                                                                        \
-    void launch_tile_family<T, ALG>(const K4Params &kp, bool smem, bool tm, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
+    void launch_tile_family<T, ALG>(const K4Params &kp, bool smem, bool tm, bool et, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
     {                                                                                                                  \
         switch (lanes)                                                                                                 \
         {                                                                                                              \
             B200_TILE_LAUNCH_CASES(T, ALG)                                                                             \
-        default: throw std::runtime_error("lanes per node must be 1, 2, 4 or 8");                                      \
+        default: throw std::runtime_error("lanes per node must be 1, 2 or 4");                                      \
         }                                                                                                              \
     }                                                                                                                  \
     template <>                                                                                                        \
-    int tile_family_occupancy<T, ALG>(bool smem, bool tm, int lanes, int threads, size_t smem_bytes)                \
+    int tile_family_occupancy<T, ALG>(bool smem, bool tm, bool et, int lanes, int threads, size_t smem_bytes)                \
     {                                                                                                                  \
         switch (lanes)                                                                                                 \
         {                                                                                                              \
             B200_TILE_OCC_CASES(T, ALG)                                                                                \
-        default: throw std::runtime_error("lanes per node must be 1, 2, 4 or 8");                                      \
+        default: throw std::runtime_error("lanes per node must be 1, 2 or 4");                                      \
         }                                                                                                              \
         return 0;                                                                                                      \
     }
 
 #define B200_LAUNCH_CASE(T, ALG, L)                                                                                    \
     case L:                                                                                                            \
-        if (smem && tm) launch_tile_one<T, ALG, true, L, true>(kp, ctas, threads, smem_bytes, s);                      \
-        else if (smem) launch_tile_one<T, ALG, true, L, false>(kp, ctas, threads, smem_bytes, s);                      \
-        else launch_tile_one<T, ALG, false, L, false>(kp, ctas, threads, smem_bytes, s);                               \
+        if (smem && tm && (et || ALG != ALG_MS)) launch_tile_one<T, ALG, true, L, true, true>(kp, ctas, threads, smem_bytes, s); \
+        else if (smem && tm) launch_tile_one<T, ALG, true, L, true, ALG != ALG_MS>(kp, ctas, threads, smem_bytes, s);  \
+        else if (smem) launch_tile_one<T, ALG, true, L, false, true>(kp, ctas, threads, smem_bytes, s);                \
+        else launch_tile_one<T, ALG, false, L, false, true>(kp, ctas, threads, smem_bytes, s);                         \
         return;
 #define B200_OCC_CASE(T, ALG, L)                                                                                       \
     case L:                                                                                                            \
-        return (smem && tm) ? occupancy_tile_one<T, ALG, true, L, true>(threads, smem_bytes)                           \
-               : smem       ? occupancy_tile_one<T, ALG, true, L, false>(threads, smem_bytes)                          \
-                            : occupancy_tile_one<T, ALG, false, L, false>(threads, 0);
-#define B200_TILE_LAUNCH_CASES(T, ALG) B200_LAUNCH_CASE(T, ALG, 1) B200_LAUNCH_CASE(T, ALG, 2) B200_LAUNCH_CASE(T, ALG, 4) B200_LAUNCH_CASE(T, ALG, 8)
-#define B200_TILE_OCC_CASES(T, ALG) B200_OCC_CASE(T, ALG, 1) B200_OCC_CASE(T, ALG, 2) B200_OCC_CASE(T, ALG, 4) B200_OCC_CASE(T, ALG, 8)
+        return (smem && tm && (et || ALG != ALG_MS)) ? occupancy_tile_one<T, ALG, true, L, true, true>(threads, smem_bytes) \
+               : (smem && tm)     ? occupancy_tile_one<T, ALG, true, L, true, ALG != ALG_MS>(threads, smem_bytes)      \
+               : smem             ? occupancy_tile_one<T, ALG, true, L, false, true>(threads, smem_bytes)              \
+                                  : occupancy_tile_one<T, ALG, false, L, false, true>(threads, smem_bytes);
+#define B200_TILE_LAUNCH_CASES(T, ALG) B200_LAUNCH_CASE(T, ALG, 1) B200_LAUNCH_CASE(T, ALG, 2) B200_LAUNCH_CASE(T, ALG, 4)
+#define B200_TILE_OCC_CASES(T, ALG) B200_OCC_CASE(T, ALG, 1) B200_OCC_CASE(T, ALG, 2) B200_OCC_CASE(T, ALG, 4)
 } // namespace b200

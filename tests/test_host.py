@@ -79,7 +79,7 @@ def test_loader_header_and_edge_cases(built_lib, tmp_path):
     c.close()
 
 
-@pytest.mark.parametrize("precision,fpc", [(0, 0), (1, 0), (0, 16), (1, 16), (0, 2), (1, 32)])
+@pytest.mark.parametrize("precision,fpc", [(0, 0), (1, 0), (0, 8), (1, 16), (0, 2), (1, 4)])
 def test_tile_layout_is_a_valid_schedule(host_ctx, precision, fpc):
     from libldpc_b200 import api
     host_ctx.set_tuning(precision=precision, residency=api.AUTO if fpc == 0 else api.GLOBAL, frames_per_cta=fpc)
