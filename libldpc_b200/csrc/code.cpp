@@ -266,95 +266,6 @@ namespace b200
         if (n_slots >= (1 << 23) || n_vslots >= (1 << 23)) throw std::runtime_error("layout too large");
     }
 
-    void TaskLayout::build(const HostCode &code, int lanes_, int threads_)
-    {
-        if (lanes_ < 1 || lanes_ > 32 || (lanes_ & (lanes_ - 1))) throw std::runtime_error("lanes per node must be a power of two <= 32");
-        if (threads_ < 32 || threads_ > 1024 || threads_ % 32) throw std::runtime_error("threads_per_cta must be a multiple of 32 <= 1024");
-        if (code.nnz >= (1 << 22)) throw std::runtime_error("code too large (nnz >= 2^22)");
-        if (code.max_cn_degree > 64) throw std::runtime_error("check degree > 64 not supported");
-        if (code.max_vn_degree > 255) throw std::runtime_error("variable degree > 255 not supported");
-        if (code.min_cn_degree < 2) throw std::runtime_error("check nodes of degree < 2 are not supported (undefined in the reference)");
-        lanes = lanes_;
-        threads = threads_;
-        warps = threads / 32;
-        npw = 32 / lanes;
-
-        std::vector<int> cdeg(code.mc), vkey(code.nc);
-        for (int i = 0; i < code.mc; ++i) cdeg[i] = code.row_ptr[i + 1] - code.row_ptr[i];
-        std::vector<char> tx(code.nc, 0);
-        for (int p : code.bit_pos) tx[p] = 1;
-        // variable classes: (degree, transmitted); the key keeps the degree dominant for the longest-first order
-        for (int i = 0; i < code.nc; ++i) vkey[i] = 2 * (code.col_ptr[i + 1] - code.col_ptr[i]) + (tx[i] ? 1 : 0);
-
-        // ---- variable side first: it defines the positions the check side gathers from -------------
-        auto vs = schedule(vkey, npw, warps);
-        vn_rounds = 0;
-        for (auto &l : vs) vn_rounds = std::max<int>(vn_rounds, (int)l.size());
-        vn_task.assign((size_t)2 * vn_rounds * warps, 0);
-        var_pos.assign(code.nc, 0);
-        int pbase = 0, qbase = 0;
-        struct VRef { int r, w, q0; };
-        std::vector<VRef> vrefs;
-        for (int r = 0; r < vn_rounds; ++r)
-            for (int w = 0; w < warps; ++w)
-            {
-                if (r >= (int)vs[w].size()) continue;
-                const Group &g = vs[w][r];
-                const int deg = g.degree >> 1, t = g.degree & 1;
-                vn_task[2 * ((size_t)r * warps + w)] = (uint32_t)qbase | ((uint32_t)deg << 23) | ((uint32_t)t << 31);
-                vn_task[2 * ((size_t)r * warps + w) + 1] = (uint32_t)pbase | ((uint32_t)g.nodes.size() << 24);
-                for (int j = 0; j < (int)g.nodes.size(); ++j) var_pos[g.nodes[j]] = (uint32_t)(pbase + j);
-                vrefs.push_back({r, w, qbase});
-                pbase += npw;
-                qbase += npw * deg;
-            }
-        n_pos = pbase;
-        n_vslots = qbase;
-
-        // ---- check side ------------------------------------------------------------------------
-        auto cs = schedule(cdeg, npw, warps);
-        cn_rounds = 0;
-        for (auto &l : cs) cn_rounds = std::max<int>(cn_rounds, (int)l.size());
-        cn_task.assign((size_t)2 * cn_rounds * warps, 0);
-        edge_slot.assign(code.nnz, -1);
-        cn_col.clear();
-        int base = 0;
-        for (int r = 0; r < cn_rounds; ++r)
-            for (int w = 0; w < warps; ++w)
-            {
-                if (r >= (int)cs[w].size()) continue;
-                const Group &g = cs[w][r];
-                cn_col.resize(base + (size_t)npw * g.degree, 0);
-                cn_task[2 * ((size_t)r * warps + w)] = (uint32_t)base | ((uint32_t)g.degree << 24);
-                cn_task[2 * ((size_t)r * warps + w) + 1] = (uint32_t)g.nodes.size();
-                for (int j = 0; j < (int)g.nodes.size(); ++j)
-                {
-                    const int row = g.nodes[j];
-                    for (int k = 0; k < g.degree; ++k)
-                    {
-                        const int e = code.row_edge[code.row_ptr[row] + k];
-                        const int slot = base + k * npw + j;
-                        edge_slot[e] = slot;
-                        cn_col[slot] = var_pos[code.e_col[e]];
-                    }
-                }
-                base += npw * g.degree;
-            }
-        n_slots = base;
-
-        vn_slot.assign(std::max(n_vslots, 1), 0);
-        for (const VRef &v : vrefs)
-        {
-            const Group &g = vs[v.w][v.r];
-            const int deg = g.degree >> 1;
-            for (int j = 0; j < (int)g.nodes.size(); ++j)
-            {
-                const int col = g.nodes[j];
-                for (int k = 0; k < deg; ++k) vn_slot[v.q0 + k * npw + j] = (uint32_t)edge_slot[code.col_edge[code.col_ptr[col] + k]];
-            }
-        }
-        if (n_slots >= (1 << 23) || n_vslots >= (1 << 23) || n_pos >= (1 << 24)) throw std::runtime_error("layout too large");
-    }
     void SegLayout::build(const HostCode &code, int lanes_, int threads_, int isz_)
     {
         if (lanes_ < 1 || lanes_ > 4 || (lanes_ & (lanes_ - 1))) throw std::runtime_error("lanes per node must be 1, 2 or 4");

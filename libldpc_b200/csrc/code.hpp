@@ -4,9 +4,9 @@
 //              src/core/sparse.h:91-153): edge list in FILE ORDER, per-row / per-column edge lists in
 //              file order (they fix the box-plus recursion order and the variable-node summation
 //              order), puncture/shorten lists, bit_pos, max degree.
-// TileLayout : the B200 mapping of one code onto a CTA tile: frames in the fast dimension,
-//              degree-sorted node groups balanced over warps, edge-slot-major message slots so that
-//              every sequential access is bank-conflict free / coalesced.
+// TileLayout : frame-in-lane mapping used by the erasure decoder (bec_kernel.cuh): frames in the fast
+//              dimension, degree-sorted node groups balanced over warps, edge-slot-major message slots.
+// SegLayout  : the vector-tile / segment mapping of the BP and min-sum decode kernel (tile4.cuh).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -64,35 +64,12 @@ namespace b200
         void build(const HostCode &code, int fpc, int threads);
     };
 
-    // Vector-tile mapping (tile3.cuh): one thread owns ONE 16-byte vector of adjacent frame lanes
-    // (2 doubles / 4 floats) of one node; `lanes` warp lanes serve the same node (so a CTA holds
-    // lanes * 16/sizeof(T) frames).  Work is cut into warp tasks: npw = 32/lanes nodes of equal degree
-    // (variable tasks also of equal transmitted/punctured status), spread longest-first over the warps;
-    // a task is described once per warp (8 bytes, broadcast load) instead of once per thread.
-    // Variables are renumbered into schedule order ("positions") so that the variable phase walks
-    // llr/out contiguously; the check side gathers by position.
-    struct TaskLayout
-    {
-        int lanes = 0, threads = 0, warps = 0, npw = 0;
-        int n_slots = 0;  // padded message slots: task base + k*npw + node
-        int n_pos = 0;    // padded variable positions: task base + node
-        int n_vslots = 0; // padded entries of vn_slot
-        int cn_rounds = 0, vn_rounds = 0;
-        // entry (round r, warp w) at 2*(r*warps + w): {slot base | degree << 24, node count (0 = idle)}
-        std::vector<uint32_t> cn_task;
-        std::vector<uint32_t> cn_col; // [n_slots] position of the variable each slot gathers from
-        // entry (round r, warp w): {vn_slot base | degree << 23 | transmitted << 31, position base | node count << 24}
-        std::vector<uint32_t> vn_task;
-        std::vector<uint32_t> vn_slot; // [n_vslots] message slot of edge k (file order) of node j at base + k*npw + j
-        std::vector<uint32_t> var_pos; // [nc] variable id -> position
-        std::vector<int> edge_slot;    // [nnz] file-order edge -> message slot
-
-        void build(const HostCode &code, int lanes, int threads);
-    };
-    // Segment mapping (tile4.cuh).  Same vector-tile idea as TaskLayout — one thread owns ONE 16-byte
-    // vector of adjacent frame lanes of one node, `lanes` warp lanes per node, npw = 32/lanes nodes per
-    // warp task — but each warp's task list is stored run-length encoded as SEGMENTS (runs of tasks of
-    // one degree), and message slots, variable positions and index entries are numbered warp-major in
+    // Segment mapping (tile4.cuh).  One thread owns ONE 16-byte vector of adjacent frame lanes (2 doubles /
+    // 4 floats) of one node; `lanes` warp lanes serve the same node (a CTA holds lanes * 16/sizeof(T)
+    // frames); npw = 32/lanes nodes of equal degree form a warp task.  Tasks are spread longest-first over
+    // the warps and each warp's task list is stored run-length encoded as SEGMENTS (runs of tasks of one
+    // degree); message slots, variable positions ("positions": variables renumbered into schedule order so
+    // that the variable phase walks llr/out contiguously) and index entries are numbered warp-major in
     // list order.  Inside a segment a warp therefore only advances three pointers by compile-time
     // strides: no per-task descriptor, no per-task dispatch.
     //
