@@ -250,3 +250,74 @@ def test_cli_results_file(built_lib, tmp_path):
     assert "N : 1152" in r.stdout and "== Decoder Parameters" in r.stdout and "FEC   |      FRAME" in r.stdout
     bad = subprocess.run([cli, H_FILE, str(out), "3", "1", "0.5"], capture_output=True, text=True)
     assert bad.returncode == 1 and "snr min > snr max" in bad.stdout
+
+
+@pytest.fixture(scope="module")
+def irregular_code(tmp_path_factory):
+    """A small irregular code that fits shared memory and exercises every node-update body: check degrees 2..13
+    (fixed-degree bodies 2..8 and the generic path), variable degrees 0..~25 (bodies 0..8 and the chunked path)."""
+    rng = np.random.default_rng(2024)
+    nc, mc = 420, 240
+    w = 1.0 / (1 + np.arange(nc)) ** 0.7          # skewed column popularity -> a wide spread of variable degrees
+    w[-3:] = 0                                    # three variables without any edge (degree 0)
+    w /= w.sum()
+    edges = []
+    for r in range(mc):
+        deg = 2 + (r % 12)
+        cols = rng.choice(nc, size=deg, replace=False, p=w)
+        edges += [(r, int(c)) for c in cols]
+    edges.append((mc - 1, nc - 4))                # make sure the last-but-three column exists with degree 1
+    edges = sorted(set(edges), key=lambda e: (e[0], rng.random()))   # rows grouped, columns in random file order
+    path = tmp_path_factory.mktemp("irr") / "irregular.txt"
+    with open(path, "w") as f:
+        f.write("puncture [3]: 0 5 9 \nshorten [2]: 17 33 \n")
+        f.write("\n".join(f"{r} {c}" for r, c in edges) + "\n")
+        f.write(f"{mc - 1} {nc - 1} 0\n")         # explicit zero-valued entry pins nc (stored as 1 by the reference: sparse.h:124)
+    return str(path)
+
+
+@pytest.mark.parametrize("tmem", [0, 1])
+@pytest.mark.parametrize("decoding,et,iters", [("BP_MS", True, 40), ("BP_MS", False, 9), ("BP", True, 25), ("BP", False, 3)])
+def test_irregular_code_all_bodies(built_lib, irregular_code, decoding, et, iters, tmem):
+    from libldpc_b200 import api
+    from oracle import oracle as O
+    ctx = api.Context(irregular_code, "", device=0)
+    oc = O.Code(irregular_code)
+    ctx.set_tuning(precision=api.F64, residency=api.SMEM, tmem=tmem)
+    rng = np.random.default_rng(99)
+    llr = rng.normal(1.4, 1.9, size=(37, oc.nc))
+    llr[:, oc.puncture] = 0.0
+    llr[:, oc.shorten] = 99999.9
+    llr[2, ::5] = -0.0
+    ro, rc, ri = oc.decode(llr, iters, et, decoding == "BP_MS")
+    out, hard, its = ctx.decode_batch(llr, decoding, iters, et)
+    assert np.array_equal(its, ri)
+    if decoding == "BP_MS":
+        assert np.array_equal(hard, rc)
+        assert np.array_equal(out.view(np.uint64), ro.view(np.uint64))
+    else:
+        assert (hard == rc).mean() >= 0.9999
+        assert _rel_err(out, ro).max() < BP_RTOL
+    g = ctx.sim_point("BSC", 0.04, seed=3, point=0, frame0=0, nframes=300, decoding=decoding, iterations=iters, early_term=et)
+    o = oc.sim_point("BSC", 0.04, seed=3, point=0, frame0=0, nframes=300, decoding=decoding, iterations=iters, early_term=et, threads=8)
+    if decoding == "BP_MS":
+        assert {k: g[k] for k in ("fec", "bec", "frames", "iters")} == o
+    ctx.close()
+
+
+def test_cli_with_generator_matrix(built_lib, tmp_path):
+    """-G: the sweep transmits random codewords; the curve stays that of the code (decoders are symmetric)."""
+    import os, subprocess
+    from conftest import ROOT
+    cli = os.path.join(ROOT, "libldpc_b200", "ldpcsim")
+    outs = []
+    for extra in ([], ["-G", G_FILE]):
+        out = tmp_path / ("res%d.txt" % len(outs))
+        r = subprocess.run([cli, H_FILE, str(out), "-5.5", "-5.4", "0.5", "--decoding", "BP_MS", "--frame-error-count", "400",
+                            "--max-frames", "40000", "-s", "3"] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        x, fer, ber, frames, avg_iter, t = out.read_text().split("\n")[1].split()
+        outs.append((float(fer), int(frames)))
+    (f0, n0), (f1, n1) = outs
+    p = (f0 * n0 + f1 * n1) / (n0 + n1)
+    assert abs(f0 - f1) < 4 * np.sqrt(p * (1 - p) * (1 / n0 + 1 / n1)) + 1e-9, outs
