@@ -193,7 +193,6 @@ namespace b200
     const SegLayout &Engine::layout_for(int precision, int alg, int *residency, size_t *smem_bytes)
     {
         const int vec = precision == LDPC_B200_F32 ? 4 : 2;
-        (void)alg;
         const int max_threads = B200_TILE_MAX_THREADS; // compile-time cap of the kernels (tile4.cuh)
         const int threads = tuning.threads_per_cta > 0 ? std::min(tuning.threads_per_cta, max_threads) : max_threads;
         int want_lanes = 0;
@@ -224,8 +223,14 @@ namespace b200
             if (tuning.residency == LDPC_B200_SMEM) throw std::runtime_error("code does not fit shared-memory residency with this tuning");
         }
         *residency = LDPC_B200_GLOBAL;
-        *smem_bytes = u_bytes(want_lanes ? want_lanes : 1);
-        return get_seg_layout(want_lanes ? want_lanes : 1, threads);
+        int g_lanes = want_lanes ? want_lanes : 1, g_threads = threads;
+        if (!want_lanes && tuning.threads_per_cta <= 0)
+        { // global residency, nothing pinned by the caller: the autotuned (lanes, threads) of this (precision, algorithm)
+            auto it = tuned_.find(std::make_pair(precision, alg));
+            if (it != tuned_.end()) { g_lanes = it->second.first; g_threads = it->second.second; }
+        }
+        *smem_bytes = u_bytes(g_lanes);
+        return get_seg_layout(g_lanes, g_threads);
     }
 
     Engine::Config Engine::choose(int precision, int alg, uint64_t n_frames)
@@ -439,6 +444,14 @@ namespace b200
         }
 
         const int alg = minsum ? ALG_MS : ALG_BP;
+        if (!in_autotune_ && n_frames >= 20000 && tuning.frames_per_cta <= 0 && tuning.threads_per_cta <= 0 &&
+            !tuned_.count(std::make_pair(tuning.precision, alg)))
+        {
+            int res = 0;
+            size_t sb = 0;
+            layout_for(tuning.precision, alg, &res, &sb);
+            if (res == LDPC_B200_GLOBAL) autotune_global(alg, dp, s);
+        }
         const Config c = choose(tuning.precision, alg, n_frames);
         DeviceSegLayout &dl = device_seg_layout(c.lanes, c.threads);
         const SegLayout &l = *dl.host;
@@ -501,6 +514,73 @@ namespace b200
         stats.launches += 1;
         stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;
         stats.residency = c.residency; stats.precision = c.precision; stats.smem_bytes = c.smem_bytes;
+    }
+
+    // Global residency has no single best tile shape: quasi-cyclic codes whose neighbouring checks gather neighbouring
+    // variables like narrow records and many CTAs, codes with scattered gathers like wide records (whole 64-byte
+    // sectors per gather).  One-off trial of a few (lanes, threads) shapes on synthetic AWGN frames, fixed iterations;
+    // the winner is cached per (precision, algorithm) and used whenever the caller pins nothing.
+    void Engine::autotune_global(int alg, const decoder_param &dp, void *stream)
+    {
+        cudaStream_t s = (cudaStream_t)stream;
+        const auto key = std::make_pair(tuning.precision, alg);
+        const ldpc_b200_tuning saved = tuning;
+        const ldpc_b200_stats saved_stats = stats;
+        in_autotune_ = true;
+        unsigned long long *d_cnt = nullptr;
+        double best = -1;
+        std::pair<int, int> best_cfg(1, std::min(512, B200_TILE_MAX_THREADS));
+        try
+        {
+            CUDA_OK(cudaMalloc(&d_cnt, 8 * sizeof(unsigned long long)));
+            CUDA_OK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), s));
+            const int vec = tuning.precision == LDPC_B200_F32 ? 4 : 2;
+            decoder_param tdp = dp;
+            tdp.earlyTerm = false;
+            tdp.iterations = std::min<uint32_t>(dp.iterations, 20); // enough iterations that decoding, not frame generation, dominates
+            const int cand[6][2] = {{1, 512}, {2, 512}, {4, 512}, {1, 256}, {2, 256}, {4, 256}};
+            for (const auto &cd : cand)
+            {
+                tuning.residency = LDPC_B200_GLOBAL;
+                tuning.frames_per_cta = cd[0] * vec;
+                tuning.threads_per_cta = cd[1];
+                tuning.zero_codeword = 1;
+                FrameSource src;
+                src.kind = SRC_AWGN;
+                src.x = 3.0;
+                src.seed = 0x5eed;
+                FrameSink sink;
+                sink.d_counters = d_cnt;
+                const uint64_t frames = (uint64_t)sm_count_ * 2 * 16; // whole waves for every shape (the widest holds 16 frames per CTA)
+                try
+                {
+                    launch(tdp, src, sink, frames / 4, s); // warm-up (tables, state block)
+                    CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
+                    launch(tdp, src, sink, frames, s);
+                    CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));
+                    CUDA_OK(cudaEventSynchronize((cudaEvent_t)ev1_));
+                    float ms = 0;
+                    CUDA_OK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
+                    const double rate = (double)frames / ms;
+                    if (rate > best) { best = rate; best_cfg = std::make_pair(cd[0], cd[1]); }
+                }
+                catch (const std::exception &)
+                { // a shape that does not fit is simply not a candidate
+                    cudaGetLastError();
+                }
+            }
+        }
+        catch (...)
+        {
+            cudaFree(d_cnt);
+            tuning = saved; stats = saved_stats; in_autotune_ = false;
+            throw;
+        }
+        cudaFree(d_cnt);
+        tuning = saved;
+        stats = saved_stats;
+        in_autotune_ = false;
+        tuned_[key] = best_cfg;
     }
 
     void Engine::launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream)

@@ -83,6 +83,7 @@ namespace b200
         const SegLayout &get_seg_layout(int lanes, int threads);
         DeviceSegLayout &device_seg_layout(int lanes, int threads);
         const TileLayout &get_layout(int fpc, int threads);
+        void autotune_global(int alg, const decoder_param &dp, void *stream);
         void launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
         DeviceLayout &device_layout(int fpc, int threads, bool idx16);
         void ensure_state(size_t bytes);
@@ -98,6 +99,8 @@ namespace b200
         std::map<std::pair<int, int>, std::unique_ptr<SegLayout>> seg_layouts_;
         std::map<std::pair<int, int>, std::unique_ptr<DeviceSegLayout>> dev_seg_layouts_;
         std::map<std::tuple<int, int, int, int, int, size_t>, int> occupancy_;
+        std::map<std::pair<int, int>, std::pair<int, int>> tuned_; // (precision, alg) -> autotuned (lanes, threads), global residency
+        bool in_autotune_ = false;
         int32_t *d_bit_pos_ = nullptr, *d_punct_ = nullptr, *d_short_ = nullptr;
         int32_t *d_g_col_ptr_ = nullptr, *d_g_row_ = nullptr; // generator matrix by column (device)
         unsigned long long *d_counters_ = nullptr;
