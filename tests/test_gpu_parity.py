@@ -321,3 +321,26 @@ def test_cli_with_generator_matrix(built_lib, tmp_path):
     (f0, n0), (f1, n1) = outs
     p = (f0 * n0 + f1 * n1) / (n0 + n1)
     assert abs(f0 - f1) < 4 * np.sqrt(p * (1 - p) * (1 / n0 + 1 / n1)) + 1e-9, outs
+
+
+def test_full_size_counters_identical_across_kernel_variants(gpu_ctx):
+    """At the bench's step size (303,104 frames, 50 iterations): the shared-memory kernel with the TMEM mirror, without it,
+    and the global-residency kernel do the same IEEE operations in the same order, so the four counters must be IDENTICAL;
+    early termination on/off must agree on everything but the iteration count for frames that converge."""
+    from libldpc_b200 import api
+    n = 148 * 4 * 512
+    kw = dict(seed=21, point=4, frame0=1 << 40, nframes=n, decoding="BP_MS", iterations=50)
+    res = {}
+    for name, t in (("smem+tmem", dict(residency=api.SMEM, tmem=0)), ("smem", dict(residency=api.SMEM, tmem=1)), ("global", dict(residency=api.GLOBAL, tmem=0))):
+        gpu_ctx.set_tuning(precision=api.F64, frames_per_cta=0, threads_per_cta=0, **t)
+        res[name] = {et: gpu_ctx.sim_point("AWGN", -4.2, early_term=et, **kw) for et in (True, False)}
+    gpu_ctx.set_tuning(residency=api.AUTO, tmem=0)
+    for et in (True, False):
+        ref = {k: res["smem+tmem"][et][k] for k in ("fec", "bec", "frames", "iters")}
+        assert ref["frames"] == n
+        for name in ("smem", "global"):
+            assert {k: res[name][et][k] for k in ("fec", "bec", "frames", "iters")} == ref, (name, et)
+    a, b = res["smem+tmem"][True], res["smem+tmem"][False]
+    assert b["iters"] == 50 * n and a["iters"] < b["iters"]
+    # a frame that never satisfies all checks is decoded identically; one that does almost always keeps its decisions
+    assert abs(a["fec"] - b["fec"]) <= 0.005 * b["fec"] + 5
