@@ -285,7 +285,11 @@ namespace b200
             if (it == occupancy_.end())
                 it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.tm, true, c.lanes, c.threads, c.smem_bytes)).first;
             if (it->second < 1) throw std::runtime_error("tile kernel does not fit on this device with the current tuning");
-            ctas = sm_count_ * it->second;
+            int per_sm = it->second;
+            // every resident CTA of a TM kernel holds tm_alloc_cols of the SM's 512 TMEM columns: do not launch more
+            // CTAs per SM than can hold their allocation at the same time (the others would wait inside tcgen05.alloc)
+            if (c.tm) per_sm = std::max(1, std::min(per_sm, (int)(512u / c.tm_alloc_cols)));
+            ctas = sm_count_ * per_sm;
         }
         const uint64_t need = (n_frames + c.fpc - 1) / c.fpc;
         if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
