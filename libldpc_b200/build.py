@@ -13,7 +13,8 @@ CLI = os.path.join(HERE, "ldpcsim")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
-SOURCES = ["tile_ms_f64.cu", "tile_ms_f32.cu", "tile_bp_f64.cu", "tile_bp_f32.cu", "engine.cu", "code.cpp", "sim_driver.cpp", "shim.cpp"]
+TILE_SOURCES = ["tile_%s_%s_l%d.cu" % (a, t, l) for a in ("bp", "ms") for t in ("f64", "f32") for l in (1, 2, 4)]  # slowest first
+SOURCES = TILE_SOURCES + ["engine.cu", "code.cpp", "sim_driver.cpp", "shim.cpp"]
 HEADERS = ["engine.hpp", "code.hpp", "kernels.cuh", "tile4.cuh", "tile_launch.cuh", "bec_kernel.cuh", "../../include/ldpc_b200.h"]
 OBJDIR = os.path.join(HERE, "build")
 if os.environ.get("B200_PHASE_TIMING"):  # debug: per-warp phase cycle counts printed by CTA 0

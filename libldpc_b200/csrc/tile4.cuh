@@ -265,13 +265,15 @@ namespace b200
         typedef Vec<T> V;
         static constexpr int VEC = V::N, CS = 512;
 
-        // CSRC: the old c2v values come from shared/global memory (0) or from the thread's TMEM mirror at
+        // CSRC: the old c2v values come from shared/global memory (0, 2) or from the thread's TMEM mirror at
         // columns tc + 4k (1); TMW: new values are also written to that mirror.
         // nx: in = this node's index entries (byte offsets), out = those of the node at ip_next when `more`
         // (software prefetch: the load is in flight while this node is computed).
         // PAR: also return the syndrome bits (only early termination consumes them, decoder.cpp:66-72).
+        // fz (CSRC == 2 only): frame lanes of this vector that hold a fresh frame — their old c2v is +0 by definition
+        // (decoder.cpp:16-19) whatever the slots still contain, so a refill never has to clear the message array.
         template <int CSRC, bool TMW, bool PAR>
-        static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, uint32_t (&nx)[D], P ip_next, bool more, uint32_t tc)
+        static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, uint32_t (&nx)[D], P ip_next, bool more, uint32_t tc, uint32_t fz)
         {
             uint32_t eo[D];
 #pragma unroll
@@ -293,6 +295,11 @@ namespace b200
                     V c;
                     if constexpr (CSRC == 1) { c = TmAcc<T>::ld(tc + 4 * k.value); tm_wait_ld(); }
                     else c = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
+                    if constexpr (CSRC == 2)
+                    {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) c.e[e] = ((fz >> e) & 1u) ? T(0) : c.e[e];
+                    }
 #pragma unroll
                     for (int e = 0; e < VEC; ++e)
                     {
@@ -324,6 +331,15 @@ namespace b200
                     else c[k.value] = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
                 });
                 if constexpr (CSRC == 1) tm_wait_ld();
+                if constexpr (CSRC == 2)
+                {
+#pragma unroll
+                    for (int k = 0; k < D; ++k)
+                    {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) c[k].e[e] = ((fz >> e) & 1u) ? T(0) : c[k].e[e];
+                    }
+                }
                 static_for<D>([&](auto k) {
                     const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[k.value]);
 #pragma unroll
@@ -391,7 +407,8 @@ namespace b200
     // arbitrary degree (9..64): running min1/min2 + sign mask for min-sum, parked forward values for box-plus.
     // The index block is walked in 16-byte chunks (chunk q at ip + q*NPW*16).
     template <typename T, typename IdxT, bool SMEM, int LANES, int ALG>
-    __device__ __noinline__ uint32_t cn4_any(typename PtrOf<SMEM>::type out_sub, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type ip, int deg)
+    __device__ __noinline__ uint32_t cn4_any(typename PtrOf<SMEM>::type out_sub, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type ip, int deg,
+                                             uint32_t fz)
     {
         typedef Vec<T> V;
         typedef IdxChunk<SMEM, IdxT> IC;
@@ -415,7 +432,9 @@ namespace b200
                     if (k < deg)
                     {
                         const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[q]);
-                        const V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                        V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) c.e[e] = ((fz >> e) & 1u) ? T(0) : c.e[e];
 #pragma unroll
                         for (int e = 0; e < VEC; ++e)
                         {
@@ -463,7 +482,9 @@ namespace b200
                     if (k < deg)
                     {
                         const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[q]);
-                        const V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                        V c = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) c.e[e] = ((fz >> e) & 1u) ? T(0) : c.e[e];
                         V vk;
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) { vk.e[e] = o.e[e] - c.e[e]; par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u; }
@@ -642,6 +663,7 @@ namespace b200
         // A refill rewrites c2v / llr in shared memory behind the TMEM mirror's back: the next check phase and the
         // next variable phase read shared memory (and refresh the mirror).  CTA-uniform.
         bool cn_stale = true, vn_stale = true;
+        uint32_t fresh = 0; // frame lanes refilled since the last check phase (CTA-uniform)
 
         // bit of the codeword of frame lane g at transmitted index t: parity of the information bits selected by
         // column tx_var[t] of the generator matrix (src/core/sparse.h:162-187); 0 without a generator matrix
@@ -660,12 +682,11 @@ namespace b200
         };
 
         // Writes the decoder input of global frame gf into frame lane g (all threads of the CTA
-        // cooperate), with the fresh-frame state: out = LLRin, c2v = +0.
+        // cooperate), with the fresh-frame state: out = LLRin (c2v = +0 is implied by the `fresh` mask).
         auto generate = [&](int g, unsigned long long gf)
         {
             const int eo = (g / VEC) * 16 + (g % VEC) * TS; // byte offset of lane g inside a record
-            const P dl = llr + eo, dout = out + eo, dc = c2v + eo;
-            for (int i = tid; i < p.n_slots; i += nthreads) Acc<SMEM, T, 0>::st(dc + i * RS, T(0));
+            const P dl = llr + eo, dout = out + eo; // c2v is not cleared: the next check phase takes a fresh lane's c2v as +0 (`fresh`)
             auto put = [&](int pos, T v)
             {
                 Acc<SMEM, T, 0>::st(dl + pos * RS, v);
@@ -811,6 +832,7 @@ namespace b200
             __syncthreads();
             active = new_active;
             skip = s_skip;
+            fresh |= mask & new_active;
             cn_stale = true;
             vn_stale = true;
         };
@@ -850,6 +872,7 @@ namespace b200
             auto cn_phase = [&](auto csrc)
             {
                 constexpr int CSRC = decltype(csrc)::value;
+                const uint32_t fz = (fresh >> (sub * VEC)) & VMASK;
                 uint32_t tc = tm_w;
                 uint4 sg_next = WAcc<SMEM, 0>::ld4(cn_seg_w);
                 for (P sp = cn_seg_w;;)
@@ -883,7 +906,7 @@ namespace b200
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
             ip += NPW * ST;                                                                                  \
-            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM, ET>(out_sub, c2v0, nx, ip, nt > 1, tc) & keep; \
+            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM, ET>(out_sub, c2v0, nx, ip, nt > 1, tc, fz) & keep; \
             c2v0 += D * 512;                                                                                 \
             if constexpr (TM) tc += 4 * D;                                                                   \
         }                                                                                                    \
@@ -904,7 +927,7 @@ namespace b200
                         P ip = ib + j * 16;
                         for (; nt > 0; --nt)
                         {
-                            bad |= cn4_any<T, IdxT, SMEM, LANES, ALG>(out_sub, c2v0, ip, deg) & keep;
+                            bad |= cn4_any<T, IdxT, SMEM, LANES, ALG>(out_sub, c2v0, ip, deg, CSRC == 2 ? fz : 0u) & keep;
                             c2v0 += deg * 512;
                             ip += NPW * st;
                         }
@@ -915,9 +938,11 @@ namespace b200
                 }
                 if constexpr (TM) tm_wait_st();
             };
-            if (TM && !cn_stale) cn_phase(std::integral_constant<int, TM ? 1 : 0>{});
-            else cn_phase(std::integral_constant<int, 0>{});
+            // right after a refill: old c2v from memory with the fresh lanes forced to +0; otherwise the fast source
+            if (!cn_stale) cn_phase(std::integral_constant<int, TM ? 1 : 0>{});
+            else cn_phase(std::integral_constant<int, 2>{});
             cn_stale = false;
+            fresh = 0;
             // syndrome flags per frame lane: frame = sub*VEC + e
             if constexpr (ET)
             {

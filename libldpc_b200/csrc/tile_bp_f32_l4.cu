@@ -1,0 +1,6 @@
+// tile kernel instantiation: T = float, algorithm = ALG_BP, lanes per node = 4
+#include "tile_launch.cuh"
+namespace b200
+{
+    B200_DEFINE_TILE_LANES(float, ALG_BP, 4)
+}

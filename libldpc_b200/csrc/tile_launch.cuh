@@ -10,15 +10,9 @@
 namespace b200
 {
     // Four variants per (T, ALG, lanes): shared-memory residency with the TMEM mirror (with / without the
-    // early-termination syndrome: --no-early-term runs skip it), shared-memory residency without the mirror,
+    // early-termination syndrome: --no-early-term min-sum runs skip it), shared-memory residency without the mirror,
     // global residency.  Index entries are 32-bit byte offsets.
     // lanes = warp lanes per node (frames per CTA = lanes * 16/sizeof(T)).
-    template <typename T, int ALG>
-    void launch_tile_family(const K4Params &kp, bool smem, bool tm, bool et, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
-
-    // resident CTAs per SM the runtime grants this configuration (occupancy query; 0 = does not fit)
-    template <typename T, int ALG>
-    int tile_family_occupancy(bool smem, bool tm, bool et, int lanes, int threads, size_t smem_bytes);
 
     constexpr int TILE_SMEM_OPTIN = 232448 - 1024; // 227 KB minus the kernel's static shared memory
 
@@ -53,40 +47,51 @@ namespace b200
         return n;
     }
 
-#define B200_DEFINE_TILE_FAMILY(T, ALG)                                                                                \
-    template <>                                                                                                        \
-    void launch_tile_family<T, ALG>(const K4Params &kp, bool smem, bool tm, bool et, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
-    {                                                                                                                  \
-        switch (lanes)                                                                                                 \
-        {                                                                                                              \
-            B200_TILE_LAUNCH_CASES(T, ALG)                                                                             \
-        default: throw std::runtime_error("lanes per node must be 1, 2 or 4");                                      \
-        }                                                                                                              \
-    }                                                                                                                  \
-    template <>                                                                                                        \
-    int tile_family_occupancy<T, ALG>(bool smem, bool tm, bool et, int lanes, int threads, size_t smem_bytes)                \
-    {                                                                                                                  \
-        switch (lanes)                                                                                                 \
-        {                                                                                                              \
-            B200_TILE_OCC_CASES(T, ALG)                                                                                \
-        default: throw std::runtime_error("lanes per node must be 1, 2 or 4");                                      \
-        }                                                                                                              \
-        return 0;                                                                                                      \
-    }
+    // One translation unit per (T, ALG, lanes) — tile_<alg>_<prec>_l<lanes>.cu — so that the build compiles the kernel
+    // variants in parallel; engine.cu holds the dispatch over `lanes`.
+    template <typename T, int ALG, int L>
+    void launch_tile_lanes(const K4Params &kp, bool smem, bool tm, bool et, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
+    template <typename T, int ALG, int L>
+    int occupancy_tile_lanes(bool smem, bool tm, bool et, int threads, size_t smem_bytes);
 
-#define B200_LAUNCH_CASE(T, ALG, L)                                                                                    \
-    case L:                                                                                                            \
+#define B200_DEFINE_TILE_LANES(T, ALG, L)                                                                              \
+    template <>                                                                                                        \
+    void launch_tile_lanes<T, ALG, L>(const K4Params &kp, bool smem, bool tm, bool et, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
+    {                                                                                                                  \
         if (smem && tm && (et || ALG != ALG_MS)) launch_tile_one<T, ALG, true, L, true, true>(kp, ctas, threads, smem_bytes, s); \
         else if (smem && tm) launch_tile_one<T, ALG, true, L, true, ALG != ALG_MS>(kp, ctas, threads, smem_bytes, s);  \
         else if (smem) launch_tile_one<T, ALG, true, L, false, true>(kp, ctas, threads, smem_bytes, s);                \
         else launch_tile_one<T, ALG, false, L, false, true>(kp, ctas, threads, smem_bytes, s);                         \
-        return;
-#define B200_OCC_CASE(T, ALG, L)                                                                                       \
-    case L:                                                                                                            \
+    }                                                                                                                  \
+    template <>                                                                                                        \
+    int occupancy_tile_lanes<T, ALG, L>(bool smem, bool tm, bool et, int threads, size_t smem_bytes)                   \
+    {                                                                                                                  \
         return (smem && tm && (et || ALG != ALG_MS)) ? occupancy_tile_one<T, ALG, true, L, true, true>(threads, smem_bytes) \
                : (smem && tm)     ? occupancy_tile_one<T, ALG, true, L, true, ALG != ALG_MS>(threads, smem_bytes)      \
                : smem             ? occupancy_tile_one<T, ALG, true, L, false, true>(threads, smem_bytes)              \
-                                  : occupancy_tile_one<T, ALG, false, L, false, true>(threads, smem_bytes);
-#define B200_TILE_LAUNCH_CASES(T, ALG) B200_LAUNCH_CASE(T, ALG, 1) B200_LAUNCH_CASE(T, ALG, 2) B200_LAUNCH_CASE(T, ALG, 4)
-#define B200_TILE_OCC_CASES(T, ALG) B200_OCC_CASE(T, ALG, 1) B200_OCC_CASE(T, ALG, 2) B200_OCC_CASE(T, ALG, 4)
+                                  : occupancy_tile_one<T, ALG, false, L, false, true>(threads, smem_bytes);            \
+    }
+
+    template <typename T, int ALG>
+    void launch_tile_family(const K4Params &kp, bool smem, bool tm, bool et, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
+    {
+        switch (lanes)
+        {
+        case 1: launch_tile_lanes<T, ALG, 1>(kp, smem, tm, et, ctas, threads, smem_bytes, s); return;
+        case 2: launch_tile_lanes<T, ALG, 2>(kp, smem, tm, et, ctas, threads, smem_bytes, s); return;
+        case 4: launch_tile_lanes<T, ALG, 4>(kp, smem, tm, et, ctas, threads, smem_bytes, s); return;
+        default: throw std::runtime_error("lanes per node must be 1, 2 or 4");
+        }
+    }
+    template <typename T, int ALG>
+    int tile_family_occupancy(bool smem, bool tm, bool et, int lanes, int threads, size_t smem_bytes)
+    {
+        switch (lanes)
+        {
+        case 1: return occupancy_tile_lanes<T, ALG, 1>(smem, tm, et, threads, smem_bytes);
+        case 2: return occupancy_tile_lanes<T, ALG, 2>(smem, tm, et, threads, smem_bytes);
+        case 4: return occupancy_tile_lanes<T, ALG, 4>(smem, tm, et, threads, smem_bytes);
+        default: throw std::runtime_error("lanes per node must be 1, 2 or 4");
+        }
+    }
 } // namespace b200

@@ -342,5 +342,6 @@ def test_full_size_counters_identical_across_kernel_variants(gpu_ctx):
             assert {k: res[name][et][k] for k in ("fec", "bec", "frames", "iters")} == ref, (name, et)
     a, b = res["smem+tmem"][True], res["smem+tmem"][False]
     assert b["iters"] == 50 * n and a["iters"] < b["iters"]
-    # a frame that never satisfies all checks is decoded identically; one that does almost always keeps its decisions
-    assert abs(a["fec"] - b["fec"]) <= 0.005 * b["fec"] + 5
+    # a frame that never satisfies all checks is decoded identically; one that does usually, but not always, keeps its
+    # decisions when min-sum keeps iterating past the codeword
+    assert abs(a["fec"] - b["fec"]) <= 0.03 * b["fec"] + 5
