@@ -9,6 +9,7 @@
 
 #include "tile_launch.cuh"
 #include "bec_kernel.cuh"
+#include "bec_slice.cuh"
 
 namespace b200
 {
@@ -117,6 +118,7 @@ namespace b200
         dev_seg_layouts_.clear();
         cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
         cudaFree(d_g_col_ptr_); cudaFree(d_g_row_);
+        cudaFree(d_bs_row_ptr_); cudaFree(d_bs_row_edge_); cudaFree(d_bs_col_ptr_); cudaFree(d_bs_col_edge_); cudaFree(d_bs_tx_flag_);
         for (int b = 0; b < 2; ++b)
         {
             cudaFree(db_in_[b]); cudaFree(db_out_[b]); cudaFree(db_hard_[b]); cudaFree(db_it_[b]);
@@ -590,6 +592,50 @@ namespace b200
     void Engine::launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream)
     {
         cudaStream_t s = (cudaStream_t)stream;
+        // Sweep mode (frames generated on the device, only the counters leave it): the bit-sliced kernel, 32 frames per
+        // word, when one word's state (a bit per edge and per variable) fits shared memory; the byte-wise kernel below
+        // serves caller-supplied frames (decode API: per-frame outputs) and larger codes.
+        const size_t slice_group_bytes = 4 * ((size_t)H.nnz + H.nc + 8);
+        const size_t slice_limit = smem_optin_ > 2048 ? smem_optin_ - 2048 : 0;
+        if (!src.d_bec_in && !sink.d_bec_out && !sink.d_hard && !sink.d_iters && H.min_cn_degree >= 2 && slice_group_bytes <= slice_limit &&
+            tuning.residency != LDPC_B200_GLOBAL)
+        {
+            if (!d_bs_row_ptr_)
+            {
+                std::vector<int32_t> rp(H.row_ptr.begin(), H.row_ptr.end()), re(H.row_edge.begin(), H.row_edge.end());
+                std::vector<int32_t> cp(H.col_ptr.begin(), H.col_ptr.end()), ce(H.col_edge.begin(), H.col_edge.end());
+                std::vector<uint8_t> tf(H.nc, 0);
+                for (int v : H.bit_pos) tf[v] = 1;
+                d_bs_row_ptr_ = upload(rp); d_bs_row_edge_ = upload(re); d_bs_col_ptr_ = upload(cp); d_bs_col_edge_ = upload(ce);
+                d_bs_tx_flag_ = upload(tf);
+                CUDA_OK(cudaFuncSetAttribute(bec_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_limit));
+            }
+            BecSliceParams bp{};
+            bp.row_ptr = d_bs_row_ptr_; bp.row_edge = d_bs_row_edge_; bp.col_ptr = d_bs_col_ptr_; bp.col_edge = d_bs_col_edge_;
+            bp.tx_var = d_bit_pos_; bp.punct = d_punct_; bp.shorten = d_short_; bp.tx_flag = d_bs_tx_flag_;
+            bp.nc = H.nc; bp.mc = H.mc; bp.nnz = H.nnz; bp.nct = H.nct();
+            bp.n_punct = (int)H.puncture.size(); bp.n_short = (int)H.shorten.size();
+            bp.max_iter = (int)dp.iterations; bp.early_term = dp.earlyTerm ? 1 : 0; bp.deg1_compat = tuning.bec_deg1_compat;
+            {
+                double t = std::floor(src.x * 4294967296.0);
+                bp.thr = t <= 0 ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+            }
+            bp.seed = src.seed; bp.point = src.point; bp.frame0 = src.frame0; bp.n_frames = n_frames;
+            bp.counters = sink.d_counters ? sink.d_counters : d_counters_;
+            const uint64_t n_words = (n_frames + 31) / 32;
+            int groups = (int)std::min<size_t>(8, slice_limit / slice_group_bytes);
+            groups = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)groups, n_words));
+            bp.groups_per_cta = groups;
+            int ctas = tuning.ctas > 0 ? tuning.ctas : sm_count_;
+            const uint64_t need = (n_words + groups - 1) / groups;
+            if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
+            bec_slice_kernel<<<ctas, groups * BEC_TPG, groups * slice_group_bytes, s>>>(bp);
+            CUDA_OK(cudaGetLastError());
+            stats.launches += 1;
+            stats.frames_per_cta = 32 * groups; stats.threads_per_cta = groups * BEC_TPG; stats.ctas = ctas;
+            stats.residency = LDPC_B200_SMEM; stats.precision = -1; stats.smem_bytes = groups * slice_group_bytes;
+            return;
+        }
         const int threads = 1024;
         const TileLayout &l = get_layout(32, threads);
         const bool idx16 = std::max({l.n_slots, l.n_vslots, H.nc}) <= 65535;

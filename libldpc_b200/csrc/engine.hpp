@@ -103,6 +103,8 @@ namespace b200
         bool in_autotune_ = false;
         int32_t *d_bit_pos_ = nullptr, *d_punct_ = nullptr, *d_short_ = nullptr;
         int32_t *d_g_col_ptr_ = nullptr, *d_g_row_ = nullptr; // generator matrix by column (device)
+        int32_t *d_bs_row_ptr_ = nullptr, *d_bs_row_edge_ = nullptr, *d_bs_col_ptr_ = nullptr, *d_bs_col_edge_ = nullptr; // bit-sliced BEC kernel
+        uint8_t *d_bs_tx_flag_ = nullptr;
         unsigned long long *d_counters_ = nullptr;
         unsigned char *d_state_ = nullptr;
         size_t state_bytes_ = 0;

@@ -345,3 +345,23 @@ def test_full_size_counters_identical_across_kernel_variants(gpu_ctx):
     # a frame that never satisfies all checks is decoded identically; one that does usually, but not always, keeps its
     # decisions when min-sum keeps iterating past the codeword
     assert abs(a["fec"] - b["fec"]) <= 0.03 * b["fec"] + 5
+
+
+@pytest.mark.parametrize("et,iters,compat", [(True, 50, 1), (False, 7, 1), (True, 20, 0), (True, 1, 1)])
+def test_bec_bit_sliced_sweep_equals_bytewise_and_oracle(gpu_ctx, oracle_code, et, iters, compat):
+    """Erasure sweep: the bit-sliced kernel (32 frames per word, shared memory) against the byte-wise kernel (forced by
+    residency=GLOBAL) on ragged frame counts, and both against the oracle's frame loop."""
+    from libldpc_b200 import api
+    gpu_ctx.set_tuning(bec_deg1_compat=compat)
+    for eps, n in ((0.88, 1000), (0.6, 333), (0.93, 65)):
+        kw = dict(seed=8, point=1, frame0=77, nframes=n, decoding="BP", iterations=iters, early_term=et)
+        gpu_ctx.set_tuning(residency=api.AUTO)
+        a = gpu_ctx.sim_point("BEC", eps, **kw)
+        st = gpu_ctx.stats()
+        assert st["residency"] == api.SMEM and st["frames_per_cta"] % 32 == 0      # the bit-sliced kernel ran
+        gpu_ctx.set_tuning(residency=api.GLOBAL)
+        b = gpu_ctx.sim_point("BEC", eps, **kw)
+        gpu_ctx.set_tuning(residency=api.AUTO)
+        o = oracle_code.sim_point("BEC", eps, bec_deg1_compat=bool(compat), threads=8, **kw)
+        assert {k: a[k] for k in ("fec", "bec", "frames", "iters")} == {k: b[k] for k in ("fec", "bec", "frames", "iters")} == o, (eps, n)
+    gpu_ctx.set_tuning(bec_deg1_compat=1)
