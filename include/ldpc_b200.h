@@ -170,6 +170,21 @@ int ldpc_b200_channel(ldpc_b200_ctx *ctx, const char *channel, double x, uint64_
  * device_ms (may be NULL) receives the CUDA-event time of the kernel(s). */
 int ldpc_b200_sim_point(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
                         uint32_t point, uint64_t frame0, uint64_t n_frames, uint64_t counters[4], float *device_ms);
+/* Same round with the per-error diagnostics log (the reference's log_error, src/sim/ldpcsim.cpp:282-405, live in
+ * gpu/sim/ldpcsim.cpp:351-464): every frame that ends with >= 1 bit error over the transmitted positions is recorded
+ * (up to `capacity` records, unordered; *n_errors receives the number of frames in error, which may exceed capacity).
+ * A record names the GLOBAL frame index: because the channel is counter-based, ldpc_b200_channel(frame0 = record.frame,
+ * n = 1) regenerates that frame's decoder input exactly and ldpc_b200_decode_batch replays the decoding, which yields
+ * the failed bit / check indices and the syndrome weight (libldpc_b200/api.py: Context.error_report).  AWGN / BSC. */
+typedef struct
+{
+    uint64_t frame;      /* global frame index of the sweep point */
+    uint32_t bit_errors; /* Hamming distance to the transmitted word over the transmitted positions */
+    int32_t iterations;  /* reference iteration count of the frame (0-based on success, decoder.cpp:66-77) */
+} ldpc_b200_error_record;
+int ldpc_b200_sim_point_log(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
+                            uint32_t point, uint64_t frame0, uint64_t n_frames, uint64_t counters[4],
+                            ldpc_b200_error_record *records, int64_t capacity, int64_t *n_errors);
 /* Asynchronous variant: d_counters is a DEVICE array of 5 uint64 that the kernel accumulates into
  * ({frame errors, bit errors, frames, sum of reference iteration counts, sum of executed iterations}). */
 int ldpc_b200_sim_point_async(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,

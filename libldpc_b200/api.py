@@ -41,6 +41,10 @@ class tuning(ct.Structure):
     _fields_ = [(k, ct.c_int) for k in ("precision", "residency", "frames_per_cta", "threads_per_cta", "ctas", "bec_deg1_compat", "tmem", "zero_codeword")]
 
 
+class error_record(ct.Structure):  # ldpc_b200_error_record
+    _fields_ = [("frame", ct.c_uint64), ("bit_errors", ct.c_uint32), ("iterations", ct.c_int32)]
+
+
 class stats(ct.Structure):
     _fields_ = [("device_ms", ct.c_double), ("launches", ct.c_uint64), ("frames", ct.c_uint64), ("edge_iterations", ct.c_uint64),
                 ("frames_per_cta", ct.c_int), ("threads_per_cta", ct.c_int), ("ctas", ct.c_int), ("residency", ct.c_int),
@@ -58,7 +62,7 @@ HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device
                   "ldpc_b200_get_puncture", "ldpc_b200_get_layout", "ldpc_b200_rank", "ldpc_b200_encode", "ldpc_b200_syndrome",
                   "ldpc_b200_decode_batch", "ldpc_b200_decode_batch_device", "ldpc_b200_decode_bec_batch", "ldpc_b200_channel",
                   "ldpc_b200_sim_point", "ldpc_b200_sim_point_async", "ldpc_b200_simulate", "ldpc_b200_simulate_ex", "ldpc_b200_get_stats",
-                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe")
+                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe", "ldpc_b200_sim_point_log")
 
 _lib = None
 
@@ -103,6 +107,8 @@ def load_library(path=None):
     L.ldpc_b200_get_stats.argtypes = [vp, ct.POINTER(stats)]
     L.ldpc_b200_reset_stats.argtypes = [vp]
     L.ldpc_b200_smem_probe.argtypes = [vp, ct.POINTER(ct.c_double)]
+    L.ldpc_b200_sim_point_log.argtypes = [vp, decoder_param, ct.c_char_p, ct.c_double, u64, u32, u64, u64, ct.POINTER(u64), ct.POINTER(error_record),
+                                          i64, ct.POINTER(i64)]
     if path is None:
         _lib = L
     return L
@@ -235,6 +241,30 @@ class Context:
         self._check(self.lib.ldpc_b200_sim_point(self._h, self._dp(decoding, iterations, early_term), channel.encode(), float(x), int(seed),
                                                  int(point), int(frame0), int(nframes), cnt, ct.byref(ms)))
         return dict(fec=int(cnt[0]), bec=int(cnt[1]), frames=int(cnt[2]), iters=int(cnt[3]), device_ms=float(ms.value))
+
+    def sim_point_log(self, channel, x, seed=0, point=0, frame0=0, nframes=1000, decoding="BP", iterations=50, early_term=True, capacity=4096):
+        """sim_point + the per-error diagnostics log: (counters dict, list of (global frame, bit errors, iterations), frames in error)."""
+        cnt = (ct.c_uint64 * 4)()
+        rec = (error_record * max(int(capacity), 1))()
+        n = ct.c_int64()
+        self._check(self.lib.ldpc_b200_sim_point_log(self._h, self._dp(decoding, iterations, early_term), channel.encode(), float(x), int(seed),
+                                                     int(point), int(frame0), int(nframes), cnt, rec, int(capacity), ct.byref(n)))
+        m = min(int(n.value), int(capacity))
+        log = sorted((int(rec[i].frame), int(rec[i].bit_errors), int(rec[i].iterations)) for i in range(m))
+        return dict(fec=int(cnt[0]), bec=int(cnt[1]), frames=int(cnt[2]), iters=int(cnt[3])), log, int(n.value)
+
+    def error_report(self, channel, x, seed, point, frame, decoding="BP", iterations=50, early_term=True):
+        """Replays ONE logged frame (the channel is counter-based, so its input is regenerated exactly) and returns what the
+        reference's log_error prints: failed bit indices (transmitted positions), failed check indices, syndrome weight."""
+        cw, llr = self.channel(channel, x, seed, point, frame, 1)
+        out, hard, its = self.decode_batch(llr, decoding, iterations, early_term)
+        r, c = self.edges()
+        synd = np.zeros(self.mc, np.uint8)
+        np.bitwise_xor.at(synd, r, hard[0][c])
+        tx = self.bit_pos()
+        bad = tx[hard[0][tx] != cw[0][tx]]
+        return dict(frame=int(frame), iterations=int(its[0]), failed_bits=[int(b) for b in bad], hamming_distance=int(len(bad)),
+                    failed_checks=[int(i) for i in np.nonzero(synd)[0]], syndrome_weight=int(synd.sum()))
 
     def sim_point_async(self, d_counters_ptr, stream_ptr, channel, x, seed=0, point=0, frame0=0, nframes=1000, decoding="BP",
                         iterations=50, early_term=True):

@@ -491,6 +491,7 @@ namespace b200
         kp.seed = src.seed; kp.point = src.point; kp.frame0 = src.frame0; kp.n_frames = n_frames;
         kp.llr_out = sink.d_llr_out; kp.hard_out = sink.d_hard; kp.iters_out = sink.d_iters;
         kp.counters = sink.d_counters ? sink.d_counters : d_counters_;
+        kp.err_log = sink.d_err_log; kp.err_count = sink.d_err_count; kp.err_cap = sink.err_cap;
         if (c.residency == LDPC_B200_GLOBAL)
         {
             kp.state_stride = ((16 * (size_t)c.lanes * ((size_t)l.n_slots + 2 * (size_t)l.n_pos)) + 255) & ~(size_t)255;
@@ -704,6 +705,54 @@ namespace b200
         stats.device_ms += ms;
         stats.frames += h[2];
         stats.edge_iterations += h[4] * (uint64_t)H.nnz;
+    }
+
+    void Engine::sim_point_log(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point, uint64_t frame0,
+                               uint64_t n_frames, uint64_t counters[5], ldpc_b200_error_record *records, int64_t capacity, int64_t *n_errors)
+    {
+        const int kind = channel_kind(channel);
+        if (kind == SRC_BEC) throw std::runtime_error("the per-error log covers the AWGN and BSC sweeps");
+        if (capacity < 0 || (capacity > 0 && !records)) throw std::runtime_error("bad error-log buffer");
+        ensure_cuda();
+        cudaStream_t s = (cudaStream_t)stream_;
+        unsigned long long *d_log = nullptr, *d_cnt = nullptr;
+        CUDA_OK(cudaMalloc(&d_log, std::max<size_t>((size_t)capacity, 1) * 2 * sizeof(unsigned long long)));
+        CUDA_OK(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+        try
+        {
+            CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+            CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), s));
+            FrameSource src;
+            src.kind = kind;
+            src.x = x; src.seed = seed; src.point = point; src.frame0 = frame0;
+            FrameSink sink;
+            sink.d_counters = d_counters_;
+            sink.d_err_log = d_log; sink.d_err_count = d_cnt; sink.err_cap = (unsigned long long)capacity;
+            launch(dp, src, sink, n_frames, s);
+            unsigned long long h[5], n = 0;
+            CUDA_OK(cudaMemcpyAsync(h, d_counters_, sizeof(h), cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaMemcpyAsync(&n, d_cnt, sizeof(n), cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaStreamSynchronize(s));
+            const size_t m = (size_t)std::min<unsigned long long>(n, (unsigned long long)capacity);
+            std::vector<unsigned long long> raw(2 * std::max<size_t>(m, 1));
+            if (m) CUDA_OK(cudaMemcpy(raw.data(), d_log, m * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < m; ++i)
+            {
+                records[i].frame = raw[2 * i];
+                records[i].bit_errors = (uint32_t)(raw[2 * i + 1] & 0xFFFFFFFFull);
+                records[i].iterations = (int32_t)(uint32_t)(raw[2 * i + 1] >> 32);
+            }
+            if (n_errors) *n_errors = (int64_t)n;
+            for (int i = 0; i < 5; ++i) counters[i] = h[i];
+            stats.frames += h[2];
+            stats.edge_iterations += h[4] * (uint64_t)H.nnz;
+        }
+        catch (...)
+        {
+            cudaFree(d_log); cudaFree(d_cnt);
+            throw;
+        }
+        cudaFree(d_log); cudaFree(d_cnt);
     }
 
     // Host-buffer batch decode: a double-buffered pipeline over three streams — H2D of chunk k+1, the decode

@@ -35,6 +35,8 @@ namespace b200
         uint8_t *d_bec_out = nullptr;
         int32_t *d_iters = nullptr;
         unsigned long long *d_counters = nullptr; // [5]; null -> engine scratch
+        unsigned long long *d_err_log = nullptr, *d_err_count = nullptr; // per-error diagnostics log (device), capacity in records
+        unsigned long long err_cap = 0;
     };
 
     class Engine
@@ -62,6 +64,8 @@ namespace b200
                           uint8_t *cw, double *llr, uint8_t *llr_u8);
         void sim_point(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
                        uint64_t frame0, uint64_t n_frames, uint64_t counters[5], float *device_ms);
+        void sim_point_log(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point, uint64_t frame0,
+                           uint64_t n_frames, uint64_t counters[5], ldpc_b200_error_record *records, int64_t capacity, int64_t *n_errors);
         void sim_point_async(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
                              uint64_t frame0, uint64_t n_frames, unsigned long long *d_counters, void *stream);
 

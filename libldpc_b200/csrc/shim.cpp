@@ -331,6 +331,18 @@ extern "C"
         });
     }
 
+    int ldpc_b200_sim_point_log(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed, uint32_t point,
+                                uint64_t frame0, uint64_t n_frames, uint64_t counters[4], ldpc_b200_error_record *records, int64_t capacity,
+                                int64_t *n_errors)
+    {
+        return guarded([&] {
+            if (!ctx || !channel || !counters) throw std::runtime_error("null argument");
+            uint64_t c[5] = {0, 0, 0, 0, 0};
+            ctx->eng->sim_point_log(dp, channel, x, seed, point, frame0, n_frames, c, records, capacity, n_errors);
+            for (int i = 0; i < 4; ++i) counters[i] += c[i];
+        });
+    }
+
     int ldpc_b200_sim_point_async(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed, uint32_t point,
                                   uint64_t frame0, uint64_t n_frames, uint64_t *d_counters, void *stream)
     {

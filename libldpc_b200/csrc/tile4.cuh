@@ -227,6 +227,10 @@ namespace b200
         uint8_t *hard_out;
         int32_t *iters_out;
         unsigned long long *counters; // [5] fec, bec, frames, sum(ret iters), sum(executed iterations)
+        // per-error diagnostics log (may be null): records {global frame, bit errors, iterations}, err_count = frames in error
+        unsigned long long *err_log;     // [err_cap][2]: frame, bit_errors | (uint32)iterations << 32
+        unsigned long long *err_count;
+        unsigned long long err_cap;
         // global-memory residency: per-CTA state block
         unsigned char *state;
         size_t state_stride;
@@ -791,6 +795,15 @@ namespace b200
                     atomicAdd(&s_cnt[4], (unsigned long long)it);
                     s_ret[lane] = ret;
                     s_old[lane] = s_frame[lane];
+                    if (e && p.err_log)
+                    { // the frame can be regenerated from its global index (counter-based channel): that is the whole record
+                        const unsigned long long slot = atomicAdd(p.err_count, 1ull);
+                        if (slot < p.err_cap)
+                        {
+                            p.err_log[2 * slot] = p.frame0 + s_frame[lane];
+                            p.err_log[2 * slot + 1] = (unsigned long long)e | ((unsigned long long)(uint32_t)ret << 32);
+                        }
+                    }
                 }
                 if (mine)
                 {

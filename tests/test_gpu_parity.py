@@ -365,3 +365,27 @@ def test_bec_bit_sliced_sweep_equals_bytewise_and_oracle(gpu_ctx, oracle_code, e
         o = oracle_code.sim_point("BEC", eps, bec_deg1_compat=bool(compat), threads=8, **kw)
         assert {k: a[k] for k in ("fec", "bec", "frames", "iters")} == {k: b[k] for k in ("fec", "bec", "frames", "iters")} == o, (eps, n)
     gpu_ctx.set_tuning(bec_deg1_compat=1)
+
+
+def test_error_log_names_the_failing_frames(gpu_ctx, oracle_code):
+    """Per-error diagnostics log: the logged (global frame, bit errors, iterations) are exactly the frames the oracle finds
+    in error on the LLRs the GPU channel dumps, and a logged frame can be replayed from its index alone."""
+    n, x, f0 = 800, -4.6, 5000
+    kw = dict(seed=13, point=2, frame0=f0, nframes=n, decoding="BP_MS", iterations=40, early_term=True)
+    cnt, log, n_err = gpu_ctx.sim_point_log("AWGN", x, capacity=n, **kw)
+    plain = gpu_ctx.sim_point("AWGN", x, **kw)
+    assert cnt == {k: plain[k] for k in ("fec", "bec", "frames", "iters")} and n_err == cnt["fec"] == len(log) > 10
+    cw, llr = gpu_ctx.channel("AWGN", x, seed=13, point=2, frame0=f0, n=n)
+    out, co, its = oracle_code.decode(llr, 40, True, True)
+    errs = (co[:, oracle_code.bit_pos] != cw[:, oracle_code.bit_pos]).sum(1)
+    want = sorted((f0 + int(i), int(errs[i]), int(its[i])) for i in np.nonzero(errs)[0])
+    assert log == want
+    rep = gpu_ctx.error_report("AWGN", x, 13, 2, log[0][0], decoding="BP_MS", iterations=40, early_term=True)
+    assert rep["hamming_distance"] == log[0][1] and rep["iterations"] == log[0][2]
+    i = log[0][0] - f0
+    assert rep["failed_bits"] == [int(b) for b in oracle_code.bit_pos[co[i][oracle_code.bit_pos] != cw[i][oracle_code.bit_pos]]]
+    assert rep["syndrome_weight"] == int(oracle_code.syndrome(co[i]).sum()) == len(rep["failed_checks"])
+    cnt2, log2, n2 = gpu_ctx.sim_point_log("AWGN", x, capacity=5, **kw)        # a short buffer truncates, the count does not
+    assert n2 == n_err and len(log2) == 5 and set(log2) <= set(log)
+    with pytest.raises(RuntimeError, match="AWGN and BSC"):
+        gpu_ctx.sim_point_log("BEC", 0.5, nframes=10)
