@@ -857,7 +857,9 @@ namespace b200
         const P cn_seg_w = cn_seg + 16 * p.cn_max_segs * warp, vn_seg_w = vn_seg + 16 * p.vn_max_segs * warp;
 
 #ifdef B200_PHASE_TIMING
-        long long pt_cn = 0, pt_wb = 0, pt_vn = 0, pt_wa = 0, pt_n = 0, pt_hdr = 0, pt_nseg = 0, pt_ntask = 0;
+        long long pt_cn = 0, pt_wb = 0, pt_vn = 0, pt_wa = 0, pt_n = 0, pt_hdr = 0, pt_nseg = 0, pt_ntask = 0, pt_rel = 0;
+        __shared__ long long s_pt[2][32]; // work-end time stamps of the warps (a barrier releases at their maximum)
+        long long pt_vcyc[3] = {0, 0, 0}, pt_vtask[3] = {0, 0, 0};
 #endif
         for (uint32_t L = 0;; ++L)
         {
@@ -878,9 +880,6 @@ namespace b200
             }
 
             // ---- check-node phase (+ syndrome of the previous iteration's decisions) ----------
-#ifdef B200_PHASE_TIMING
-            const long long pt0 = clock64();
-#endif
             uint32_t bad = 0;
             auto cn_phase = [&](auto csrc)
             {
@@ -964,10 +963,12 @@ namespace b200
             }
 #ifdef B200_PHASE_TIMING
             const long long pt1 = clock64();
+            if (lane == 0) s_pt[0][warp] = pt1;
 #endif
             __syncthreads(); // B
 #ifdef B200_PHASE_TIMING
-            const long long pt2 = clock64();
+            long long pt2 = 0; // release time of barrier B = arrival of the last warp
+            for (int w = 0; w < warps; ++w) pt2 = max(pt2, s_pt[0][w]);
 #endif
 
             // ---- decision: converged (decoder.cpp:66-72) or out of iterations ---------------------
@@ -1003,6 +1004,11 @@ namespace b200
                     sg_next = WAcc<SMEM, 0>::ld4(sp);
                     const int deg = (int)(sg.x & 0xFFu);
                     int nt = (int)(sg.x >> 16);
+#ifdef B200_PHASE_TIMING
+                    const long long vs0 = clock64();
+                    const int vcls = deg == 1 ? 0 : deg == 2 ? 1 : 2;
+                    pt_vtask[vcls] += nt;
+#endif
                     P lp = llr_lane + sg.y, op = out_lane + sg.y;
                     const P ib = vn_idx + sg.z;
                     auto channel_llr = [&]() -> V // decoder.cpp:50
@@ -1069,6 +1075,9 @@ namespace b200
                     }
                     }
 #undef B200_VN_CASE
+#ifdef B200_PHASE_TIMING
+                    pt_vcyc[vcls] += clock64() - vs0;
+#endif
                 }
                 if constexpr (TM && LSRC == 0) tm_wait_st();
             };
@@ -1081,17 +1090,24 @@ namespace b200
             skip = 0;
 #ifdef B200_PHASE_TIMING
             const long long pt3 = clock64();
+            if (lane == 0) s_pt[1][warp] = pt3;
 #endif
             __syncthreads(); // A: variable-phase writes visible to the next check phase
 #ifdef B200_PHASE_TIMING
-            const long long pt4 = clock64();
-            pt_cn += pt1 - pt0; pt_wb += pt2 - pt1; pt_vn += pt3 - pt2; pt_wa += pt4 - pt3; ++pt_n;
+            long long pt4 = 0; // release time of barrier A
+            for (int w = 0; w < warps; ++w) pt4 = max(pt4, s_pt[1][w]);
+            if (pt_rel) { pt_cn += pt1 - pt_rel; pt_wb += pt2 - pt1; pt_vn += pt3 - pt2; pt_wa += pt4 - pt3; ++pt_n; }
+            pt_rel = pt4;
 #endif
         }
 #ifdef B200_PHASE_TIMING
         if (blockIdx.x == 0 && lane == 0)
-            printf("warp %2d: iterations %lld  check %lld  wait-B %lld  decision+variable %lld  wait-A %lld  (cycles per iteration); check segments/it %lld tasks/it %lld header cycles/seg %lld\n", warp, pt_n,
+            printf("warp %2d: iterations %lld  check work %lld  wait-B %lld  decision+variable work %lld  wait-A %lld  (cycles per iteration, from barrier release); check segments/it %lld tasks/it %lld header cycles/seg %lld\n", warp, pt_n,
                    pt_cn / pt_n, pt_wb / pt_n, pt_vn / pt_n, pt_wa / pt_n, pt_nseg / pt_n, pt_ntask / pt_n, pt_hdr / (pt_nseg ? pt_nseg : 1));
+        if (blockIdx.x == 0 && lane == 0)
+            printf("warp %2d: variable segments: deg1 %lld tasks/it %lld cycles/task | deg2 %lld tasks/it %lld cycles/task | other %lld tasks/it %lld cycles/task\n", warp,
+                   pt_vtask[0] / (pt_n + 1), pt_vcyc[0] / (pt_vtask[0] ? pt_vtask[0] : 1), pt_vtask[1] / (pt_n + 1), pt_vcyc[1] / (pt_vtask[1] ? pt_vtask[1] : 1),
+                   pt_vtask[2] / (pt_n + 1), pt_vcyc[2] / (pt_vtask[2] ? pt_vtask[2] : 1));
 #endif
 
         __syncthreads();
