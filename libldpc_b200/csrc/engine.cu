@@ -85,13 +85,13 @@ namespace b200
             return b + 16;
         }
 
-        int family_occupancy(int precision, int alg, bool smem, bool tm, bool et, int lanes, int threads, size_t smem_bytes)
+        int family_occupancy(int precision, int alg, bool smem, bool tm, bool et, bool wide, int lanes, int threads, size_t smem_bytes)
         {
             if (precision == LDPC_B200_F32)
-                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, tm, et, lanes, threads, smem_bytes)
-                                     : tile_family_occupancy<float, ALG_BP>(smem, tm, et, lanes, threads, smem_bytes);
-            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, tm, et, lanes, threads, smem_bytes)
-                                 : tile_family_occupancy<double, ALG_BP>(smem, tm, et, lanes, threads, smem_bytes);
+                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, tm, et, wide, lanes, threads, smem_bytes)
+                                     : tile_family_occupancy<float, ALG_BP>(smem, tm, et, wide, lanes, threads, smem_bytes);
+            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, tm, et, wide, lanes, threads, smem_bytes)
+                                 : tile_family_occupancy<double, ALG_BP>(smem, tm, et, wide, lanes, threads, smem_bytes);
         }
     } // namespace
 
@@ -229,7 +229,7 @@ namespace b200
         if (!want_lanes && tuning.threads_per_cta <= 0)
         { // global residency, nothing pinned by the caller: the autotuned (lanes, threads) of this (precision, algorithm)
             auto it = tuned_.find(std::make_pair(precision, alg));
-            if (it != tuned_.end()) { g_lanes = it->second.first; g_threads = it->second.second; }
+            if (it != tuned_.end()) { g_lanes = std::get<0>(it->second); g_threads = std::get<1>(it->second); }
         }
         *smem_bytes = u_bytes(g_lanes);
         return get_seg_layout(g_lanes, g_threads);
@@ -249,6 +249,16 @@ namespace b200
         // share a TMEM lane partition (warp % 4) lie side by side in the 512 columns.
         c.tm = false;
         c.tm_alloc_cols = c.tm_cols_per_warp = c.tm_vn_off = 0;
+        c.wide = false;
+        if (c.residency == LDPC_B200_GLOBAL)
+        {
+            if (force_wide_ >= 0) c.wide = force_wide_ != 0;
+            else
+            {
+                auto it = tuned_.find(std::make_pair(precision, alg));
+                if (it != tuned_.end() && tuning.frames_per_cta <= 0 && tuning.threads_per_cta <= 0) c.wide = std::get<2>(it->second) != 0;
+            }
+        }
         if (c.residency == LDPC_B200_SMEM && tuning.tmem == 0)
         {
             uint32_t cn_max = 0, vn_max = 0;
@@ -282,10 +292,10 @@ namespace b200
         int ctas = tuning.ctas;
         if (ctas <= 0)
         { // persistent grid: every SM gets as many CTAs as the runtime keeps resident
-            auto key = std::make_tuple(precision, alg, c.residency * 2 + (c.tm ? 1 : 0), c.lanes, c.threads, c.smem_bytes);
+            auto key = std::make_tuple(precision, alg, c.residency * 4 + (c.tm ? 1 : 0) + (c.wide ? 2 : 0), c.lanes, c.threads, c.smem_bytes);
             auto it = occupancy_.find(key);
             if (it == occupancy_.end())
-                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.tm, true, c.lanes, c.threads, c.smem_bytes)).first;
+                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.tm, true, c.wide, c.lanes, c.threads, c.smem_bytes)).first;
             if (it->second < 1) throw std::runtime_error("tile kernel does not fit on this device with the current tuning");
             int per_sm = it->second;
             // every resident CTA of a TM kernel holds tm_alloc_cols of the SM's 512 TMEM columns: do not launch more
@@ -510,13 +520,13 @@ namespace b200
         const bool smem = c.residency == LDPC_B200_SMEM;
         if (c.precision == LDPC_B200_F32)
         {
-            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<float, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<float, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         else
         {
-            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<double, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<double, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         stats.launches += 1;
         stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;
@@ -536,7 +546,7 @@ namespace b200
         in_autotune_ = true;
         unsigned long long *d_cnt = nullptr;
         double best = -1;
-        std::pair<int, int> best_cfg(1, std::min(512, B200_TILE_MAX_THREADS));
+        std::tuple<int, int, int> best_cfg(1, std::min(512, B200_TILE_MAX_THREADS), 0);
         try
         {
             CUDA_OK(cudaMalloc(&d_cnt, 8 * sizeof(unsigned long long)));
@@ -545,9 +555,11 @@ namespace b200
             decoder_param tdp = dp;
             tdp.earlyTerm = false;
             tdp.iterations = std::min<uint32_t>(dp.iterations, 20); // enough iterations that decoding, not frame generation, dominates
-            const int cand[6][2] = {{1, 512}, {2, 512}, {4, 512}, {1, 256}, {2, 256}, {4, 256}};
+            const int cand[9][3] = {{1, 512, 0}, {2, 512, 0}, {4, 512, 0}, {1, 512, 1}, {2, 512, 1}, {4, 512, 1}, {1, 256, 0}, {2, 256, 0}, {4, 256, 0}};
             for (const auto &cd : cand)
             {
+                if (cd[2] && alg != ALG_MS) continue; // the wide build only differs for min-sum
+                force_wide_ = cd[2];
                 tuning.residency = LDPC_B200_GLOBAL;
                 tuning.frames_per_cta = cd[0] * vec;
                 tuning.threads_per_cta = cd[1];
@@ -569,7 +581,7 @@ namespace b200
                     float ms = 0;
                     CUDA_OK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
                     const double rate = (double)frames / ms;
-                    if (rate > best) { best = rate; best_cfg = std::make_pair(cd[0], cd[1]); }
+                    if (rate > best) { best = rate; best_cfg = std::make_tuple(cd[0], cd[1], cd[2]); }
                 }
                 catch (const std::exception &)
                 { // a shape that does not fit is simply not a candidate
@@ -580,13 +592,14 @@ namespace b200
         catch (...)
         {
             cudaFree(d_cnt);
-            tuning = saved; stats = saved_stats; in_autotune_ = false;
+            tuning = saved; stats = saved_stats; in_autotune_ = false; force_wide_ = -1;
             throw;
         }
         cudaFree(d_cnt);
         tuning = saved;
         stats = saved_stats;
         in_autotune_ = false;
+        force_wide_ = -1;
         tuned_[key] = best_cfg;
     }
 

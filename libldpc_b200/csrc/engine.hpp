@@ -81,6 +81,7 @@ namespace b200
             int precision, alg, residency, lanes, fpc, threads, ctas;
             size_t smem_bytes;
             bool tm;                                  // TMEM mirror in use
+            bool wide;                                // global residency: the 1-CTA-per-SM / 128-register kernel build
             uint32_t tm_alloc_cols, tm_cols_per_warp, tm_vn_off;
         };
         Config choose(int precision, int alg, uint64_t n_frames);
@@ -103,8 +104,9 @@ namespace b200
         std::map<std::pair<int, int>, std::unique_ptr<SegLayout>> seg_layouts_;
         std::map<std::pair<int, int>, std::unique_ptr<DeviceSegLayout>> dev_seg_layouts_;
         std::map<std::tuple<int, int, int, int, int, size_t>, int> occupancy_;
-        std::map<std::pair<int, int>, std::pair<int, int>> tuned_; // (precision, alg) -> autotuned (lanes, threads), global residency
+        std::map<std::pair<int, int>, std::tuple<int, int, int>> tuned_; // (precision, alg) -> autotuned (lanes, threads, wide), global residency
         bool in_autotune_ = false;
+        int force_wide_ = -1; // autotune trials: -1 = use tuned_/default, 0/1 = force
         int32_t *d_bit_pos_ = nullptr, *d_punct_ = nullptr, *d_short_ = nullptr;
         int32_t *d_g_col_ptr_ = nullptr, *d_g_row_ = nullptr; // generator matrix by column (device)
         int32_t *d_bs_row_ptr_ = nullptr, *d_bs_row_edge_ = nullptr, *d_bs_col_ptr_ = nullptr, *d_bs_col_edge_ = nullptr; // bit-sliced BEC kernel

@@ -587,8 +587,10 @@ namespace b200
 #endif
     // TM: keep the write-through TMEM mirror (K4Params::tm_*; shared-memory residency only).
     // ET: compiled with early termination support (syndrome in the check phase); ET = false serves --no-early-term runs.
-    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM, bool ET>
-    __global__ void __launch_bounds__(B200_TILE_MAX_THREADS, (SMEM || ALG == ALG_BP) ? 1 : (1024 / B200_TILE_MAX_THREADS)) tile4_kernel(const K4Params p)
+    // MINB: resident CTAs per SM the kernel is compiled for (register budget 65536 / (MINB * B200_TILE_MAX_THREADS)): 1 everywhere
+    // except the narrow global-residency min-sum variant (2: more warps, 64 registers), which quasi-cyclic codes prefer.
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
+    __global__ void __launch_bounds__(B200_TILE_MAX_THREADS, MINB) tile4_kernel(const K4Params p)
     {
         static_assert(SMEM || !TM, "the TMEM mirror belongs to shared-memory residency");
         typedef typename PtrOf<SMEM>::type P;

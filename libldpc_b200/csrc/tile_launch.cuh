@@ -9,88 +9,94 @@
 
 namespace b200
 {
-    // Four variants per (T, ALG, lanes): shared-memory residency with the TMEM mirror (with / without the
+    // Variants per (T, ALG, lanes): shared-memory residency with the TMEM mirror (with / without the
     // early-termination syndrome: --no-early-term min-sum runs skip it), shared-memory residency without the mirror,
-    // global residency.  Index entries are 32-bit byte offsets.
+    // global residency (min-sum: a narrow 2-CTA/64-register and a wide 1-CTA/128-register build).  Index entries are
+    // 32-bit byte offsets.
     // lanes = warp lanes per node (frames per CTA = lanes * 16/sizeof(T)).
 
     constexpr int TILE_SMEM_OPTIN = 232448 - 1024; // 227 KB minus the kernel's static shared memory
 
-    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET>
+    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
     void prepare_tile_one()
     {
         static bool attr_set = false;
         if (!attr_set)
         {
-            cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
+            cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
             if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
             attr_set = true;
         }
     }
 
-    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET>
+    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
     void launch_tile_one(const K4Params &kp, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
     {
-        prepare_tile_one<T, ALG, SMEM, LANES, TM, ET>();
-        tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET><<<ctas, threads, smem_bytes, s>>>(kp);
+        prepare_tile_one<T, ALG, SMEM, LANES, TM, ET, MINB>();
+        tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET, MINB><<<ctas, threads, smem_bytes, s>>>(kp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " (tile kernel launch)");
     }
 
-    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET>
+    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
     int occupancy_tile_one(int threads, size_t smem_bytes)
     {
-        prepare_tile_one<T, ALG, SMEM, LANES, TM, ET>();
+        prepare_tile_one<T, ALG, SMEM, LANES, TM, ET, MINB>();
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET>, threads, smem_bytes);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET, MINB>, threads, smem_bytes);
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
         return n;
     }
 
     // One translation unit per (T, ALG, lanes) — tile_<alg>_<prec>_l<lanes>.cu — so that the build compiles the kernel
     // variants in parallel; engine.cu holds the dispatch over `lanes`.
+    // wide (global residency, min-sum): the 1-CTA-per-SM / 128-register build instead of the 2-CTA / 64-register one
     template <typename T, int ALG, int L>
-    void launch_tile_lanes(const K4Params &kp, bool smem, bool tm, bool et, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
+    void launch_tile_lanes(const K4Params &kp, bool smem, bool tm, bool et, bool wide, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
     template <typename T, int ALG, int L>
-    int occupancy_tile_lanes(bool smem, bool tm, bool et, int threads, size_t smem_bytes);
+    int occupancy_tile_lanes(bool smem, bool tm, bool et, bool wide, int threads, size_t smem_bytes);
 
 #define B200_DEFINE_TILE_LANES(T, ALG, L)                                                                              \
     template <>                                                                                                        \
-    void launch_tile_lanes<T, ALG, L>(const K4Params &kp, bool smem, bool tm, bool et, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
+    void launch_tile_lanes<T, ALG, L>(const K4Params &kp, bool smem, bool tm, bool et, bool wide, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
     {                                                                                                                  \
-        if (smem && tm && (et || ALG != ALG_MS)) launch_tile_one<T, ALG, true, L, true, true>(kp, ctas, threads, smem_bytes, s); \
-        else if (smem && tm) launch_tile_one<T, ALG, true, L, true, ALG != ALG_MS>(kp, ctas, threads, smem_bytes, s);  \
-        else if (smem) launch_tile_one<T, ALG, true, L, false, true>(kp, ctas, threads, smem_bytes, s);                \
-        else launch_tile_one<T, ALG, false, L, false, true>(kp, ctas, threads, smem_bytes, s);                         \
+        constexpr int NB = (ALG == ALG_MS) ? (1024 / B200_TILE_MAX_THREADS) : 1;                                       \
+        if (smem && tm && (et || ALG != ALG_MS)) launch_tile_one<T, ALG, true, L, true, true, 1>(kp, ctas, threads, smem_bytes, s); \
+        else if (smem && tm) launch_tile_one<T, ALG, true, L, true, ALG != ALG_MS, 1>(kp, ctas, threads, smem_bytes, s); \
+        else if (smem) launch_tile_one<T, ALG, true, L, false, true, 1>(kp, ctas, threads, smem_bytes, s);             \
+        else if (wide) launch_tile_one<T, ALG, false, L, false, true, 1>(kp, ctas, threads, smem_bytes, s);            \
+        else launch_tile_one<T, ALG, false, L, false, true, NB>(kp, ctas, threads, smem_bytes, s);                     \
     }                                                                                                                  \
     template <>                                                                                                        \
-    int occupancy_tile_lanes<T, ALG, L>(bool smem, bool tm, bool et, int threads, size_t smem_bytes)                   \
+    int occupancy_tile_lanes<T, ALG, L>(bool smem, bool tm, bool et, bool wide, int threads, size_t smem_bytes)        \
     {                                                                                                                  \
-        return (smem && tm && (et || ALG != ALG_MS)) ? occupancy_tile_one<T, ALG, true, L, true, true>(threads, smem_bytes) \
-               : (smem && tm)     ? occupancy_tile_one<T, ALG, true, L, true, ALG != ALG_MS>(threads, smem_bytes)      \
-               : smem             ? occupancy_tile_one<T, ALG, true, L, false, true>(threads, smem_bytes)              \
-                                  : occupancy_tile_one<T, ALG, false, L, false, true>(threads, smem_bytes);            \
+        constexpr int NB = (ALG == ALG_MS) ? (1024 / B200_TILE_MAX_THREADS) : 1;                                       \
+        return (smem && tm && (et || ALG != ALG_MS)) ? occupancy_tile_one<T, ALG, true, L, true, true, 1>(threads, smem_bytes) \
+               : (smem && tm)     ? occupancy_tile_one<T, ALG, true, L, true, ALG != ALG_MS, 1>(threads, smem_bytes)   \
+               : smem             ? occupancy_tile_one<T, ALG, true, L, false, true, 1>(threads, smem_bytes)           \
+               : wide             ? occupancy_tile_one<T, ALG, false, L, false, true, 1>(threads, smem_bytes)          \
+                                  : occupancy_tile_one<T, ALG, false, L, false, true, NB>(threads, smem_bytes);        \
     }
 
     template <typename T, int ALG>
-    void launch_tile_family(const K4Params &kp, bool smem, bool tm, bool et, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
+    void launch_tile_family(const K4Params &kp, bool smem, bool tm, bool et, bool wide, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
     {
         switch (lanes)
         {
-        case 1: launch_tile_lanes<T, ALG, 1>(kp, smem, tm, et, ctas, threads, smem_bytes, s); return;
-        case 2: launch_tile_lanes<T, ALG, 2>(kp, smem, tm, et, ctas, threads, smem_bytes, s); return;
-        case 4: launch_tile_lanes<T, ALG, 4>(kp, smem, tm, et, ctas, threads, smem_bytes, s); return;
+        case 1: launch_tile_lanes<T, ALG, 1>(kp, smem, tm, et, wide, ctas, threads, smem_bytes, s); return;
+        case 2: launch_tile_lanes<T, ALG, 2>(kp, smem, tm, et, wide, ctas, threads, smem_bytes, s); return;
+        case 4: launch_tile_lanes<T, ALG, 4>(kp, smem, tm, et, wide, ctas, threads, smem_bytes, s); return;
         default: throw std::runtime_error("lanes per node must be 1, 2 or 4");
         }
     }
     template <typename T, int ALG>
-    int tile_family_occupancy(bool smem, bool tm, bool et, int lanes, int threads, size_t smem_bytes)
+    int tile_family_occupancy(bool smem, bool tm, bool et, bool wide, int lanes, int threads, size_t smem_bytes)
     {
         switch (lanes)
         {
-        case 1: return occupancy_tile_lanes<T, ALG, 1>(smem, tm, et, threads, smem_bytes);
-        case 2: return occupancy_tile_lanes<T, ALG, 2>(smem, tm, et, threads, smem_bytes);
-        case 4: return occupancy_tile_lanes<T, ALG, 4>(smem, tm, et, threads, smem_bytes);
+        case 1: return occupancy_tile_lanes<T, ALG, 1>(smem, tm, et, wide, threads, smem_bytes);
+        case 2: return occupancy_tile_lanes<T, ALG, 2>(smem, tm, et, wide, threads, smem_bytes);
+        case 4: return occupancy_tile_lanes<T, ALG, 4>(smem, tm, et, wide, threads, smem_bytes);
         default: throw std::runtime_error("lanes per node must be 1, 2 or 4");
         }
     }
