@@ -666,6 +666,9 @@ namespace b200
         // per-frame iteration counter: lane g of warp 0 owns frame lane g
         int it = 0;
         uint32_t active = 0, skip = 0; // CTA-uniform copies of s_active / s_skip
+#ifdef B200_PHASE_TIMING
+        long long pt_refill = 0, pt_nrefill = 0;
+#endif
         // A refill rewrites c2v / llr in shared memory behind the TMEM mirror's back: the next check phase and the
         // next variable phase read shared memory (and refresh the mirror).  CTA-uniform.
         bool cn_stale = true, vn_stale = true;
@@ -766,6 +769,9 @@ namespace b200
         //   as_skip        : the new frames must sit out the variable phase that follows
         auto retire_and_refill = [&](uint32_t mask, uint32_t synd, uint32_t started, bool as_skip, bool first_fill)
         {
+#ifdef B200_PHASE_TIMING
+            const long long rf0 = clock64();
+#endif
             if (!first_fill)
             { // bit errors of the final decisions over the transmitted positions vs the transmitted codeword (ldpcsim.cpp:184-190)
                 for (int g = 0; g < FPC; ++g)
@@ -850,6 +856,10 @@ namespace b200
             fresh |= mask & new_active;
             cn_stale = true;
             vn_stale = true;
+#ifdef B200_PHASE_TIMING
+            pt_refill += clock64() - rf0;
+            pt_nrefill += 1;
+#endif
         };
 
         retire_and_refill(ALL, 0, 0, false, true);
@@ -1106,6 +1116,8 @@ namespace b200
         if (blockIdx.x == 0 && lane == 0)
             printf("warp %2d: iterations %lld  check work %lld  wait-B %lld  decision+variable work %lld  wait-A %lld  (cycles per iteration, from barrier release); check segments/it %lld tasks/it %lld header cycles/seg %lld\n", warp, pt_n,
                    pt_cn / pt_n, pt_wb / pt_n, pt_vn / pt_n, pt_wa / pt_n, pt_nseg / pt_n, pt_ntask / pt_n, pt_hdr / (pt_nseg ? pt_nseg : 1));
+        if (blockIdx.x == 0 && tid == 0)
+            printf("refills: %lld events, %lld cycles each; iterations %lld\n", pt_nrefill, pt_refill / (pt_nrefill ? pt_nrefill : 1), pt_n);
         if (blockIdx.x == 0 && lane == 0)
             printf("warp %2d: variable segments: deg1 %lld tasks/it %lld cycles/task | deg2 %lld tasks/it %lld cycles/task | other %lld tasks/it %lld cycles/task\n", warp,
                    pt_vtask[0] / (pt_n + 1), pt_vcyc[0] / (pt_vtask[0] ? pt_vtask[0] : 1), pt_vtask[1] / (pt_n + 1), pt_vcyc[1] / (pt_vtask[1] ? pt_vtask[1] : 1),
