@@ -4,14 +4,20 @@
 //   --channel AWGN|BSC|BEC (AWGN)  --decoding BP|BP_MS (BP)  --max-frames N (10e9)
 //   --frame-error-count N (50)  --no-early-term  -h/--help  -v/--version
 // Negative MIN/MAX are positionals, as with the reference's argument parser.
-// B200 extras (do not exist in the reference): --precision f64|f32, --device N.
+// B200 extras (do not exist in the reference): --precision f64|f32, --device N, --gpus N (frames of every round sharded
+// over N GPUs of this process, one host thread per GPU; the counters are summed on the host, results do not depend on N).
 #include <cstdio>
 #include <cstdlib>
+#include <array>
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <cuda_runtime.h>
 
 #include "engine.hpp"
 
@@ -36,7 +42,8 @@ namespace
         "--frame-error-count \tMaximum frame errors for given simulation point.\n"
         "--no-early-term     \tDisable early termination for decoding.\n"
         "--precision         \tB200 only: message arithmetic \"f64\" (bit-exact with the reference, default) or \"f32\"\n"
-        "--device            \tB200 only: CUDA device index (Default: 0)\n";
+        "--device            \tB200 only: CUDA device index (Default: 0)\n"
+        "--gpus              \tB200 only: number of GPUs to shard every round of frames over, starting at --device (Default: 1, 0 = all)\n";
 
     bool looks_numeric(const std::string &s)
     {
@@ -44,6 +51,40 @@ namespace
         char *end = nullptr;
         std::strtod(s.c_str(), &end);
         return end && *end == 0;
+    }
+
+    // Multi-GPU rounds: the sweep driver hands one round [frame0, frame0 + n) of a sweep point to this callback, which
+    // splits it contiguously over the engines (one per GPU, one host thread each) and sums the counters.  The frame ->
+    // Philox substream mapping depends only on the global frame index, so the totals do not depend on the split.
+    struct MultiGpu
+    {
+        std::vector<std::unique_ptr<b200::Engine>> engines;
+        decoder_param dp;
+        std::string channel;
+        uint64_t seed = 0;
+    };
+    int multi_gpu_round(uint32_t point, double x, uint64_t frame0, uint64_t n, uint64_t *counters, void *user)
+    {
+        MultiGpu &m = *static_cast<MultiGpu *>(user);
+        const size_t g = m.engines.size();
+        std::vector<std::array<uint64_t, 5>> part(g);
+        std::vector<std::string> err(g);
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < g; ++i)
+            th.emplace_back([&, i] {
+                const uint64_t lo = frame0 + n * i / g, hi = frame0 + n * (i + 1) / g;
+                part[i] = {0, 0, 0, 0, 0};
+                if (hi == lo) return;
+                try { m.engines[i]->sim_point(m.dp, m.channel, x, m.seed, point, lo, hi - lo, part[i].data(), nullptr); }
+                catch (const std::exception &e) { err[i] = e.what(); }
+            });
+        for (auto &t : th) t.join();
+        for (size_t i = 0; i < g; ++i)
+        {
+            if (!err[i].empty()) { std::cout << "Error: GPU " << i << ": " << err[i] << std::endl; return 1; }
+            for (int k = 0; k < 5; ++k) counters[k] += part[i][k];
+        }
+        return 0;
     }
 
     template <typename V>
@@ -61,7 +102,7 @@ int main(int argc, char **argv)
     unsigned iterations = 50, threads = 1;
     unsigned long seed = 0, max_frames = (unsigned long)10e9, fec = 50;
     bool early_term = true;
-    int device = 0;
+    int device = 0, gpus = 1;
     std::vector<std::string> pos;
     try
     {
@@ -86,6 +127,7 @@ int main(int argc, char **argv)
             else if (a == "--no-early-term") early_term = false;
             else if (a == "--precision") precision = value();
             else if (a == "--device") device = std::stoi(value());
+            else if (a == "--gpus") gpus = std::stoi(value());
             else if (a.size() > 1 && a[0] == '-' && !looks_numeric(a)) throw std::runtime_error("Unknown argument: " + a);
             else pos.push_back(a);
         }
@@ -131,14 +173,28 @@ int main(int argc, char **argv)
         std::cout << "== Simulation Parameters\n Threads: " << sp.threads << "\n FEC: " << sp.fec << "\n Max Frames: " << sp.maxFrames
                   << "\n Output File: " << sp.resultFile << "\n" << std::endl;
         std::cout << bar << std::endl;
-        if (eng->has_gen)
-            std::cout << "note: generator matrix loaded for encode(); the simulation transmits the all-zero codeword "
-                         "(the decoders are symmetric, results do not depend on the codeword)" << std::endl;
+        if (eng->has_gen && channel == "BEC")
+            std::cout << "note: the erasure-channel sweep transmits the all-zero codeword (the generator matrix serves AWGN / BSC sweeps)" << std::endl;
 
         bool stop = false;
         try
         {
-            b200::run_sweep(*eng, dp, cp, sp, nullptr, &stop, 0, 1, nullptr, nullptr, false, true);
+            if (gpus == 0 && cudaGetDeviceCount(&gpus) != cudaSuccess) gpus = 1;
+            if (gpus < 1) throw std::runtime_error("--gpus must be >= 0");
+            if (gpus == 1) b200::run_sweep(*eng, dp, cp, sp, nullptr, &stop, 0, 1, nullptr, nullptr, false, true);
+            else
+            {
+                MultiGpu m;
+                m.dp = dp; m.channel = channel; m.seed = seed;
+                m.engines.push_back(std::move(eng));
+                for (int g = 1; g < gpus; ++g)
+                {
+                    m.engines.push_back(std::make_unique<b200::Engine>(pos[0], gen, device + g));
+                    m.engines.back()->tuning.precision = m.engines[0]->tuning.precision;
+                }
+                std::cout << "GPUs: " << gpus << " (devices " << device << " .. " << device + gpus - 1 << ")" << std::endl;
+                b200::run_sweep(*m.engines[0], dp, cp, sp, nullptr, &stop, 0, 1, nullptr, &m, false, true, multi_gpu_round);
+            }
         }
         catch (const std::exception &e)
         {

@@ -1,6 +1,7 @@
 // Launch front end of the tile kernel family.  Each (T, ALG) pair is instantiated in its own
 // translation unit (tile_*.cu) so that the build can compile them in parallel.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdexcept>
 #include <string>
@@ -20,12 +21,15 @@ namespace b200
     template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
     void prepare_tile_one()
     {
-        static bool attr_set = false;
-        if (!attr_set)
+        // the opt-in is a per-device attribute of the function: remember it per device (several GPUs in one process)
+        static std::atomic<bool> attr_set[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire))
         {
             cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
             if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
-            attr_set = true;
+            if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
         }
     }
 

@@ -389,3 +389,21 @@ def test_error_log_names_the_failing_frames(gpu_ctx, oracle_code):
     assert n2 == n_err and len(log2) == 5 and set(log2) <= set(log)
     with pytest.raises(RuntimeError, match="AWGN and BSC"):
         gpu_ctx.sim_point_log("BEC", 0.5, nframes=10)
+
+
+def test_cli_multi_gpu_gives_identical_results(built_lib, tmp_path):
+    """ldpcsim --gpus N shards every round over N GPUs of one process: same counters, hence the same results file
+    (all columns but the frame time), as one GPU."""
+    import os, subprocess
+    from conftest import ROOT
+    if built_lib.ldpc_b200_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cli = os.path.join(ROOT, "libldpc_b200", "ldpcsim")
+    rows = []
+    for g in (1, 2):
+        out = tmp_path / f"res_g{g}.txt"
+        r = subprocess.run([cli, H_FILE, str(out), "-5.5", "-4.4", "0.5", "--decoding", "BP_MS", "--frame-error-count", "300",
+                            "--max-frames", "200000", "-s", "4", "--gpus", str(g)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        rows.append([l.split()[:5] for l in out.read_text().split("\n")[1:] if l.strip()])
+    assert rows[0] == rows[1] and len(rows[0]) == 3
