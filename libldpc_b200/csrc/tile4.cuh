@@ -1076,13 +1076,33 @@ namespace b200
                         B200_VN_CASE(8)
                     default:
                     {
-                        const int st = idx_stride_of(deg, ISZ);
-                        P ip = ib + j * 16;
-                        for (; nt > 0; --nt)
+                        auto generic = [&]()
                         {
-                            finish(vn4_any<T, IdxT, SMEM, LANES>(c2v_sub, ip, deg, channel_llr()));
-                            ip += NPW * st;
+                            const int st = idx_stride_of(deg, ISZ);
+                            P ip = ib + j * 16;
+                            for (; nt > 0; --nt)
+                            {
+                                finish(vn4_any<T, IdxT, SMEM, LANES>(c2v_sub, ip, deg, channel_llr()));
+                                ip += NPW * st;
+                            }
+                        };
+                        if constexpr (SMEM)
+                        { // the 128-register kernels also unroll degrees 9..16: every gather of the node is in flight before the
+                          // (strictly ordered) additions start
+                            switch (deg)
+                            {
+                                B200_VN_CASE(9)
+                                B200_VN_CASE(10)
+                                B200_VN_CASE(11)
+                                B200_VN_CASE(12)
+                                B200_VN_CASE(13)
+                                B200_VN_CASE(14)
+                                B200_VN_CASE(15)
+                                B200_VN_CASE(16)
+                            default: generic(); break;
+                            }
                         }
+                        else generic();
                         break;
                     }
                     }
