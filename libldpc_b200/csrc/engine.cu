@@ -778,7 +778,16 @@ namespace b200
         ensure_cuda();
         cudaStream_t sk = (cudaStream_t)stream_;
         const size_t nc = H.nc;
-        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, std::max<int64_t>((int64_t)((48ull << 20) / (nc * sizeof(double))), 1184)));
+        // chunk = whole waves of the persistent grid (CTAs x frames per CTA), about 32 MB of input: no partly filled last wave
+        // per launch, and a short pipeline fill
+        int64_t chunk = std::max<int64_t>((int64_t)((32ull << 20) / (nc * sizeof(double))), 1);
+        {
+            const bool minsum = dp.type && std::string(dp.type) == "BP_MS";
+            const Config c = choose(tuning.precision, minsum ? ALG_MS : ALG_BP, ~0ull >> 1);
+            const int64_t wave = (int64_t)c.ctas * c.fpc;
+            chunk = std::max<int64_t>(wave, chunk / wave * wave);
+        }
+        chunk = std::min<int64_t>(n, chunk);
         if (!copy_in_)
         {
             CUDA_OK(cudaStreamCreateWithFlags((cudaStream_t *)&copy_in_, cudaStreamNonBlocking));
