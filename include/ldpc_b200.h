@@ -86,6 +86,11 @@ void syndrome(uint8_t *word, uint8_t *syndrome);
 /* Part 2 — handle-based B200 API                                                             */
 /* ------------------------------------------------------------------------------------------ */
 
+/* A context owns one loaded code, its device tables on ONE CUDA device, a stream and workspaces.  It is not
+ * thread-safe: use one context per host thread (and per GPU); different contexts may be used concurrently, also on
+ * different devices of one process.  Every function returns 0 on success and non-zero on failure (message:
+ * ldpc_b200_last_error(), thread-local); compute entry points fail when no CUDA device is present — there is no CPU
+ * fallback. */
 typedef struct ldpc_b200_ctx ldpc_b200_ctx;
 
 enum { LDPC_B200_F64 = 0, LDPC_B200_F32 = 1 };          /* arithmetic / message type of the decoder */
