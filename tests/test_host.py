@@ -153,3 +153,16 @@ def test_large_code_files_and_layout(built_lib, which):
         assert lay["residency"] == api.GLOBAL
         assert len(np.unique(es)) == c.nnz and es.min() >= 0 and es.max() < lay["n_slots"]
     c.close()
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/ldpc_b200.h is the drop-in boundary: it must compile as C11 and as C++17 on its own (extern "C", plain
+    pointers and sizes, no CUDA / torch types)."""
+    inc = os.path.join(ROOT, "include")
+    (tmp_path / "t.c").write_text('#include "ldpc_b200.h"\nint main(void) { return (int)sizeof(sim_results_t) - 48; }\n')
+    (tmp_path / "t.cpp").write_text('#include "ldpc_b200.h"\nint main() { return (int)sizeof(decoder_param) - 16; }\n')
+    for cc, std, src in (("gcc", "-std=c11", "t.c"), ("g++", "-std=c++17", "t.cpp")):
+        r = subprocess.run([cc, std, "-Wall", "-Wextra", "-Werror", "-I", inc, str(tmp_path / src), "-o", str(tmp_path / (src + ".out"))],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert subprocess.run([str(tmp_path / (src + ".out"))]).returncode == 0
