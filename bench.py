@@ -335,7 +335,7 @@ def run_ours(args):
             "frames_per_s": total_frames / (ms * 1e-3),
             "edge_updates_per_s": total_frames * ITERS * NNZ / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "tile4_kernel<double,MS,SMEM,lanes=2,TMEM>", "kernel_ms": kernel_ms,
+                         "peak_source": peak_src, "kernel": "tile4_kernel<double,MS,SMEM,lanes=%d,TMEM>, %d CTAs/SM x %d threads" % (st["frames_per_cta"] // 2, max(1, st["ctas"] // 148), st["threads_per_cta"]), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "algorithmic message traffic (4 x 8 B per edge-iteration, SURVEY.md 8d) over the measured HBM copy peak, as the "
                                  "contract asks; the messages are SHARED-MEMORY resident (DRAM traffic per launch = `traffic`, ~0), so this "

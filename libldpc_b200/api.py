@@ -38,7 +38,7 @@ class code_info(ct.Structure):
 
 
 class tuning(ct.Structure):
-    _fields_ = [(k, ct.c_int) for k in ("precision", "residency", "frames_per_cta", "threads_per_cta", "ctas", "bec_deg1_compat", "tmem", "zero_codeword")]
+    _fields_ = [(k, ct.c_int) for k in ("precision", "residency", "frames_per_cta", "threads_per_cta", "ctas", "bec_deg1_compat", "tmem", "idx16", "zero_codeword")]
 
 
 class error_record(ct.Structure):  # ldpc_b200_error_record

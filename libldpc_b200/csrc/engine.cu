@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <tuple>
@@ -85,13 +86,13 @@ namespace b200
             return b + 16;
         }
 
-        int family_occupancy(int precision, int alg, bool smem, bool tm, bool et, bool wide, int lanes, int threads, size_t smem_bytes)
+        int family_occupancy(int precision, int alg, bool smem, bool tm, bool et, bool wide, bool idx16, int lanes, int threads, size_t smem_bytes)
         {
             if (precision == LDPC_B200_F32)
-                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, tm, et, wide, lanes, threads, smem_bytes)
-                                     : tile_family_occupancy<float, ALG_BP>(smem, tm, et, wide, lanes, threads, smem_bytes);
-            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, tm, et, wide, lanes, threads, smem_bytes)
-                                 : tile_family_occupancy<double, ALG_BP>(smem, tm, et, wide, lanes, threads, smem_bytes);
+                return alg == ALG_MS ? tile_family_occupancy<float, ALG_MS>(smem, tm, et, wide, idx16, lanes, threads, smem_bytes)
+                                     : tile_family_occupancy<float, ALG_BP>(smem, tm, et, wide, idx16, lanes, threads, smem_bytes);
+            return alg == ALG_MS ? tile_family_occupancy<double, ALG_MS>(smem, tm, et, wide, idx16, lanes, threads, smem_bytes)
+                                 : tile_family_occupancy<double, ALG_BP>(smem, tm, et, wide, idx16, lanes, threads, smem_bytes);
         }
     } // namespace
 
@@ -152,6 +153,7 @@ namespace b200
         if (prop.major < 10) throw std::runtime_error(std::string("libldpc_b200 is built for sm_100a only; found ") + prop.name);
         sm_count_ = prop.multiProcessorCount;
         smem_optin_ = prop.sharedMemPerBlockOptin;
+        smem_per_sm_ = prop.sharedMemPerMultiprocessor;
         cudaStream_t s;
         CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         stream_ = s;
@@ -175,14 +177,14 @@ namespace b200
         cuda_ready_ = true;
     }
 
-    const SegLayout &Engine::get_seg_layout(int lanes, int threads)
+    const SegLayout &Engine::get_seg_layout(int lanes, int threads, int isz)
     {
-        auto key = std::make_pair(lanes, threads);
+        auto key = std::make_tuple(lanes, threads, isz);
         auto it = seg_layouts_.find(key);
         if (it == seg_layouts_.end())
         {
             auto l = std::make_unique<SegLayout>();
-            l->build(H, lanes, threads, 4);
+            l->build(H, lanes, threads, isz);
             it = seg_layouts_.emplace(key, std::move(l)).first;
         }
         return *it->second;
@@ -210,13 +212,39 @@ namespace b200
         auto u_bytes = [&](int lanes) -> size_t { return has_gen ? (((size_t)4 * lanes * vec * ((G.mc + 31) / 32)) + 15) & ~(size_t)15 : 0; };
         if (tuning.residency != LDPC_B200_GLOBAL)
         {
+            // 16-bit entries (record offset / 16) need every record offset of the layout below 2^16
+            auto fits16 = [&](int lanes) { return (size_t)lanes * (size_t)(H.nnz + 32 * 64) < 65536 && (size_t)lanes * (size_t)(H.nc + 32 * 64) < 65536; };
             for (int lanes = 4; lanes >= 1; lanes >>= 1)
             {
                 if (want_lanes && lanes != want_lanes) continue;
-                const SegLayout &l = get_seg_layout(lanes, threads);
+                const bool i16 = tuning.idx16 == 2 && tuning.tmem == 0 && fits16(lanes);
+                const SegLayout &l = get_seg_layout(lanes, threads, i16 ? 2 : 4);
                 const size_t need = seg_smem_bytes(l) + u_bytes(lanes);
                 if (need <= limit)
                 {
+                    // Nothing pinned by the caller and the widest tile that fits is two lanes: the same frames as TWO
+                    // CTAs per SM of one lane and half the threads each hide each other's barriers and latencies
+                    // (h.txt f64: 4.36 -> 4.47 Gb/s fixed-iteration, 6.48 -> 7.19 Gb/s with early termination).  The
+                    // tables only fit twice with 16-bit entries.  Taken when the one-off trial (autotune_pair) found it
+                    // faster on this device; choose() falls back when the pair cannot be resident.
+                    bool want_pair = force_pair_ == 1;
+                    if (force_pair_ < 0)
+                    {
+                        auto it = pair_tuned_.find(std::make_pair(precision, alg));
+                        want_pair = it != pair_tuned_.end() && it->second == 1;
+                    }
+                    if (want_pair && lanes == 2 && !want_lanes && tuning.threads_per_cta <= 0 && tuning.idx16 == 0 && tuning.tmem == 0 &&
+                        tuning.ctas <= 0 && fits16(1))
+                    {
+                        const SegLayout &l1 = get_seg_layout(1, max_threads / 2, 2);
+                        const size_t need1 = seg_smem_bytes(l1) + u_bytes(1);
+                        if (2 * (need1 + 2048) <= smem_per_sm_)
+                        {
+                            *residency = LDPC_B200_SMEM;
+                            *smem_bytes = need1;
+                            return l1;
+                        }
+                    }
                     *residency = LDPC_B200_SMEM;
                     *smem_bytes = need;
                     return l;
@@ -289,18 +317,49 @@ namespace b200
                 c.tm_alloc_cols = cols; c.tm_cols_per_warp = per_warp; c.tm_vn_off = 4 * cn_max;
             }
         }
+        c.idx16 = l.isz == 2;
+        const bool pair = c.idx16 && tuning.idx16 == 0; // the automatic two-CTAs-per-SM shape of layout_for
+        // the 16-bit tables only exist for the TMEM-mirror kernels; the pair needs both CTAs' TMEM windows at once
+        if (c.idx16 && (!c.tm || (pair && c.tm_alloc_cols > 256)))
+        {
+            if (pair)
+            {
+                if (force_pair_ == 1) throw std::runtime_error("the two-CTAs-per-SM shape does not fit");
+                pair_tuned_[std::make_pair(precision, alg)] = 0;
+                return choose(precision, alg, n_frames);
+            }
+            const int saved = tuning.idx16; // asked for by the caller: redo the choice with 32-bit entries
+            tuning.idx16 = 1;
+            try
+            {
+                const Config c32 = choose(precision, alg, n_frames);
+                tuning.idx16 = saved;
+                return c32;
+            }
+            catch (...)
+            {
+                tuning.idx16 = saved;
+                throw;
+            }
+        }
         int ctas = tuning.ctas;
         if (ctas <= 0)
         { // persistent grid: every SM gets as many CTAs as the runtime keeps resident
-            auto key = std::make_tuple(precision, alg, c.residency * 4 + (c.tm ? 1 : 0) + (c.wide ? 2 : 0), c.lanes, c.threads, c.smem_bytes);
+            auto key = std::make_tuple(precision, alg, c.residency * 8 + (c.tm ? 1 : 0) + (c.wide ? 2 : 0) + (c.idx16 ? 4 : 0), c.lanes, c.threads, c.smem_bytes);
             auto it = occupancy_.find(key);
             if (it == occupancy_.end())
-                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.tm, true, c.wide, c.lanes, c.threads, c.smem_bytes)).first;
+                it = occupancy_.emplace(key, family_occupancy(precision, alg, c.residency == LDPC_B200_SMEM, c.tm, true, c.wide, c.idx16, c.lanes, c.threads, c.smem_bytes)).first;
             if (it->second < 1) throw std::runtime_error("tile kernel does not fit on this device with the current tuning");
             int per_sm = it->second;
             // every resident CTA of a TM kernel holds tm_alloc_cols of the SM's 512 TMEM columns: do not launch more
             // CTAs per SM than can hold their allocation at the same time (the others would wait inside tcgen05.alloc)
+            if (std::getenv("LDPC_B200_DEBUG"))
+                fprintf(stderr, "[choose] lanes %d threads %d smem %zu tm %d cols %u idx16 %d occupancy %d\n", c.lanes, c.threads, c.smem_bytes, (int)c.tm,
+                        c.tm_alloc_cols, (int)c.idx16, per_sm);
             if (c.tm) per_sm = std::max(1, std::min(per_sm, (int)(512u / c.tm_alloc_cols)));
+            // the occupancy calculator answers 1 for the pair although two CTAs are resident (measured: 296 CTAs run at
+            // 1.47 x the rate of 148); the shape is only ever chosen after it won the timed trial on this device
+            if (pair) per_sm = 2;
             ctas = sm_count_ * per_sm;
         }
         const uint64_t need = (n_frames + c.fpc - 1) / c.fpc;
@@ -309,12 +368,12 @@ namespace b200
         return c;
     }
 
-    DeviceSegLayout &Engine::device_seg_layout(int lanes, int threads)
+    DeviceSegLayout &Engine::device_seg_layout(int lanes, int threads, int isz)
     {
-        auto key = std::make_pair(lanes, threads);
+        auto key = std::make_tuple(lanes, threads, isz);
         auto it = dev_seg_layouts_.find(key);
         if (it != dev_seg_layouts_.end()) return *it->second;
-        const SegLayout &l = get_seg_layout(lanes, threads);
+        const SegLayout &l = get_seg_layout(lanes, threads, isz);
         auto d = std::make_unique<DeviceSegLayout>();
         d->host = &l;
         d->cn_seg = upload(l.cn_seg);
@@ -461,15 +520,17 @@ namespace b200
 
         const int alg = minsum ? ALG_MS : ALG_BP;
         if (!in_autotune_ && n_frames >= 20000 && tuning.frames_per_cta <= 0 && tuning.threads_per_cta <= 0 &&
-            !tuned_.count(std::make_pair(tuning.precision, alg)))
+            !(tuned_.count(std::make_pair(tuning.precision, alg)) || pair_tuned_.count(std::make_pair(tuning.precision, alg))))
         {
             int res = 0;
             size_t sb = 0;
             layout_for(tuning.precision, alg, &res, &sb);
             if (res == LDPC_B200_GLOBAL) autotune_global(alg, dp, s);
+            else if (tuning.idx16 == 0 && tuning.tmem == 0 && tuning.ctas <= 0 && !pair_tuned_.count(std::make_pair(tuning.precision, alg)))
+                autotune_pair(alg, dp, s);
         }
         const Config c = choose(tuning.precision, alg, n_frames);
-        DeviceSegLayout &dl = device_seg_layout(c.lanes, c.threads);
+        DeviceSegLayout &dl = device_seg_layout(c.lanes, c.threads, c.idx16 ? 2 : 4);
         const SegLayout &l = *dl.host;
 
         K4Params kp{};
@@ -520,13 +581,13 @@ namespace b200
         const bool smem = c.residency == LDPC_B200_SMEM;
         if (c.precision == LDPC_B200_F32)
         {
-            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<float, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<float, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<float, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         else
         {
-            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
-            else launch_tile_family<double, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
+            else launch_tile_family<double, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
         stats.launches += 1;
         stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;
@@ -601,6 +662,67 @@ namespace b200
         in_autotune_ = false;
         force_wide_ = -1;
         tuned_[key] = best_cfg;
+    }
+
+    // Shared-memory residency, nothing pinned by the caller: one CTA per SM (two lanes, 32-bit index tables) against two
+    // CTAs per SM (one lane, half the threads, 16-bit tables) on the same frames, timed once per (precision, algorithm).
+    void Engine::autotune_pair(int alg, const decoder_param &dp, void *stream)
+    {
+        cudaStream_t s = (cudaStream_t)stream;
+        const auto key = std::make_pair(tuning.precision, alg);
+        const ldpc_b200_tuning saved = tuning;
+        const ldpc_b200_stats saved_stats = stats;
+        in_autotune_ = true;
+        unsigned long long *d_cnt = nullptr;
+        double rate[2] = {0, 0};
+        try
+        {
+            CUDA_OK(cudaMalloc(&d_cnt, 8 * sizeof(unsigned long long)));
+            CUDA_OK(cudaMemsetAsync(d_cnt, 0, 8 * sizeof(unsigned long long), s));
+            decoder_param tdp = dp;
+            tdp.iterations = std::min<uint32_t>(dp.iterations, 20);
+            tuning.zero_codeword = 1;
+            FrameSource src;
+            src.kind = SRC_AWGN;
+            src.x = -4.0;
+            src.seed = 0x5eed;
+            FrameSink sink;
+            sink.d_counters = d_cnt;
+            const uint64_t frames = (uint64_t)sm_count_ * 2 * 64; // whole waves for both shapes
+            for (int cand = 0; cand < 2; ++cand)
+            {
+                force_pair_ = cand;
+                try
+                {
+                    launch(tdp, src, sink, frames / 4, s); // warm-up (tables, attributes)
+                    if (cand == 1 && stats.threads_per_cta != B200_TILE_MAX_THREADS / 2) break; // not eligible: the one-CTA shape ran
+                    CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
+                    launch(tdp, src, sink, frames, s);
+                    CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));
+                    CUDA_OK(cudaEventSynchronize((cudaEvent_t)ev1_));
+                    float ms = 0;
+                    CUDA_OK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
+                    rate[cand] = (double)frames / ms;
+                }
+                catch (const std::exception &)
+                { // a shape that does not fit is simply not a candidate
+                    cudaGetLastError();
+                }
+            }
+        }
+        catch (...)
+        {
+            cudaFree(d_cnt);
+            tuning = saved; stats = saved_stats; in_autotune_ = false; force_pair_ = -1;
+            throw;
+        }
+        cudaFree(d_cnt);
+        tuning = saved;
+        stats = saved_stats;
+        in_autotune_ = false;
+        force_pair_ = -1;
+        if (std::getenv("LDPC_B200_DEBUG")) fprintf(stderr, "[autotune_pair] one CTA/SM %.1f frames/ms, two CTAs/SM %.1f frames/ms\n", rate[0], rate[1]);
+        pair_tuned_[key] = rate[1] > 1.01 * rate[0] ? 1 : 0;
     }
 
     void Engine::launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream)

@@ -82,13 +82,15 @@ namespace b200
             size_t smem_bytes;
             bool tm;                                  // TMEM mirror in use
             bool wide;                                // global residency: the 1-CTA-per-SM / 128-register kernel build
+            bool idx16;                               // 16-bit index entries (shared-memory residency with the TMEM mirror)
             uint32_t tm_alloc_cols, tm_cols_per_warp, tm_vn_off;
         };
         Config choose(int precision, int alg, uint64_t n_frames);
-        const SegLayout &get_seg_layout(int lanes, int threads);
-        DeviceSegLayout &device_seg_layout(int lanes, int threads);
+        const SegLayout &get_seg_layout(int lanes, int threads, int isz = 4);
+        DeviceSegLayout &device_seg_layout(int lanes, int threads, int isz = 4);
         const TileLayout &get_layout(int fpc, int threads);
         void autotune_global(int alg, const decoder_param &dp, void *stream);
+        void autotune_pair(int alg, const decoder_param &dp, void *stream);
         void launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
         DeviceLayout &device_layout(int fpc, int threads, bool idx16);
         void ensure_state(size_t bytes);
@@ -96,13 +98,15 @@ namespace b200
 
         bool cuda_ready_ = false;
         int sm_count_ = 148;
-        size_t smem_optin_ = 227 * 1024;
+        size_t smem_optin_ = 227 * 1024, smem_per_sm_ = 228 * 1024;
+        std::map<std::pair<int, int>, int> pair_tuned_; // (precision, alg) -> 1 when the two-CTAs-per-SM shape won its trial (shared-memory residency)
+        int force_pair_ = -1;                           // trial: -1 = use pair_tuned_, 0/1 = force
         void *stream_ = nullptr;
         void *ev0_ = nullptr, *ev1_ = nullptr;
         std::map<std::pair<int, int>, std::unique_ptr<TileLayout>> layouts_;
         std::map<std::tuple<int, int, bool>, std::unique_ptr<DeviceLayout>> dev_layouts_;
-        std::map<std::pair<int, int>, std::unique_ptr<SegLayout>> seg_layouts_;
-        std::map<std::pair<int, int>, std::unique_ptr<DeviceSegLayout>> dev_seg_layouts_;
+        std::map<std::tuple<int, int, int>, std::unique_ptr<SegLayout>> seg_layouts_;
+        std::map<std::tuple<int, int, int>, std::unique_ptr<DeviceSegLayout>> dev_seg_layouts_;
         std::map<std::tuple<int, int, int, int, int, size_t>, int> occupancy_;
         std::map<std::pair<int, int>, std::tuple<int, int, int>> tuned_; // (precision, alg) -> autotuned (lanes, threads, wide), global residency
         bool in_autotune_ = false;

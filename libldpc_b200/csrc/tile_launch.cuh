@@ -18,7 +18,7 @@ namespace b200
 
     constexpr int TILE_SMEM_OPTIN = 232448 - 1024; // 227 KB minus the kernel's static shared memory
 
-    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
     void prepare_tile_one()
     {
         // the opt-in is a per-device attribute of the function: remember it per device (several GPUs in one process)
@@ -27,27 +27,29 @@ namespace b200
         cudaGetDevice(&dev);
         if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire))
         {
-            cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
+            cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, IdxT, ALG, SMEM, LANES, TM, ET, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
             if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
+            // all of the L1/shared array as shared memory: the kernels keep their working set there (two CTAs per SM need it)
+            cudaFuncSetAttribute(tile4_kernel<T, IdxT, ALG, SMEM, LANES, TM, ET, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
         }
     }
 
-    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
     void launch_tile_one(const K4Params &kp, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
     {
-        prepare_tile_one<T, ALG, SMEM, LANES, TM, ET, MINB>();
-        tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET, MINB><<<ctas, threads, smem_bytes, s>>>(kp);
+        prepare_tile_one<T, IdxT, ALG, SMEM, LANES, TM, ET, MINB>();
+        tile4_kernel<T, IdxT, ALG, SMEM, LANES, TM, ET, MINB><<<ctas, threads, smem_bytes, s>>>(kp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " (tile kernel launch)");
     }
 
-    template <typename T, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
+    template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
     int occupancy_tile_one(int threads, size_t smem_bytes)
     {
-        prepare_tile_one<T, ALG, SMEM, LANES, TM, ET, MINB>();
+        prepare_tile_one<T, IdxT, ALG, SMEM, LANES, TM, ET, MINB>();
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile4_kernel<T, uint32_t, ALG, SMEM, LANES, TM, ET, MINB>, threads, smem_bytes);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile4_kernel<T, IdxT, ALG, SMEM, LANES, TM, ET, MINB>, threads, smem_bytes);
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
         return n;
     }
@@ -56,51 +58,60 @@ namespace b200
     // variants in parallel; engine.cu holds the dispatch over `lanes`.
     // wide (global residency, min-sum): the 1-CTA-per-SM / 128-register build instead of the 2-CTA / 64-register one
     template <typename T, int ALG, int L>
-    void launch_tile_lanes(const K4Params &kp, bool smem, bool tm, bool et, bool wide, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
+    void launch_tile_lanes(const K4Params &kp, bool smem, bool tm, bool et, bool wide, bool idx16, int ctas, int threads, size_t smem_bytes, cudaStream_t s);
     template <typename T, int ALG, int L>
-    int occupancy_tile_lanes(bool smem, bool tm, bool et, bool wide, int threads, size_t smem_bytes);
+    int occupancy_tile_lanes(bool smem, bool tm, bool et, bool wide, bool idx16, int threads, size_t smem_bytes);
 
 #define B200_DEFINE_TILE_LANES(T, ALG, L)                                                                              \
     template <>                                                                                                        \
-    void launch_tile_lanes<T, ALG, L>(const K4Params &kp, bool smem, bool tm, bool et, bool wide, int ctas, int threads, size_t smem_bytes, cudaStream_t s) \
+    void launch_tile_lanes<T, ALG, L>(const K4Params &kp, bool smem, bool tm, bool et, bool wide, bool idx16, int ctas, int threads, size_t smem_bytes, \
+                                      cudaStream_t s)                                                                  \
     {                                                                                                                  \
         constexpr int NB = (ALG == ALG_MS) ? (1024 / B200_TILE_MAX_THREADS) : 1;                                       \
-        if (smem && tm && (et || ALG != ALG_MS)) launch_tile_one<T, ALG, true, L, true, true, 1>(kp, ctas, threads, smem_bytes, s); \
-        else if (smem && tm) launch_tile_one<T, ALG, true, L, true, ALG != ALG_MS, 1>(kp, ctas, threads, smem_bytes, s); \
-        else if (smem) launch_tile_one<T, ALG, true, L, false, true, 1>(kp, ctas, threads, smem_bytes, s);             \
-        else if (wide) launch_tile_one<T, ALG, false, L, false, true, 1>(kp, ctas, threads, smem_bytes, s);            \
-        else launch_tile_one<T, ALG, false, L, false, true, NB>(kp, ctas, threads, smem_bytes, s);                     \
+        typedef uint32_t U32;                                                                                          \
+        typedef uint16_t U16;                                                                                          \
+        if (smem && tm && idx16 && (et || ALG != ALG_MS)) launch_tile_one<T, U16, ALG, true, L, true, true, 1>(kp, ctas, threads, smem_bytes, s); \
+        else if (smem && tm && idx16) launch_tile_one<T, U16, ALG, true, L, true, ALG != ALG_MS, 1>(kp, ctas, threads, smem_bytes, s); \
+        else if (smem && tm && (et || ALG != ALG_MS)) launch_tile_one<T, U32, ALG, true, L, true, true, 1>(kp, ctas, threads, smem_bytes, s); \
+        else if (smem && tm) launch_tile_one<T, U32, ALG, true, L, true, ALG != ALG_MS, 1>(kp, ctas, threads, smem_bytes, s); \
+        else if (smem) launch_tile_one<T, U32, ALG, true, L, false, true, 1>(kp, ctas, threads, smem_bytes, s);        \
+        else if (wide) launch_tile_one<T, U32, ALG, false, L, false, true, 1>(kp, ctas, threads, smem_bytes, s);       \
+        else launch_tile_one<T, U32, ALG, false, L, false, true, NB>(kp, ctas, threads, smem_bytes, s);                \
     }                                                                                                                  \
     template <>                                                                                                        \
-    int occupancy_tile_lanes<T, ALG, L>(bool smem, bool tm, bool et, bool wide, int threads, size_t smem_bytes)        \
+    int occupancy_tile_lanes<T, ALG, L>(bool smem, bool tm, bool et, bool wide, bool idx16, int threads, size_t smem_bytes) \
     {                                                                                                                  \
         constexpr int NB = (ALG == ALG_MS) ? (1024 / B200_TILE_MAX_THREADS) : 1;                                       \
-        return (smem && tm && (et || ALG != ALG_MS)) ? occupancy_tile_one<T, ALG, true, L, true, true, 1>(threads, smem_bytes) \
-               : (smem && tm)     ? occupancy_tile_one<T, ALG, true, L, true, ALG != ALG_MS, 1>(threads, smem_bytes)   \
-               : smem             ? occupancy_tile_one<T, ALG, true, L, false, true, 1>(threads, smem_bytes)           \
-               : wide             ? occupancy_tile_one<T, ALG, false, L, false, true, 1>(threads, smem_bytes)          \
-                                  : occupancy_tile_one<T, ALG, false, L, false, true, NB>(threads, smem_bytes);        \
+        typedef uint32_t U32;                                                                                          \
+        typedef uint16_t U16;                                                                                          \
+        return (smem && tm && idx16 && (et || ALG != ALG_MS)) ? occupancy_tile_one<T, U16, ALG, true, L, true, true, 1>(threads, smem_bytes) \
+               : (smem && tm && idx16) ? occupancy_tile_one<T, U16, ALG, true, L, true, ALG != ALG_MS, 1>(threads, smem_bytes) \
+               : (smem && tm && (et || ALG != ALG_MS)) ? occupancy_tile_one<T, U32, ALG, true, L, true, true, 1>(threads, smem_bytes) \
+               : (smem && tm)     ? occupancy_tile_one<T, U32, ALG, true, L, true, ALG != ALG_MS, 1>(threads, smem_bytes) \
+               : smem             ? occupancy_tile_one<T, U32, ALG, true, L, false, true, 1>(threads, smem_bytes)      \
+               : wide             ? occupancy_tile_one<T, U32, ALG, false, L, false, true, 1>(threads, smem_bytes)     \
+                                  : occupancy_tile_one<T, U32, ALG, false, L, false, true, NB>(threads, smem_bytes);   \
     }
 
     template <typename T, int ALG>
-    void launch_tile_family(const K4Params &kp, bool smem, bool tm, bool et, bool wide, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
+    void launch_tile_family(const K4Params &kp, bool smem, bool tm, bool et, bool wide, bool idx16, int lanes, int ctas, int threads, size_t smem_bytes, cudaStream_t s)
     {
         switch (lanes)
         {
-        case 1: launch_tile_lanes<T, ALG, 1>(kp, smem, tm, et, wide, ctas, threads, smem_bytes, s); return;
-        case 2: launch_tile_lanes<T, ALG, 2>(kp, smem, tm, et, wide, ctas, threads, smem_bytes, s); return;
-        case 4: launch_tile_lanes<T, ALG, 4>(kp, smem, tm, et, wide, ctas, threads, smem_bytes, s); return;
+        case 1: launch_tile_lanes<T, ALG, 1>(kp, smem, tm, et, wide, idx16, ctas, threads, smem_bytes, s); return;
+        case 2: launch_tile_lanes<T, ALG, 2>(kp, smem, tm, et, wide, idx16, ctas, threads, smem_bytes, s); return;
+        case 4: launch_tile_lanes<T, ALG, 4>(kp, smem, tm, et, wide, idx16, ctas, threads, smem_bytes, s); return;
         default: throw std::runtime_error("lanes per node must be 1, 2 or 4");
         }
     }
     template <typename T, int ALG>
-    int tile_family_occupancy(bool smem, bool tm, bool et, bool wide, int lanes, int threads, size_t smem_bytes)
+    int tile_family_occupancy(bool smem, bool tm, bool et, bool wide, bool idx16, int lanes, int threads, size_t smem_bytes)
     {
         switch (lanes)
         {
-        case 1: return occupancy_tile_lanes<T, ALG, 1>(smem, tm, et, wide, threads, smem_bytes);
-        case 2: return occupancy_tile_lanes<T, ALG, 2>(smem, tm, et, wide, threads, smem_bytes);
-        case 4: return occupancy_tile_lanes<T, ALG, 4>(smem, tm, et, wide, threads, smem_bytes);
+        case 1: return occupancy_tile_lanes<T, ALG, 1>(smem, tm, et, wide, idx16, threads, smem_bytes);
+        case 2: return occupancy_tile_lanes<T, ALG, 2>(smem, tm, et, wide, idx16, threads, smem_bytes);
+        case 4: return occupancy_tile_lanes<T, ALG, 4>(smem, tm, et, wide, idx16, threads, smem_bytes);
         default: throw std::runtime_error("lanes per node must be 1, 2 or 4");
         }
     }

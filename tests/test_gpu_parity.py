@@ -276,14 +276,14 @@ def irregular_code(tmp_path_factory):
     return str(path)
 
 
-@pytest.mark.parametrize("tmem", [0, 1])
+@pytest.mark.parametrize("tmem,idx16", [(0, 0), (1, 0), (0, 2)])
 @pytest.mark.parametrize("decoding,et,iters", [("BP_MS", True, 40), ("BP_MS", False, 9), ("BP", True, 25), ("BP", False, 3)])
-def test_irregular_code_all_bodies(built_lib, irregular_code, decoding, et, iters, tmem):
+def test_irregular_code_all_bodies(built_lib, irregular_code, decoding, et, iters, tmem, idx16):
     from libldpc_b200 import api
     from oracle import oracle as O
     ctx = api.Context(irregular_code, "", device=0)
     oc = O.Code(irregular_code)
-    ctx.set_tuning(precision=api.F64, residency=api.SMEM, tmem=tmem)
+    ctx.set_tuning(precision=api.F64, residency=api.SMEM, tmem=tmem, idx16=idx16)
     rng = np.random.default_rng(99)
     llr = rng.normal(1.4, 1.9, size=(37, oc.nc))
     llr[:, oc.puncture] = 0.0
@@ -331,14 +331,22 @@ def test_full_size_counters_identical_across_kernel_variants(gpu_ctx):
     n = 148 * 4 * 512
     kw = dict(seed=21, point=4, frame0=1 << 40, nframes=n, decoding="BP_MS", iterations=50)
     res = {}
-    for name, t in (("smem+tmem", dict(residency=api.SMEM, tmem=0)), ("smem", dict(residency=api.SMEM, tmem=1)), ("global", dict(residency=api.GLOBAL, tmem=0))):
-        gpu_ctx.set_tuning(precision=api.F64, frames_per_cta=0, threads_per_cta=0, **t)
+    shapes = {}
+    auto = dict(frames_per_cta=0, threads_per_cta=0, ctas=0)
+    for name, t in (("smem+tmem", dict(residency=api.SMEM, tmem=0, idx16=0, **auto)),     # automatic (whichever shape won the timed trial)
+                    ("smem+tmem32", dict(residency=api.SMEM, tmem=0, idx16=1, **auto)),   # one CTA per SM, 32-bit index tables
+                    ("pair16", dict(residency=api.SMEM, tmem=0, idx16=2, frames_per_cta=2, threads_per_cta=256, ctas=296)),  # two per SM, 16-bit tables
+                    ("smem", dict(residency=api.SMEM, tmem=1, idx16=0, **auto)), ("global", dict(residency=api.GLOBAL, tmem=0, idx16=0, **auto))):
+        gpu_ctx.set_tuning(precision=api.F64, **t)
         res[name] = {et: gpu_ctx.sim_point("AWGN", -4.2, early_term=et, **kw) for et in (True, False)}
-    gpu_ctx.set_tuning(residency=api.AUTO, tmem=0)
+        st = gpu_ctx.stats()
+        shapes[name] = (st["frames_per_cta"], st["threads_per_cta"], st["ctas"])
+    gpu_ctx.set_tuning(residency=api.AUTO, tmem=0, idx16=0, **auto)
+    assert shapes["pair16"] == (2, 256, 296) and shapes["smem+tmem32"] == (4, 512, 148), shapes
     for et in (True, False):
         ref = {k: res["smem+tmem"][et][k] for k in ("fec", "bec", "frames", "iters")}
         assert ref["frames"] == n
-        for name in ("smem", "global"):
+        for name in ("smem+tmem32", "pair16", "smem", "global"):
             assert {k: res[name][et][k] for k in ("fec", "bec", "frames", "iters")} == ref, (name, et)
     a, b = res["smem+tmem"][True], res["smem+tmem"][False]
     assert b["iters"] == 50 * n and a["iters"] < b["iters"]
