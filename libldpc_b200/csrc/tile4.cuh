@@ -139,6 +139,14 @@ namespace b200
             asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(v.e[0]), "f"(v.e[1]), "f"(v.e[2]), "f"(v.e[3]) : "memory");
         }
     };
+    // a segment descriptor is the same in every lane (one address per warp): say so with a broadcast, so that the degree
+    // dispatch, the task loop and the TMEM addresses derived from it are uniform-datapath work
+    __device__ __forceinline__ uint4 uniform4(uint4 v)
+    {
+        v.x = __shfl_sync(0xFFFFFFFFu, v.x, 0); v.y = __shfl_sync(0xFFFFFFFFu, v.y, 0);
+        v.z = __shfl_sync(0xFFFFFFFFu, v.z, 0); v.w = __shfl_sync(0xFFFFFFFFu, v.w, 0);
+        return v;
+    }
     __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
     __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -608,7 +616,8 @@ namespace b200
         __shared__ uint32_t s_active, s_skip, s_next, s_tmem;
 
         const int tid = threadIdx.x, nthreads = blockDim.x;
-        const int lane = tid & 31, warp = tid >> 5, warps = nthreads >> 5;
+        // the warp index through a broadcast: the compiler then keeps everything derived from it in uniform registers
+        const int lane = tid & 31, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0), warps = nthreads >> 5;
         const int sub = lane & (LANES - 1), j = lane / LANES;
 
         // ---- carve state and tables --------------------------------------------------------
@@ -904,7 +913,7 @@ namespace b200
 #ifdef B200_PHASE_TIMING
                     const long long ph0 = clock64();
 #endif
-                    const uint4 sg = sg_next;
+                    const uint4 sg = uniform4(sg_next);
                     if (sg.x == 0) break;
                     sp += 16;
                     sg_next = WAcc<SMEM, 0>::ld4(sp); // the next descriptor (or the terminator) is in flight while this segment runs
@@ -1010,7 +1019,7 @@ namespace b200
                 uint4 sg_next = WAcc<SMEM, 0>::ld4(vn_seg_w);
                 for (P sp = vn_seg_w;;)
                 {
-                    const uint4 sg = sg_next;
+                    const uint4 sg = uniform4(sg_next);
                     if (sg.x == 0) break;
                     sp += 16;
                     sg_next = WAcc<SMEM, 0>::ld4(sp);

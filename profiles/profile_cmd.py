@@ -1,5 +1,6 @@
 """Short, deterministic workload for ncu captures (a few launches of the dominant kernel).
-usage: python profiles/profile_cmd.py [ms|bp|ms32|et] [frames] [frames_per_cta] [threads_per_cta] [codefile]"""
+usage: python profiles/profile_cmd.py [ms|bp|ms32|et] [frames] [frames_per_cta] [threads_per_cta] [codefile]
+PAIR=1 in the environment: the two-CTAs-per-SM shape (one lane, 256 threads, 16-bit index tables, 296 CTAs)."""
 import os
 import sys
 
@@ -14,6 +15,8 @@ threads = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 code = sys.argv[5] if len(sys.argv) > 5 else os.path.join(ROOT, "codes", "ref_h_n1152_m1024.txt")
 ctx = api.Context(code, "", device=0)
 ctx.set_tuning(precision=api.F32 if mode == "ms32" else api.F64, frames_per_cta=fpc, threads_per_cta=threads)
+if os.environ.get("PAIR") == "1":
+    ctx.set_tuning(frames_per_cta=4 if mode == "ms32" else 2, threads_per_cta=256, idx16=2, ctas=296)
 dec = "BP" if mode == "bp" else "BP_MS"
 for i in range(3):
     r = ctx.sim_point("AWGN", -4.5, seed=0, point=0, frame0=i * frames, nframes=frames, decoding=dec, iterations=50, early_term=(mode == "et"))
