@@ -617,7 +617,8 @@ namespace b200
 
         const int tid = threadIdx.x, nthreads = blockDim.x;
         // the warp index through a broadcast: the compiler then keeps everything derived from it in uniform registers
-        const int lane = tid & 31, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0), warps = nthreads >> 5;
+        // (shared-memory residency only: the global-residency kernels lost 25-30 % with it, their loads want to stay in flight)
+        const int lane = tid & 31, warp = SMEM ? __shfl_sync(0xFFFFFFFFu, tid >> 5, 0) : (tid >> 5), warps = nthreads >> 5;
         const int sub = lane & (LANES - 1), j = lane / LANES;
 
         // ---- carve state and tables --------------------------------------------------------
@@ -913,7 +914,7 @@ namespace b200
 #ifdef B200_PHASE_TIMING
                     const long long ph0 = clock64();
 #endif
-                    const uint4 sg = uniform4(sg_next);
+                    const uint4 sg = SMEM ? uniform4(sg_next) : sg_next;
                     if (sg.x == 0) break;
                     sp += 16;
                     sg_next = WAcc<SMEM, 0>::ld4(sp); // the next descriptor (or the terminator) is in flight while this segment runs
@@ -1019,7 +1020,7 @@ namespace b200
                 uint4 sg_next = WAcc<SMEM, 0>::ld4(vn_seg_w);
                 for (P sp = vn_seg_w;;)
                 {
-                    const uint4 sg = uniform4(sg_next);
+                    const uint4 sg = SMEM ? uniform4(sg_next) : sg_next;
                     if (sg.x == 0) break;
                     sp += 16;
                     sg_next = WAcc<SMEM, 0>::ld4(sp);

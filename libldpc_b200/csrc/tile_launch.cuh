@@ -29,8 +29,9 @@ namespace b200
         {
             cudaError_t e = cudaFuncSetAttribute(tile4_kernel<T, IdxT, ALG, SMEM, LANES, TM, ET, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN);
             if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
-            // all of the L1/shared array as shared memory: the kernels keep their working set there (two CTAs per SM need it)
-            cudaFuncSetAttribute(tile4_kernel<T, IdxT, ALG, SMEM, LANES, TM, ET, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            // all of the L1/shared array as shared memory: the shared-memory kernels keep their working set there (two CTAs per
+            // SM need it); the global-residency kernels keep the default split, they live off the L1 cache
+            if constexpr (SMEM) cudaFuncSetAttribute(tile4_kernel<T, IdxT, ALG, SMEM, LANES, TM, ET, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
         }
     }
