@@ -174,7 +174,18 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the decode path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner to fd 1 at communicator creation: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.all_reduce(torch.zeros(1, device="cuda"))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     if not os.path.exists(api.lib_path()):
         if rank == 0:
             B.build()
