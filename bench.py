@@ -296,6 +296,9 @@ def run_ours(args):
     #       result arrays out; the frames are generated on the device, so no bulk input crosses PCIe by construction
     import numpy as np
     nb = 148 * 4 * 96
+    # NUMA placement of the caller's buffers (what a deployment does): run this rank on the cores next to its GPU while the
+    # pinned buffers are allocated and first touched, so that 8 ranks do not pull their LLRs through one socket
+    old_affinity = _bind_near_gpu(torch.cuda.get_device_properties(local))
     _, gen = ctx.channel("AWGN", SNR_DB, 5 + rank, 0, 0, nb)
     pin_in = torch.empty((nb, NC), dtype=torch.float64, pin_memory=True)
     pin_in.numpy()[:] = gen
@@ -315,6 +318,8 @@ def run_ours(args):
         t_dec = float(t.item())
     assert int(pin_its.numpy().min()) == ITERS and int(pin_its.numpy().max()) == ITERS
     e2e_dec = reps * nb * world * NCT / t_dec / 1e9
+    if old_affinity:
+        os.sched_setaffinity(0, old_affinity)   # the CPU baseline below uses every host core
 
     sim_frames = n_step * max(args.steps // 2, 1) * world
     barrier()
@@ -382,6 +387,29 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _bind_near_gpu(prop):
+    """Pins this process to the CPUs local to the GPU's PCIe root (sysfs local_cpulist); returns the previous affinity
+    (None when nothing was changed)."""
+    try:
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus or cpus == old:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
 
 
 def main():
