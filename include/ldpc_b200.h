@@ -115,8 +115,9 @@ typedef struct
     int ctas;             /* 0 = auto (148 x resident CTAs) */
     int bec_deg1_compat;  /* 1 (default) = erased degree-1 variable nodes send 0 like the reference's UB outcome */
     int tmem;             /* 0 = auto (Tensor-Memory mirror of thread-private state when it fits), 1 = off */
-    int idx16;            /* index entries of the shared-memory tables: 0 = auto (16-bit entries where they make two CTAs per SM
-                             resident, else 32-bit), 1 = always 32-bit, 2 = 16-bit whenever the code is small enough for them */
+    int idx16;            /* index entries of the shared-memory tables: 0 = auto (16-bit entries and two CTAs per SM where a one-off
+                             timed trial finds that shape faster, else 32-bit), 1 = always 32-bit, 2 = 16-bit whenever the code is
+                             small enough for them */
     int zero_codeword;    /* 0 (default) = with a generator matrix loaded the sweep transmits random codewords like the
                              reference's -G; 1 = always the all-zero codeword */
 } ldpc_b200_tuning;
