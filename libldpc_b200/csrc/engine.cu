@@ -906,14 +906,47 @@ namespace b200
         const size_t nc = H.nc;
         // chunk = whole waves of the persistent grid (CTAs x frames per CTA), about 32 MB of input: no partly filled last wave
         // per launch, and a short pipeline fill
-        int64_t chunk = std::max<int64_t>((int64_t)((32ull << 20) / (nc * sizeof(double))), 1);
+        int64_t chunk = std::max<int64_t>((int64_t)((32ull << 20) / (nc * sizeof(double))), 1), wave = 1;
         {
             const bool minsum = dp.type && std::string(dp.type) == "BP_MS";
             const Config c = choose(tuning.precision, minsum ? ALG_MS : ALG_BP, ~0ull >> 1);
-            const int64_t wave = (int64_t)c.ctas * c.fpc;
+            wave = (int64_t)c.ctas * c.fpc;
             chunk = std::max<int64_t>(wave, chunk / wave * wave);
         }
         chunk = std::min<int64_t>(n, chunk);
+        // Piece sizes: the pipeline fills with the H2D copy of the first piece and drains with the kernel and D2H copy of the
+        // last one, so both ends ramp (1, 2, 4 ... waves up to the steady chunk, and down again); the ragged remainder of
+        // the batch rides in the last piece.
+        std::vector<int64_t> pieces;
+        {
+            std::vector<int64_t> ramp;
+            int64_t ramp_sum = 0;
+            for (int64_t w = wave; w < chunk; w *= 2) { ramp.push_back(w); ramp_sum += w; }
+            const int64_t ragged = n % wave, body = n - ragged;
+            if (body >= 2 * ramp_sum + 2 * chunk)
+            {
+                pieces = ramp;
+                for (int64_t left = body - 2 * ramp_sum; left > 0;)
+                {
+                    const int64_t m = std::min(chunk, left);
+                    pieces.push_back(m);
+                    left -= m;
+                }
+                for (auto it = ramp.rbegin(); it != ramp.rend(); ++it) pieces.push_back(*it);
+                pieces.back() += ragged;
+            }
+            else
+                for (int64_t left = n; left > 0;)
+                {
+                    int64_t m = std::min(chunk, left);
+                    if (left - m > 0 && left - m < wave) m = left; // no sliver launch of its own
+                    pieces.push_back(m);
+                    left -= m;
+                }
+        }
+        int64_t max_piece = 0;
+        for (int64_t m : pieces) max_piece = std::max(max_piece, m);
+        chunk = max_piece;
         if (!copy_in_)
         {
             CUDA_OK(cudaStreamCreateWithFlags((cudaStream_t *)&copy_in_, cudaStreamNonBlocking));
@@ -944,11 +977,11 @@ namespace b200
         }
         CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), sk));
         CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, sk));
-        int64_t k = 0;
-        for (int64_t o = 0; o < n; o += chunk, ++k)
+        int64_t k = 0, o = 0;
+        for (size_t pi = 0; pi < pieces.size(); o += pieces[pi], ++pi, ++k)
         {
             const int b = (int)(k & 1);
-            const int64_t m = std::min(chunk, n - o);
+            const int64_t m = pieces[pi];
             if (k >= 2) CUDA_OK(cudaStreamWaitEvent(si, (cudaEvent_t)ev_k_[b], 0)); // the kernel that read this input buffer is done
             CUDA_OK(cudaMemcpyAsync(db_in_[b], llr + o * nc, m * nc * sizeof(double), cudaMemcpyHostToDevice, si));
             CUDA_OK(cudaEventRecord((cudaEvent_t)ev_in_[b], si));

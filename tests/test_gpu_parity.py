@@ -107,6 +107,23 @@ def test_ragged_batches_and_refill(gpu_ctx, oracle_code):
     assert np.array_equal(full[2][:40], ri) and np.array_equal(full[1][:40], rc)
 
 
+def test_large_host_batch_pipeline(gpu_ctx, oracle_code):
+    """A batch long enough for the ramped, double-buffered host pipeline (1, 2, 4 ... waves up, steady chunks, down again, ragged
+    tail): every frame must come back in its place, equal to the same frame decoded in a small batch and to the oracle."""
+    n = 17000 + 37
+    cw, llr = gpu_ctx.channel("AWGN", -4.0, seed=11, point=0, frame0=0, n=n)
+    out, hard, its = gpu_ctx.decode_batch(llr, "BP_MS", 8, True)
+    assert out.shape == (n, oracle_code.nc) and its.shape == (n,)
+    rng = np.random.default_rng(5)
+    for o in [0, 591, 592, 4143, 4144, n - 700] + list(rng.integers(0, n - 64, 6)):
+        part = gpu_ctx.decode_batch(llr[o:o + 64], "BP_MS", 8, True)
+        assert np.array_equal(part[0].view(np.uint64), out[o:o + 64].view(np.uint64)), o
+        assert np.array_equal(part[1], hard[o:o + 64]) and np.array_equal(part[2], its[o:o + 64]), o
+    sel = np.r_[0:8, n - 8:n]
+    ro, rc, ri = oracle_code.decode(llr[sel], 8, True, True)
+    assert np.array_equal(its[sel], ri) and np.array_equal(hard[sel], rc) and np.array_equal(out[sel].view(np.uint64), ro.view(np.uint64))
+
+
 def test_channel_kernel_vs_spec(gpu_ctx, oracle_code, oracle_gen):
     """Philox channel: BSC/BEC inputs bit-exact with the CPU specification, AWGN within 1e-12.  The context holds a
     generator matrix, so AWGN/BSC frames carry random codewords u*G (the reference's -G); the erasure path transmits
