@@ -519,20 +519,7 @@ namespace b200
         }
 
         const int alg = minsum ? ALG_MS : ALG_BP;
-        if (!in_autotune_ && n_frames >= 20000 && tuning.frames_per_cta <= 0 && tuning.threads_per_cta <= 0 &&
-            !(tuned_.count(std::make_pair(tuning.precision, alg)) || pair_tuned_.count(std::make_pair(tuning.precision, alg))))
-        {
-            int res = 0;
-            size_t sb = 0;
-            layout_for(tuning.precision, alg, &res, &sb);
-            if (res == LDPC_B200_GLOBAL) autotune_global(alg, dp, s);
-            else if (tuning.idx16 == 0 && tuning.tmem == 0 && tuning.ctas <= 0 && !pair_tuned_.count(std::make_pair(tuning.precision, alg)))
-            { // LDPC_B200_PAIR=0/1 presets the outcome (runs under a profiler, whose serialised replays distort the trial)
-                const char *preset = std::getenv("LDPC_B200_PAIR");
-                if (preset && (preset[0] == '0' || preset[0] == '1')) pair_tuned_[std::make_pair(tuning.precision, alg)] = preset[0] == '1';
-                else autotune_pair(alg, dp, s);
-            }
-        }
+        maybe_autotune(alg, dp, n_frames, s);
         const Config c = choose(tuning.precision, alg, n_frames);
         DeviceSegLayout &dl = device_seg_layout(c.lanes, c.threads, c.idx16 ? 2 : 4);
         const SegLayout &l = *dl.host;
@@ -602,6 +589,25 @@ namespace b200
     // variables like narrow records and many CTAs, codes with scattered gathers like wide records (whole 64-byte
     // sectors per gather).  One-off trial of a few (lanes, threads) shapes on synthetic AWGN frames, fixed iterations;
     // the winner is cached per (precision, algorithm) and used whenever the caller pins nothing.
+    // One-off tile-shape trials, run before the first large job of a (precision, algorithm) when the caller pinned nothing:
+    // global residency -> autotune_global, shared-memory residency -> autotune_pair.  `n_frames` is the size of the whole
+    // job (a batch decode passes its total, not the size of one pipeline piece).
+    void Engine::maybe_autotune(int alg, const decoder_param &dp, uint64_t n_frames, void *stream)
+    {
+        const auto key = std::make_pair(tuning.precision, alg);
+        if (in_autotune_ || n_frames < 20000 || tuning.frames_per_cta > 0 || tuning.threads_per_cta > 0 || tuned_.count(key) || pair_tuned_.count(key)) return;
+        int res = 0;
+        size_t sb = 0;
+        layout_for(tuning.precision, alg, &res, &sb);
+        if (res == LDPC_B200_GLOBAL) autotune_global(alg, dp, stream);
+        else if (tuning.idx16 == 0 && tuning.tmem == 0 && tuning.ctas <= 0)
+        { // LDPC_B200_PAIR=0/1 presets the outcome (runs under a profiler, whose serialised replays distort the trial)
+            const char *preset = std::getenv("LDPC_B200_PAIR");
+            if (preset && (preset[0] == '0' || preset[0] == '1')) pair_tuned_[key] = preset[0] == '1';
+            else autotune_pair(alg, dp, stream);
+        }
+    }
+
     void Engine::autotune_global(int alg, const decoder_param &dp, void *stream)
     {
         cudaStream_t s = (cudaStream_t)stream;
@@ -909,6 +915,7 @@ namespace b200
         int64_t chunk = std::max<int64_t>((int64_t)((32ull << 20) / (nc * sizeof(double))), 1), wave = 1;
         {
             const bool minsum = dp.type && std::string(dp.type) == "BP_MS";
+            maybe_autotune(minsum ? ALG_MS : ALG_BP, dp, (uint64_t)n, sk);
             const Config c = choose(tuning.precision, minsum ? ALG_MS : ALG_BP, ~0ull >> 1);
             wave = (int64_t)c.ctas * c.fpc;
             chunk = std::max<int64_t>(wave, chunk / wave * wave);

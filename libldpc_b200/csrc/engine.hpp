@@ -91,6 +91,7 @@ namespace b200
         const TileLayout &get_layout(int fpc, int threads);
         void autotune_global(int alg, const decoder_param &dp, void *stream);
         void autotune_pair(int alg, const decoder_param &dp, void *stream);
+        void maybe_autotune(int alg, const decoder_param &dp, uint64_t n_frames, void *stream);
         void launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
         DeviceLayout &device_layout(int fpc, int threads, bool idx16);
         void ensure_state(size_t bytes);
