@@ -677,7 +677,7 @@ namespace b200
         int it = 0;
         uint32_t active = 0, skip = 0; // CTA-uniform copies of s_active / s_skip
 #ifdef B200_PHASE_TIMING
-        long long pt_refill = 0, pt_nrefill = 0;
+        long long pt_refill = 0, pt_nrefill = 0, pt_rf[4] = {0, 0, 0, 0}; // stages: bit errors (+ arrival skew), bookkeeping, outputs, generate
 #endif
         // A refill rewrites c2v / llr in shared memory behind the TMEM mirror's back: the next check phase and the
         // next variable phase read shared memory (and refresh the mirror).  CTA-uniform.
@@ -796,6 +796,10 @@ namespace b200
                     }
                 __syncthreads();
             }
+#ifdef B200_PHASE_TIMING
+            const long long rf1 = clock64();
+            pt_rf[0] += rf1 - rf0;
+#endif
             if (warp == 0)
             {
                 bool got = false;
@@ -840,6 +844,10 @@ namespace b200
                 }
             }
             __syncthreads();
+#ifdef B200_PHASE_TIMING
+            const long long rf2 = clock64();
+            pt_rf[1] += rf2 - rf1;
+#endif
             const uint32_t new_active = s_active;
             if (!first_fill && (p.llr_out || p.hard_out || p.iters_out))
             {
@@ -858,9 +866,16 @@ namespace b200
                     }
                 __syncthreads();
             }
+#ifdef B200_PHASE_TIMING
+            const long long rf3 = clock64();
+            pt_rf[2] += rf3 - rf2;
+#endif
             for (int g = 0; g < FPC; ++g)
                 if (((mask & new_active) >> g) & 1u) generate(g, s_frame[g]);
             __syncthreads();
+#ifdef B200_PHASE_TIMING
+            pt_rf[3] += clock64() - rf3;
+#endif
             active = new_active;
             skip = s_skip;
             fresh |= mask & new_active;
@@ -1147,7 +1162,9 @@ namespace b200
             printf("warp %2d: iterations %lld  check work %lld  wait-B %lld  decision+variable work %lld  wait-A %lld  (cycles per iteration, from barrier release); check segments/it %lld tasks/it %lld header cycles/seg %lld\n", warp, pt_n,
                    pt_cn / pt_n, pt_wb / pt_n, pt_vn / pt_n, pt_wa / pt_n, pt_nseg / pt_n, pt_ntask / pt_n, pt_hdr / (pt_nseg ? pt_nseg : 1));
         if (blockIdx.x == 0 && tid == 0)
-            printf("refills: %lld events, %lld cycles each; iterations %lld\n", pt_nrefill, pt_refill / (pt_nrefill ? pt_nrefill : 1), pt_n);
+            printf("refills: %lld events, %lld cycles each (bit errors %lld, bookkeeping %lld, outputs %lld, generate %lld); iterations %lld\n", pt_nrefill,
+                   pt_refill / (pt_nrefill ? pt_nrefill : 1), pt_rf[0] / (pt_nrefill ? pt_nrefill : 1), pt_rf[1] / (pt_nrefill ? pt_nrefill : 1),
+                   pt_rf[2] / (pt_nrefill ? pt_nrefill : 1), pt_rf[3] / (pt_nrefill ? pt_nrefill : 1), pt_n);
         if (blockIdx.x == 0 && lane == 0)
             printf("warp %2d: variable segments: deg1 %lld tasks/it %lld cycles/task | deg2 %lld tasks/it %lld cycles/task | other %lld tasks/it %lld cycles/task\n", warp,
                    pt_vtask[0] / (pt_n + 1), pt_vcyc[0] / (pt_vtask[0] ? pt_vtask[0] : 1), pt_vtask[1] / (pt_n + 1), pt_vcyc[1] / (pt_vtask[1] ? pt_vtask[1] : 1),
