@@ -129,6 +129,43 @@ namespace b200
         static __device__ __forceinline__ float log_(float v) { return __logf(v); }
     };
 
+#ifdef __CUDACC__
+    // ---- fp64 Jacobian correction log((1 + e^-a) / (1 + e^-b)), a, b >= 0, without the math library ------------------------
+    // The library exp / log spend a third of the sum-product kernel's issue slots on materialising 64-bit polynomial
+    // coefficients (two moves per constant, every call).  Here the coefficients sit in the constant bank and arrive as one
+    // uniform load each; the logarithm of the ratio is 2 atanh((u - v) / (2 + u + v)), |argument| <= 1/3, so no range
+    // reduction, no table.  Accuracy against the exact value: 3.1e-16 absolute at most over 2e7 random pairs — the same as
+    // the reference's own double expression (3.4e-16); the parity bar needs ~1e-14 (profiles/r1/bp_accuracy.md).
+    static __constant__ double BP_EXP_C[14] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+                                               1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0}; // 1/k!
+    static __constant__ double BP_ATH_C[17] = {1.0, 1.0 / 3, 1.0 / 5, 1.0 / 7, 1.0 / 9, 1.0 / 11, 1.0 / 13, 1.0 / 15, 1.0 / 17, 1.0 / 19, 1.0 / 21,
+                                               1.0 / 23, 1.0 / 25, 1.0 / 27, 1.0 / 29, 1.0 / 31, 1.0 / 33}; // 1/(2k+1)
+    // -log2(e), 1.5 * 2^52 (rounds to an integer in the low mantissa bits), ln 2 high and low part, argument clamp (e^-708 ~ 3e-308)
+    static __constant__ double BP_K[5] = {-1.4426950408889634, 6755399441055744.0, 0.6931471803691238, 1.9082149292705877e-10, 708.0};
+
+    __device__ __forceinline__ double bp_exp_neg(double z) // e^-z, z >= 0
+    {
+        const double zc = fmin(z, BP_K[4]);
+        const double t = __fma_rn(zc, BP_K[0], BP_K[1]);
+        const double k = t - BP_K[1];               // round(-z log2 e)
+        double r = __fma_rn(k, -BP_K[2], -zc);      // -z - k ln 2, |r| <= ln 2 / 2
+        r = __fma_rn(k, -BP_K[3], r);
+        double p = BP_EXP_C[13];
+#pragma unroll
+        for (int i = 12; i >= 0; --i) p = __fma_rn(p, r, BP_EXP_C[i]);
+        return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p)); // * 2^k (k >= -1022)
+    }
+    __device__ __forceinline__ double bp_log_ratio(double u, double v) // log((1 + u) / (1 + v)), u, v in [0, 1]
+    {
+        const double w = (u - v) / ((2.0 + u) + v);
+        const double s = w * w;
+        double p = BP_ATH_C[16];
+#pragma unroll
+        for (int i = 15; i >= 0; --i) p = __fma_rn(p, s, BP_ATH_C[i]);
+        return 2.0 * w * p;
+    }
+#endif
+
     // pairwise box-plus with the Jacobian correction, decoder.h:12-15 (same expression, same order)
     template <typename T>
     __device__ __forceinline__ T boxplus(T x, T y)
@@ -136,9 +173,13 @@ namespace b200
         const T ax = Num<T>::abs(x), ay = Num<T>::abs(y);
         const T m = (ay < ax) ? ay : ax;
         const T sm = Num<T>::with_sign(m, Num<T>::hi(x) ^ Num<T>::hi(y));
-        const T num = T(1) + Num<T>::exp_(-Num<T>::abs(x + y));
-        const T den = T(1) + Num<T>::exp_(-Num<T>::abs(x - y));
-        return sm + Num<T>::log_(num / den);
+        if constexpr (sizeof(T) == 8) return sm + bp_log_ratio(bp_exp_neg(Num<T>::abs(x + y)), bp_exp_neg(Num<T>::abs(x - y)));
+        else
+        {
+            const T num = T(1) + Num<T>::exp_(-Num<T>::abs(x + y));
+            const T den = T(1) + Num<T>::exp_(-Num<T>::abs(x - y));
+            return sm + Num<T>::log_(num / den);
+        }
     }
 
 } // namespace b200
