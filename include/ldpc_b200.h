@@ -20,6 +20,13 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* The library is built with -fvisibility=hidden: only the functions declared here are exported. */
+#if defined(__GNUC__)
+#define LDPC_B200_API __attribute__((visibility("default")))
+#else
+#define LDPC_B200_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -67,20 +74,20 @@ typedef struct
 
 /* replaces src/shared.cpp:11-24 — loads the code (and optional generator) into the process-global
  * context; prints "Error: ..." and exit(EXIT_FAILURE)s on file errors like src/core/ldpc.cpp:16-20 */
-void ldpc_setup(const char *pcFile, const char *genFile, int *n, int *m, int *nct, int *mct);
+LDPC_B200_API void ldpc_setup(const char *pcFile, const char *genFile, int *n, int *m, int *nct, int *mct);
 /* replaces src/shared.cpp:26-30 — blocking Monte-Carlo sweep; fills results[] per point; polls *stopFlag */
-void simulate(decoder_param decoderParams, channel_param channelParam, simulation_param simParam,
+LDPC_B200_API void simulate(decoder_param decoderParams, channel_param channelParam, simulation_param simParam,
               sim_results_t *results, bool *stopFlag);
 /* replaces src/shared.cpp:32-35 */
-int calculate_rank(void);
+LDPC_B200_API int calculate_rank(void);
 /* replaces src/shared.cpp:37-45 — infoWord[kct] -> codeWord[nct] (transmitted positions of u*G) */
-void encode(uint8_t *infoWord, uint8_t *codeWord);
+LDPC_B200_API void encode(uint8_t *infoWord, uint8_t *codeWord);
 /* replaces src/shared.cpp:47-65 — llr[nct] in, llrOut[nct] out, returns the 0-based iteration count
  * (src/decoding/decoder.cpp:66-77).  Punctured and shortened inputs are 0.0 (shared.cpp:50).
  * Unlike the reference there is no sticky min-sum state between calls (reference quirk: decoder.h:73-80). */
-int decode(decoder_param decoderParams, double *llr, double *llrOut);
+LDPC_B200_API int decode(decoder_param decoderParams, double *llr, double *llrOut);
 /* replaces src/shared.cpp:67-77 — word[nc] -> syndrome[mc] */
-void syndrome(uint8_t *word, uint8_t *syndrome);
+LDPC_B200_API void syndrome(uint8_t *word, uint8_t *syndrome);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Part 2 — handle-based B200 API                                                             */
@@ -122,32 +129,42 @@ typedef struct
                              reference's -G; 1 = always the all-zero codeword */
 } ldpc_b200_tuning;
 
-const char *ldpc_b200_last_error(void);
-const char *ldpc_b200_version(void);
+LDPC_B200_API const char *ldpc_b200_last_error(void);
+LDPC_B200_API const char *ldpc_b200_version(void);
 /* number of CUDA devices visible (0 when there is no GPU / driver) */
-int ldpc_b200_device_count(void);
+LDPC_B200_API int ldpc_b200_device_count(void);
 
 /* Loads pcFile (+ genFile, may be NULL/"") on the host.  device >= 0 binds the context to that CUDA
  * device (tables are uploaded lazily on first use); device = -1 keeps it host-only.  NULL on failure. */
-ldpc_b200_ctx *ldpc_b200_open(const char *pcFile, const char *genFile, int device);
-void ldpc_b200_close(ldpc_b200_ctx *ctx);
-int ldpc_b200_info(const ldpc_b200_ctx *ctx, ldpc_b200_code_info *info);
-int ldpc_b200_set_tuning(ldpc_b200_ctx *ctx, const ldpc_b200_tuning *t);
-int ldpc_b200_get_tuning(const ldpc_b200_ctx *ctx, ldpc_b200_tuning *t);
+LDPC_B200_API ldpc_b200_ctx *ldpc_b200_open(const char *pcFile, const char *genFile, int device);
+LDPC_B200_API void ldpc_b200_close(ldpc_b200_ctx *ctx);
+LDPC_B200_API int ldpc_b200_info(const ldpc_b200_ctx *ctx, ldpc_b200_code_info *info);
+LDPC_B200_API int ldpc_b200_set_tuning(ldpc_b200_ctx *ctx, const ldpc_b200_tuning *t);
+LDPC_B200_API int ldpc_b200_get_tuning(const ldpc_b200_ctx *ctx, ldpc_b200_tuning *t);
+
+/* One launch in flight per context at a time is the supported use.  Launches of one context that do overlap (different
+ * caller streams) are still safe: the per-CTA message workspace in HBM (large codes, byte-wise erasure decoder) is shared
+ * by the launches of a context and every launch waits, on its own stream, for the previous user of that workspace.
+ *
+ * The kernel shape of a (decoder type, precision) pair is picked by a one-off timed trial before the first large job.  The
+ * blocking entry points run it themselves; the asynchronous ones (ldpc_b200_decode_batch_device, ldpc_b200_sim_point_async)
+ * never block and use the cached outcome or the default shape.  Call ldpc_b200_prepare once (blocking) to have the trial
+ * done before a stream of asynchronous launches; n_frames = the size of the job (jobs below ~20000 frames skip the trial). */
+LDPC_B200_API int ldpc_b200_prepare(ldpc_b200_ctx *ctx, decoder_param dp, uint64_t n_frames);
 
 /* host-side views of the loaded code (file order; sizes from ldpc_b200_info) */
-int ldpc_b200_get_edges(const ldpc_b200_ctx *ctx, int *rows /*[nnz]*/, int *cols /*[nnz]*/);
-int ldpc_b200_get_bit_pos(const ldpc_b200_ctx *ctx, int *bit_pos /*[nct]*/);
-int ldpc_b200_get_puncture(const ldpc_b200_ctx *ctx, int *punct /*[n_punct]*/, int *shorten /*[n_short]*/);
+LDPC_B200_API int ldpc_b200_get_edges(const ldpc_b200_ctx *ctx, int *rows /*[nnz]*/, int *cols /*[nnz]*/);
+LDPC_B200_API int ldpc_b200_get_bit_pos(const ldpc_b200_ctx *ctx, int *bit_pos /*[nct]*/);
+LDPC_B200_API int ldpc_b200_get_puncture(const ldpc_b200_ctx *ctx, int *punct /*[n_punct]*/, int *shorten /*[n_short]*/);
 /* device schedule for the current tuning (for tests): for every edge e (file order) the check-major
  * message slot it lives in; n_slots = padded slot count */
-int ldpc_b200_get_layout(ldpc_b200_ctx *ctx, int *edge_slot /*[nnz]*/, int *n_slots, int *frames_per_cta,
+LDPC_B200_API int ldpc_b200_get_layout(ldpc_b200_ctx *ctx, int *edge_slot /*[nnz]*/, int *n_slots, int *frames_per_cta,
                          int *threads_per_cta, int *residency);
 
 /* GF(2) helpers on the host (reference: src/core/sparse.h:162-218,227-294) */
-int ldpc_b200_rank(const ldpc_b200_ctx *ctx);
-int ldpc_b200_encode(const ldpc_b200_ctx *ctx, const uint8_t *info /*[g_rows]*/, uint8_t *cw_full /*[nc]*/);
-int ldpc_b200_syndrome(const ldpc_b200_ctx *ctx, const uint8_t *word /*[nc]*/, uint8_t *synd /*[mc]*/);
+LDPC_B200_API int ldpc_b200_rank(const ldpc_b200_ctx *ctx);
+LDPC_B200_API int ldpc_b200_encode(const ldpc_b200_ctx *ctx, const uint8_t *info /*[g_rows]*/, uint8_t *cw_full /*[nc]*/);
+LDPC_B200_API int ldpc_b200_syndrome(const ldpc_b200_ctx *ctx, const uint8_t *word /*[nc]*/, uint8_t *synd /*[mc]*/);
 
 /* Batched flooding decode on the GPU, HOST buffers (copies are part of the call).
  *   llr      [n_frames][nc]  full-length LLRs (punctured/shortened positions included)
@@ -155,28 +172,28 @@ int ldpc_b200_syndrome(const ldpc_b200_ctx *ctx, const uint8_t *word /*[nc]*/, u
  *   hard     [n_frames][nc]  decisions (LLR <= 0 -> 1, src/decoding/decoder.cpp:58)   (may be NULL)
  *   iters    [n_frames]      reference iteration count (0-based on success)              (may be NULL)
  * Decoder type/iterations/early termination come from decoder_param (reference semantics). */
-int ldpc_b200_decode_batch(ldpc_b200_ctx *ctx, decoder_param dp, const double *llr, int64_t n_frames,
+LDPC_B200_API int ldpc_b200_decode_batch(ldpc_b200_ctx *ctx, decoder_param dp, const double *llr, int64_t n_frames,
                            double *llr_out, uint8_t *hard, int32_t *iters);
 /* Same with DEVICE buffers (already resident in HBM), asynchronous on `stream` (cudaStream_t). */
-int ldpc_b200_decode_batch_device(ldpc_b200_ctx *ctx, decoder_param dp, const double *d_llr, int64_t n_frames,
+LDPC_B200_API int ldpc_b200_decode_batch_device(ldpc_b200_ctx *ctx, decoder_param dp, const double *d_llr, int64_t n_frames,
                                   double *d_llr_out, uint8_t *d_hard, int32_t *d_iters, void *stream);
 
 /* BEC decode, HOST buffers: in[n][nc] in {0,1,'E'}, cw[n][nc] true bits (genie check of the
  * reference's vn_update, src/decoding/decoder.h:145-149). */
-int ldpc_b200_decode_bec_batch(ldpc_b200_ctx *ctx, decoder_param dp, const uint8_t *in, const uint8_t *cw,
+LDPC_B200_API int ldpc_b200_decode_bec_batch(ldpc_b200_ctx *ctx, decoder_param dp, const uint8_t *in, const uint8_t *cw,
                                int64_t n_frames, uint8_t *out, uint8_t *hard, int32_t *iters);
 
 /* Philox channel only: writes the decoder inputs the simulator would generate for global frames
  * [frame0, frame0+n) of sweep point `point`: cw[n][nc] (may be NULL), and llr[n][nc] doubles
  * (AWGN/BSC) or llr_u8[n][nc] (BEC).  HOST buffers. */
-int ldpc_b200_channel(ldpc_b200_ctx *ctx, const char *channel, double x, uint64_t seed, uint32_t point,
+LDPC_B200_API int ldpc_b200_channel(ldpc_b200_ctx *ctx, const char *channel, double x, uint64_t seed, uint32_t point,
                       uint64_t frame0, int64_t n_frames, uint8_t *cw, double *llr, uint8_t *llr_u8);
 
 /* One Monte-Carlo round of one sweep point, fully on the GPU (channel -> decode -> accounting):
  * global frames [frame0, frame0+n_frames).  counters[4] += {frame errors, bit errors, frames,
  * sum of reference iteration counts} (src/sim/ldpcsim.cpp:175-190).  Blocking; counters on the host.
  * device_ms (may be NULL) receives the CUDA-event time of the kernel(s). */
-int ldpc_b200_sim_point(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
+LDPC_B200_API int ldpc_b200_sim_point(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
                         uint32_t point, uint64_t frame0, uint64_t n_frames, uint64_t counters[4], float *device_ms);
 /* Same round with the per-error diagnostics log (the reference's log_error, src/sim/ldpcsim.cpp:282-405, live in
  * gpu/sim/ldpcsim.cpp:351-464): every frame that ends with >= 1 bit error over the transmitted positions is recorded
@@ -190,12 +207,12 @@ typedef struct
     uint32_t bit_errors; /* Hamming distance to the transmitted word over the transmitted positions */
     int32_t iterations;  /* reference iteration count of the frame (0-based on success, decoder.cpp:66-77) */
 } ldpc_b200_error_record;
-int ldpc_b200_sim_point_log(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
+LDPC_B200_API int ldpc_b200_sim_point_log(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
                             uint32_t point, uint64_t frame0, uint64_t n_frames, uint64_t counters[4],
                             ldpc_b200_error_record *records, int64_t capacity, int64_t *n_errors);
 /* Asynchronous variant: d_counters is a DEVICE array of 5 uint64 that the kernel accumulates into
  * ({frame errors, bit errors, frames, sum of reference iteration counts, sum of executed iterations}). */
-int ldpc_b200_sim_point_async(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
+LDPC_B200_API int ldpc_b200_sim_point_async(ldpc_b200_ctx *ctx, decoder_param dp, const char *channel, double x, uint64_t seed,
                               uint32_t point, uint64_t frame0, uint64_t n_frames, uint64_t *d_counters, void *stream);
 
 /* Whole sweep with the reference's semantics (x list, reversed order for BSC/BEC, stop rule, results
@@ -203,7 +220,7 @@ int ldpc_b200_sim_point_async(ldpc_b200_ctx *ctx, decoder_param dp, const char *
  * processes; `allreduce` (may be NULL when world == 1) is called once per round with a small host
  * array of uint64 counters to be summed over ranks (the caller wires it to NCCL/gloo).  quiet != 0 suppresses the console table. */
 typedef void (*ldpc_b200_allreduce_fn)(uint64_t *values, int n, void *user); /* in-place sum over ranks */
-int ldpc_b200_simulate(ldpc_b200_ctx *ctx, decoder_param dp, channel_param cp, simulation_param sp,
+LDPC_B200_API int ldpc_b200_simulate(ldpc_b200_ctx *ctx, decoder_param dp, channel_param cp, simulation_param sp,
                        sim_results_t *results, bool *stopFlag, int rank, int world,
                        ldpc_b200_allreduce_fn allreduce, void *user, int quiet);
 /* Same sweep with the frame processor injected: round_fn (if non-NULL) is called instead of the GPU
@@ -213,7 +230,7 @@ int ldpc_b200_simulate(ldpc_b200_ctx *ctx, decoder_param dp, channel_param cp, s
  * writer) be exercised on machines without a GPU.  Returns non-zero from round_fn to abort. */
 typedef int (*ldpc_b200_round_fn)(uint32_t point, double x, uint64_t frame0, uint64_t n_frames,
                                   uint64_t *counters4, void *user);
-int ldpc_b200_simulate_ex(ldpc_b200_ctx *ctx, decoder_param dp, channel_param cp, simulation_param sp,
+LDPC_B200_API int ldpc_b200_simulate_ex(ldpc_b200_ctx *ctx, decoder_param dp, channel_param cp, simulation_param sp,
                           sim_results_t *results, bool *stopFlag, int rank, int world,
                           ldpc_b200_allreduce_fn allreduce, ldpc_b200_round_fn round_fn, void *user, int quiet);
 
@@ -227,11 +244,11 @@ typedef struct
     int frames_per_cta, threads_per_cta, ctas, residency, precision;
     size_t smem_bytes;
 } ldpc_b200_stats;
-int ldpc_b200_get_stats(const ldpc_b200_ctx *ctx, ldpc_b200_stats *s);
+LDPC_B200_API int ldpc_b200_get_stats(const ldpc_b200_ctx *ctx, ldpc_b200_stats *s);
 /* Measurement aid: sustained shared-memory read bandwidth of the context's device in GB/s (a conflict-free
  * LDS.128 streaming kernel on every SM) — the roofline that bounds the shared-memory-resident decode kernel. */
-int ldpc_b200_smem_probe(ldpc_b200_ctx *ctx, double *gb_per_s);
-int ldpc_b200_reset_stats(ldpc_b200_ctx *ctx);
+LDPC_B200_API int ldpc_b200_smem_probe(ldpc_b200_ctx *ctx, double *gb_per_s);
+LDPC_B200_API int ldpc_b200_reset_stats(ldpc_b200_ctx *ctx);
 
 #ifdef __cplusplus
 }

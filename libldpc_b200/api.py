@@ -62,7 +62,7 @@ HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device
                   "ldpc_b200_get_puncture", "ldpc_b200_get_layout", "ldpc_b200_rank", "ldpc_b200_encode", "ldpc_b200_syndrome",
                   "ldpc_b200_decode_batch", "ldpc_b200_decode_batch_device", "ldpc_b200_decode_bec_batch", "ldpc_b200_channel",
                   "ldpc_b200_sim_point", "ldpc_b200_sim_point_async", "ldpc_b200_simulate", "ldpc_b200_simulate_ex", "ldpc_b200_get_stats",
-                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe", "ldpc_b200_sim_point_log")
+                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe", "ldpc_b200_sim_point_log", "ldpc_b200_prepare")
 
 _lib = None
 
@@ -87,6 +87,7 @@ def load_library(path=None):
     L.ldpc_b200_info.argtypes = [vp, ct.POINTER(code_info)]
     L.ldpc_b200_set_tuning.argtypes = [vp, ct.POINTER(tuning)]
     L.ldpc_b200_get_tuning.argtypes = [vp, ct.POINTER(tuning)]
+    L.ldpc_b200_prepare.argtypes = [vp, decoder_param, u64]
     L.ldpc_b200_get_edges.argtypes = [vp, iptr, iptr]
     L.ldpc_b200_get_bit_pos.argtypes = [vp, iptr]
     L.ldpc_b200_get_puncture.argtypes = [vp, iptr, iptr]
@@ -265,6 +266,10 @@ class Context:
         bad = tx[hard[0][tx] != cw[0][tx]]
         return dict(frame=int(frame), iterations=int(its[0]), failed_bits=[int(b) for b in bad], hamming_distance=int(len(bad)),
                     failed_checks=[int(i) for i in np.nonzero(synd)[0]], syndrome_weight=int(synd.sum()))
+
+    def prepare(self, decoding="BP", iterations=50, early_term=True, nframes=1 << 20):
+        """Runs the one-off kernel-shape trial for this (decoder, precision) now, so that asynchronous launches use its outcome."""
+        self._check(self.lib.ldpc_b200_prepare(self._h, self._dp(decoding, iterations, early_term), int(nframes)))
 
     def sim_point_async(self, d_counters_ptr, stream_ptr, channel, x, seed=0, point=0, frame0=0, nframes=1000, decoding="BP",
                         iterations=50, early_term=True):

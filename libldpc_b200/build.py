@@ -12,10 +12,10 @@ LIB = os.path.join(HERE, "libldpc.so")
 CLI = os.path.join(HERE, "ldpcsim")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function,-fvisibility=hidden"]
 TILE_SOURCES = ["tile_%s_%s_l%d.cu" % (a, t, l) for a in ("bp", "ms") for t in ("f64", "f32") for l in (1, 2, 4)]  # slowest first
 SOURCES = TILE_SOURCES + ["engine.cu", "code.cpp", "sim_driver.cpp", "shim.cpp"]
-HEADERS = ["engine.hpp", "code.hpp", "kernels.cuh", "tile4.cuh", "tile_launch.cuh", "bec_kernel.cuh", "bec_slice.cuh", "../../include/ldpc_b200.h"]
+HEADERS = ["exports.map", "engine.hpp", "code.hpp", "kernels.cuh", "tile4.cuh", "tile_launch.cuh", "bec_kernel.cuh", "bec_slice.cuh", "../../include/ldpc_b200.h"]
 OBJDIR = os.path.join(HERE, "build")
 if os.environ.get("B200_PHASE_TIMING"):  # debug: per-warp phase cycle counts printed by CTA 0
     COMMON = COMMON + ["-DB200_PHASE_TIMING=1"]
@@ -53,10 +53,11 @@ def build(force=False, verbose=False):
 
         with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
             objs = list(ex.map(compile_one, srcs))
-        subprocess.run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs, check=True)
+        # exported: exactly the functions include/ldpc_b200.h declares (LDPC_B200_API); the static CUDA runtime stays internal
+        subprocess.run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++", "-Xlinker", "--exclude-libs,ALL", "-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map"), "-o", LIB] + objs, check=True)
     cli_src = os.path.join(CSRC, "cli_main.cpp")
     if force or _stale(CLI, [cli_src, LIB]):
-        cmd = [NVCC] + ARCH + COMMON + ["-o", CLI, cli_src, LIB, "-Xlinker", "-rpath,$ORIGIN"]
+        cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", CLI, cli_src, LIB, "-Wl,-rpath,$ORIGIN"]  # a plain C-ABI client
         subprocess.run(cmd, check=True)
     return LIB
 

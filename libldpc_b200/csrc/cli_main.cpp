@@ -4,8 +4,11 @@
 //   --channel AWGN|BSC|BEC (AWGN)  --decoding BP|BP_MS (BP)  --max-frames N (10e9)
 //   --frame-error-count N (50)  --no-early-term  -h/--help  -v/--version
 // Negative MIN/MAX are positionals, as with the reference's argument parser.
-// B200 extras (do not exist in the reference): --precision f64|f32, --device N, --gpus N (frames of every round sharded
-// over N GPUs of this process, one host thread per GPU; the counters are summed on the host, results do not depend on N).
+// B200 extras (do not exist in the reference): --precision f64|f32, --device N, --gpus N / --devices LIST (frames of every
+// round sharded over N GPUs of this process, one host thread per shard; the counters are summed on the host, results do not
+// depend on the number of shards).
+// The CLI is a client of the C ABI only (include/ldpc_b200.h): the library exports nothing else.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <array>
@@ -17,9 +20,7 @@
 #include <thread>
 #include <vector>
 
-#include <cuda_runtime.h>
-
-#include "engine.hpp"
+#include "../../include/ldpc_b200.h"
 
 namespace
 {
@@ -43,7 +44,8 @@ namespace
         "--no-early-term     \tDisable early termination for decoding.\n"
         "--precision         \tB200 only: message arithmetic \"f64\" (bit-exact with the reference, default) or \"f32\"\n"
         "--device            \tB200 only: CUDA device index (Default: 0)\n"
-        "--gpus              \tB200 only: number of GPUs to shard every round of frames over, starting at --device (Default: 1, 0 = all)\n";
+        "--gpus              \tB200 only: number of GPUs to shard every round of frames over, starting at --device (Default: 1, 0 = all)\n"
+        "--devices           \tB200 only: explicit device list for the shards, e.g. 0,1,2,3 (an index may repeat: several shards on one GPU)\n";
 
     bool looks_numeric(const std::string &s)
     {
@@ -54,37 +56,54 @@ namespace
     }
 
     // Multi-GPU rounds: the sweep driver hands one round [frame0, frame0 + n) of a sweep point to this callback, which
-    // splits it contiguously over the engines (one per GPU, one host thread each) and sums the counters.  The frame ->
+    // splits it contiguously over the contexts (one per GPU, one host thread each) and sums the counters.  The frame ->
     // Philox substream mapping depends only on the global frame index, so the totals do not depend on the split.
     struct MultiGpu
     {
-        std::vector<std::unique_ptr<b200::Engine>> engines;
+        std::vector<ldpc_b200_ctx *> ctxs;
         decoder_param dp;
         std::string channel;
         uint64_t seed = 0;
+        ~MultiGpu() { for (auto *c : ctxs) ldpc_b200_close(c); }
     };
     int multi_gpu_round(uint32_t point, double x, uint64_t frame0, uint64_t n, uint64_t *counters, void *user)
     {
         MultiGpu &m = *static_cast<MultiGpu *>(user);
-        const size_t g = m.engines.size();
-        std::vector<std::array<uint64_t, 5>> part(g);
+        const size_t g = m.ctxs.size();
+        std::vector<std::array<uint64_t, 4>> part(g);
         std::vector<std::string> err(g);
         std::vector<std::thread> th;
         for (size_t i = 0; i < g; ++i)
             th.emplace_back([&, i] {
                 const uint64_t lo = frame0 + n * i / g, hi = frame0 + n * (i + 1) / g;
-                part[i] = {0, 0, 0, 0, 0};
+                part[i] = {0, 0, 0, 0};
                 if (hi == lo) return;
-                try { m.engines[i]->sim_point(m.dp, m.channel, x, m.seed, point, lo, hi - lo, part[i].data(), nullptr); }
-                catch (const std::exception &e) { err[i] = e.what(); }
+                if (ldpc_b200_sim_point(m.ctxs[i], m.dp, m.channel.c_str(), x, m.seed, point, lo, hi - lo, part[i].data(), nullptr) != 0)
+                    err[i] = ldpc_b200_last_error(); // thread-local message of the failing call
             });
         for (auto &t : th) t.join();
         for (size_t i = 0; i < g; ++i)
         {
             if (!err[i].empty()) { std::cout << "Error: GPU " << i << ": " << err[i] << std::endl; return 1; }
-            for (int k = 0; k < 5; ++k) counters[k] += part[i][k];
+            for (int k = 0; k < 4; ++k) counters[k] += part[i][k];
         }
         return 0;
+    }
+
+    std::vector<int> parse_devices(const std::string &list)
+    {
+        std::vector<int> v;
+        size_t pos = 0;
+        while (pos <= list.size())
+        {
+            const size_t c = list.find(',', pos);
+            const std::string tok = list.substr(pos, c == std::string::npos ? std::string::npos : c - pos);
+            if (tok.empty()) throw std::runtime_error("--devices expects a comma-separated list of CUDA device indices");
+            v.push_back(std::stoi(tok));
+            if (c == std::string::npos) break;
+            pos = c + 1;
+        }
+        return v;
     }
 
     template <typename V>
@@ -103,6 +122,7 @@ int main(int argc, char **argv)
     unsigned long seed = 0, max_frames = (unsigned long)10e9, fec = 50;
     bool early_term = true;
     int device = 0, gpus = 1;
+    std::string device_list;
     std::vector<std::string> pos;
     try
     {
@@ -128,6 +148,7 @@ int main(int argc, char **argv)
             else if (a == "--precision") precision = value();
             else if (a == "--device") device = std::stoi(value());
             else if (a == "--gpus") gpus = std::stoi(value());
+            else if (a == "--devices") device_list = value();
             else if (a.size() > 1 && a[0] == '-' && !looks_numeric(a)) throw std::runtime_error("Unknown argument: " + a);
             else pos.push_back(a);
         }
@@ -137,30 +158,44 @@ int main(int argc, char **argv)
         if (snr[0] > snr[1]) throw std::runtime_error("snr min > snr max");
         if (precision != "f64" && precision != "f32") throw std::runtime_error("--precision must be f64 or f32");
 
-        std::unique_ptr<b200::Engine> eng;
-        try
+        std::vector<int> devices;
+        if (!device_list.empty()) devices = parse_devices(device_list);
+        else
         {
-            eng = std::make_unique<b200::Engine>(pos[0], gen, device);
+            if (gpus == 0) gpus = std::max(ldpc_b200_device_count(), 1);
+            if (gpus < 1) throw std::runtime_error("--gpus must be >= 0");
+            for (int g = 0; g < gpus; ++g) devices.push_back(device + g);
         }
-        catch (const std::exception &e)
+        MultiGpu m;
+        ldpc_b200_ctx *ctx = ldpc_b200_open(pos[0].c_str(), gen.c_str(), devices[0]);
+        if (!ctx)
         {
-            std::cout << "Error: ldpc_code(): " << e.what() << std::endl; // src/core/ldpc.cpp:16-20
+            std::cout << "Error: ldpc_code(): " << ldpc_b200_last_error() << std::endl; // src/core/ldpc.cpp:16-20
             return EXIT_FAILURE;
         }
-        eng->tuning.precision = precision == "f32" ? LDPC_B200_F32 : LDPC_B200_F64;
-        const auto &H = eng->H;
+        m.ctxs.push_back(ctx);
+        ldpc_b200_tuning tn;
+        ldpc_b200_get_tuning(ctx, &tn);
+        tn.precision = precision == "f32" ? LDPC_B200_F32 : LDPC_B200_F64;
+        ldpc_b200_set_tuning(ctx, &tn);
+        ldpc_b200_code_info H;
+        ldpc_b200_info(ctx, &H);
+        std::vector<int> puncture(std::max(H.n_punct, 1)), shorten(std::max(H.n_short, 1));
+        ldpc_b200_get_puncture(ctx, puncture.data(), shorten.data());
+        puncture.resize(H.n_punct);
+        shorten.resize(H.n_short);
         const char *bar = "========================================================================================";
         std::cout << bar << std::endl;
         std::cout << "Parity-Check Matrix: " << pos[0] << std::endl;
         std::cout << "Generator Matrix: " << gen << std::endl;
         // code summary, src/core/ldpc.cpp:112-130
-        std::cout << "N : " << H.nc << "\nM : " << H.mc << "\nK : " << H.kc() << "\nNNZ : " << H.nnz << "\n";
-        std::cout << "puncture[" << H.puncture.size() << "] : ";
-        print_list(std::cout, H.puncture);
-        std::cout << "\nshorten[" << H.shorten.size() << "] : ";
-        print_list(std::cout, H.shorten);
-        std::cout << "\nRate : " << 1. - (double)H.mct() / (double)H.nct() << "\n";
-        std::cout << "N (transmitted) : " << H.nct() << "\nM (transmitted) : " << H.mct() << "\nK (transmitted) : " << H.kct() << "\n" << std::endl;
+        std::cout << "N : " << H.nc << "\nM : " << H.mc << "\nK : " << H.kc << "\nNNZ : " << H.nnz << "\n";
+        std::cout << "puncture[" << puncture.size() << "] : ";
+        print_list(std::cout, puncture);
+        std::cout << "\nshorten[" << shorten.size() << "] : ";
+        print_list(std::cout, shorten);
+        std::cout << "\nRate : " << 1. - (double)H.mct / (double)H.nct << "\n";
+        std::cout << "N (transmitted) : " << H.nct << "\nM (transmitted) : " << H.mct << "\nK (transmitted) : " << H.kct << "\n" << std::endl;
         std::cout << bar << std::endl;
 
         decoder_param dp{early_term, iterations, decoding.c_str()};
@@ -173,32 +208,27 @@ int main(int argc, char **argv)
         std::cout << "== Simulation Parameters\n Threads: " << sp.threads << "\n FEC: " << sp.fec << "\n Max Frames: " << sp.maxFrames
                   << "\n Output File: " << sp.resultFile << "\n" << std::endl;
         std::cout << bar << std::endl;
-        if (eng->has_gen && channel == "BEC")
-            std::cout << "note: the erasure-channel sweep transmits the all-zero codeword (the generator matrix serves AWGN / BSC sweeps)" << std::endl;
-
         bool stop = false;
-        try
+        int rc;
+        if (devices.size() == 1) rc = ldpc_b200_simulate(ctx, dp, cp, sp, nullptr, &stop, 0, 1, nullptr, nullptr, 0);
+        else
         {
-            if (gpus == 0 && cudaGetDeviceCount(&gpus) != cudaSuccess) gpus = 1;
-            if (gpus < 1) throw std::runtime_error("--gpus must be >= 0");
-            if (gpus == 1) b200::run_sweep(*eng, dp, cp, sp, nullptr, &stop, 0, 1, nullptr, nullptr, false, true);
-            else
+            m.dp = dp; m.channel = channel; m.seed = seed;
+            for (size_t g = 1; g < devices.size(); ++g)
             {
-                MultiGpu m;
-                m.dp = dp; m.channel = channel; m.seed = seed;
-                m.engines.push_back(std::move(eng));
-                for (int g = 1; g < gpus; ++g)
-                {
-                    m.engines.push_back(std::make_unique<b200::Engine>(pos[0], gen, device + g));
-                    m.engines.back()->tuning.precision = m.engines[0]->tuning.precision;
-                }
-                std::cout << "GPUs: " << gpus << " (devices " << device << " .. " << device + gpus - 1 << ")" << std::endl;
-                b200::run_sweep(*m.engines[0], dp, cp, sp, nullptr, &stop, 0, 1, nullptr, &m, false, true, multi_gpu_round);
+                ldpc_b200_ctx *c = ldpc_b200_open(pos[0].c_str(), gen.c_str(), devices[g]);
+                if (!c) { std::cout << "Error: ldpc_code(): " << ldpc_b200_last_error() << std::endl; return EXIT_FAILURE; }
+                ldpc_b200_set_tuning(c, &tn);
+                m.ctxs.push_back(c);
             }
+            std::cout << "GPUs: " << devices.size() << " shards on devices ";
+            print_list(std::cout, devices);
+            std::cout << std::endl;
+            rc = ldpc_b200_simulate_ex(ctx, dp, cp, sp, nullptr, &stop, 0, 1, nullptr, multi_gpu_round, &m, 0);
         }
-        catch (const std::exception &e)
+        if (rc != 0)
         {
-            std::cout << "Error: ldpc_sim::ldpc_sim() " << e.what() << std::endl; // src/sim/ldpcsim.cpp:77-81
+            std::cout << "Error: ldpc_sim::ldpc_sim() " << ldpc_b200_last_error() << std::endl; // src/sim/ldpcsim.cpp:77-81
             return EXIT_FAILURE;
         }
     }

@@ -118,6 +118,7 @@ namespace b200
         dev_layouts_.clear();
         dev_seg_layouts_.clear();
         cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
+        if (ev_state_) cudaEventDestroy((cudaEvent_t)ev_state_);
         cudaFree(d_g_col_ptr_); cudaFree(d_g_row_);
         cudaFree(d_bs_row_ptr_); cudaFree(d_bs_row_edge_); cudaFree(d_bs_col_ptr_); cudaFree(d_bs_col_edge_); cudaFree(d_bs_tx_flag_);
         for (int b = 0; b < 2; ++b)
@@ -190,6 +191,20 @@ namespace b200
         return *it->second;
     }
 
+    // false when the layout cannot be built (e.g. the padded slots of a code with many distinct degrees do not fit 16-bit entries)
+    bool Engine::try_seg_layout(int lanes, int threads, int isz)
+    {
+        try
+        {
+            get_seg_layout(lanes, threads, isz);
+            return true;
+        }
+        catch (const std::exception &)
+        {
+            return false;
+        }
+    }
+
     // Configuration policy.  A CTA holds lanes * VEC frames (VEC = 2 doubles / 4 floats per 16-byte
     // vector).  Shared-memory residency is used whenever the code fits: the widest tile that fits
     // with the default thread count wins (it shares every index load / address computation between
@@ -217,7 +232,8 @@ namespace b200
             for (int lanes = 4; lanes >= 1; lanes >>= 1)
             {
                 if (want_lanes && lanes != want_lanes) continue;
-                const bool i16 = tuning.idx16 == 2 && tuning.tmem == 0 && fits16(lanes);
+                bool i16 = tuning.idx16 == 2 && tuning.tmem == 0 && fits16(lanes);
+                if (i16 && !try_seg_layout(lanes, threads, 2)) i16 = false; // many distinct degrees: the padded layout can still exceed 16 bits
                 const SegLayout &l = get_seg_layout(lanes, threads, i16 ? 2 : 4);
                 const size_t need = seg_smem_bytes(l) + u_bytes(lanes);
                 if (need <= limit)
@@ -234,7 +250,7 @@ namespace b200
                         want_pair = it != pair_tuned_.end() && it->second == 1;
                     }
                     if (want_pair && lanes == 2 && !want_lanes && tuning.threads_per_cta <= 0 && tuning.idx16 == 0 && tuning.tmem == 0 &&
-                        tuning.ctas <= 0 && fits16(1))
+                        tuning.ctas <= 0 && fits16(1) && try_seg_layout(1, max_threads / 2, 2))
                     {
                         const SegLayout &l1 = get_seg_layout(1, max_threads / 2, 2);
                         const size_t need1 = seg_smem_bytes(l1) + u_bytes(1);
@@ -429,15 +445,28 @@ namespace b200
         return *dev_layouts_.emplace(key, std::move(d)).first->second;
     }
 
-    void Engine::ensure_state(size_t bytes)
+    // The per-CTA state block (global residency, byte-wise erasure kernel) is ONE allocation per context: every launch that
+    // uses it first waits for the previous user (an event recorded after that launch), whatever streams the two run on, so
+    // overlapping launches of one context serialise instead of overwriting each other's messages.
+    void Engine::ensure_state(size_t bytes, void *stream)
     {
-        if (bytes <= state_bytes_) return;
-        CUDA_OK(cudaDeviceSynchronize());
-        cudaFree(d_state_);
-        d_state_ = nullptr;
-        state_bytes_ = 0;
-        CUDA_OK(cudaMalloc(&d_state_, bytes));
-        state_bytes_ = bytes;
+        if (bytes > state_bytes_)
+        {
+            CUDA_OK(cudaDeviceSynchronize());
+            cudaFree(d_state_);
+            d_state_ = nullptr;
+            state_bytes_ = 0;
+            CUDA_OK(cudaMalloc(&d_state_, bytes));
+            state_bytes_ = bytes;
+        }
+        if (!ev_state_) CUDA_OK(cudaEventCreateWithFlags((cudaEvent_t *)&ev_state_, cudaEventDisableTiming));
+        else if (state_used_) CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev_state_, 0));
+    }
+
+    void Engine::release_state(void *stream)
+    {
+        CUDA_OK(cudaEventRecord((cudaEvent_t)ev_state_, (cudaStream_t)stream));
+        state_used_ = true;
     }
 
     // Shared-memory streaming probe: every CTA (1024 threads, one per SM) reads a 128 KB window with
@@ -504,7 +533,7 @@ namespace b200
         throw std::runtime_error("No channel selected."); // message of src/sim/ldpcsim.cpp:72
     }
 
-    void Engine::launch(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream)
+    void Engine::launch(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream, bool may_block)
     {
         if (n_frames == 0) return;
         ensure_cuda();
@@ -519,7 +548,9 @@ namespace b200
         }
 
         const int alg = minsum ? ALG_MS : ALG_BP;
-        maybe_autotune(alg, dp, n_frames, s);
+        // the one-off shape trials time kernels and wait for them: only on the blocking entry points.  The asynchronous ones
+        // (caller stream, possibly under graph capture) use the cached outcome or the default shape.
+        if (may_block) maybe_autotune(alg, dp, n_frames, s);
         const Config c = choose(tuning.precision, alg, n_frames);
         DeviceSegLayout &dl = device_seg_layout(c.lanes, c.threads, c.idx16 ? 2 : 4);
         const SegLayout &l = *dl.host;
@@ -557,7 +588,7 @@ namespace b200
         if (c.residency == LDPC_B200_GLOBAL)
         {
             kp.state_stride = ((16 * (size_t)c.lanes * ((size_t)l.n_slots + 2 * (size_t)l.n_pos)) + 255) & ~(size_t)255;
-            ensure_state(kp.state_stride * c.ctas);
+            ensure_state(kp.state_stride * c.ctas, s);
             kp.state = d_state_;
         }
         kp.tm_alloc_cols = c.tm_alloc_cols; kp.tm_cols_per_warp = c.tm_cols_per_warp; kp.tm_vn_off = c.tm_vn_off;
@@ -580,6 +611,7 @@ namespace b200
             if (alg == ALG_MS) launch_tile_family<double, ALG_MS>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
             else launch_tile_family<double, ALG_BP>(kp, smem, c.tm, kp.early_term != 0, c.wide, c.idx16, c.lanes, c.ctas, c.threads, c.smem_bytes, s);
         }
+        if (c.residency == LDPC_B200_GLOBAL) release_state(s);
         stats.launches += 1;
         stats.frames_per_cta = c.fpc; stats.threads_per_cta = c.threads; stats.ctas = c.ctas;
         stats.residency = c.residency; stats.precision = c.precision; stats.smem_bytes = c.smem_bytes;
@@ -644,9 +676,9 @@ namespace b200
                 const uint64_t frames = (uint64_t)sm_count_ * 2 * 16; // whole waves for every shape (the widest holds 16 frames per CTA)
                 try
                 {
-                    launch(tdp, src, sink, frames / 4, s); // warm-up (tables, state block)
+                    launch(tdp, src, sink, frames / 4, s, true); // warm-up (tables, state block)
                     CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
-                    launch(tdp, src, sink, frames, s);
+                    launch(tdp, src, sink, frames, s, true);
                     CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));
                     CUDA_OK(cudaEventSynchronize((cudaEvent_t)ev1_));
                     float ms = 0;
@@ -704,10 +736,10 @@ namespace b200
                 force_pair_ = cand;
                 try
                 {
-                    launch(tdp, src, sink, frames / 4, s); // warm-up (tables, attributes)
+                    launch(tdp, src, sink, frames / 4, s, true); // warm-up (tables, attributes)
                     if (cand == 1 && stats.threads_per_cta != B200_TILE_MAX_THREADS / 2) break; // not eligible: the one-CTA shape ran
                     CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
-                    launch(tdp, src, sink, frames, s);
+                    launch(tdp, src, sink, frames, s, true);
                     CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));
                     CUDA_OK(cudaEventSynchronize((cudaEvent_t)ev1_));
                     float ms = 0;
@@ -805,11 +837,12 @@ namespace b200
         const uint64_t need = (n_frames + 31) / 32;
         if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
         bp.state_stride = (((2 * (size_t)l.n_slots + 3 * (size_t)H.nc) * 32) + 255) & ~(size_t)255;
-        ensure_state(bp.state_stride * ctas);
+        ensure_state(bp.state_stride * ctas, s);
         bp.state = d_state_;
         if (idx16) bec_kernel<uint16_t><<<ctas, threads, 0, s>>>(bp);
         else bec_kernel<uint32_t><<<ctas, threads, 0, s>>>(bp);
         CUDA_OK(cudaGetLastError());
+        release_state(s);
         stats.launches += 1;
         stats.frames_per_cta = 32; stats.threads_per_cta = threads; stats.ctas = ctas;
         stats.residency = LDPC_B200_GLOBAL; stats.precision = -1; stats.smem_bytes = 0;
@@ -820,14 +853,22 @@ namespace b200
     // ------------------------------------------------------------------------------------------
 
     void Engine::sim_point_async(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
-                                 uint64_t frame0, uint64_t n_frames, unsigned long long *d_counters, void *stream)
+                                 uint64_t frame0, uint64_t n_frames, unsigned long long *d_counters, void *stream, bool may_block)
     {
         FrameSource src;
         src.kind = channel_kind(channel);
         src.x = x; src.seed = seed; src.point = point; src.frame0 = frame0;
         FrameSink sink;
         sink.d_counters = d_counters;
-        launch(dp, src, sink, n_frames, stream);
+        launch(dp, src, sink, n_frames, stream, may_block);
+    }
+
+    // One-off shape trials of (decoder type, current precision) for a job of n_frames, on the engine stream.  Blocking.
+    void Engine::prepare(const decoder_param &dp, uint64_t n_frames)
+    {
+        ensure_cuda();
+        const bool minsum = dp.type && std::string(dp.type) == "BP_MS";
+        maybe_autotune(minsum ? ALG_MS : ALG_BP, dp, n_frames, stream_);
     }
 
     void Engine::sim_point(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
@@ -838,7 +879,7 @@ namespace b200
         cudaStream_t s = (cudaStream_t)stream_;
         CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), s));
         CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
-        sim_point_async(dp, channel, x, seed, point, frame0, n_frames, d_counters_, s);
+        sim_point_async(dp, channel, x, seed, point, frame0, n_frames, d_counters_, s, true);
         CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));
         unsigned long long h[5];
         CUDA_OK(cudaMemcpyAsync(h, d_counters_, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -873,7 +914,7 @@ namespace b200
             FrameSink sink;
             sink.d_counters = d_counters_;
             sink.d_err_log = d_log; sink.d_err_count = d_cnt; sink.err_cap = (unsigned long long)capacity;
-            launch(dp, src, sink, n_frames, s);
+            launch(dp, src, sink, n_frames, s, true);
             unsigned long long h[5], n = 0;
             CUDA_OK(cudaMemcpyAsync(h, d_counters_, sizeof(h), cudaMemcpyDeviceToHost, s));
             CUDA_OK(cudaMemcpyAsync(&n, d_cnt, sizeof(n), cudaMemcpyDeviceToHost, s));
@@ -982,6 +1023,9 @@ namespace b200
             if (hard) grow(db_hard_[b], db_hard_cap_[b], (size_t)chunk * nc);
             if (iters) grow(db_it_[b], db_it_cap_[b], (size_t)chunk * sizeof(int32_t));
         }
+        unsigned long long h[5] = {0, 0, 0, 0, 0};
+        try
+        {
         CUDA_OK(cudaMemsetAsync(d_counters_, 0, 8 * sizeof(unsigned long long), sk));
         CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, sk));
         int64_t k = 0, o = 0;
@@ -1010,10 +1054,15 @@ namespace b200
             CUDA_OK(cudaEventRecord((cudaEvent_t)ev_out_[b], so));
         }
         CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, sk));
-        unsigned long long h[5];
         CUDA_OK(cudaMemcpyAsync(h, d_counters_, sizeof(h), cudaMemcpyDeviceToHost, sk));
         CUDA_OK(cudaStreamSynchronize(sk));
         CUDA_OK(cudaStreamSynchronize(so));
+        }
+        catch (...)
+        { // copies in flight still reference the caller's buffers and the cached device buffers: drain all three streams first
+            cudaStreamSynchronize(si); cudaStreamSynchronize(sk); cudaStreamSynchronize(so);
+            throw;
+        }
         float ms = 0;
         CUDA_OK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev0_, (cudaEvent_t)ev1_));
         stats.device_ms += ms;
@@ -1044,7 +1093,7 @@ namespace b200
             src.d_bec_in = d_in; src.d_bec_cw = d_cw;
             FrameSink sink;
             sink.d_bec_out = d_out; sink.d_hard = d_hard; sink.d_iters = d_it;
-            launch(dp, src, sink, (uint64_t)n, s);
+            launch(dp, src, sink, (uint64_t)n, s, true);
             if (out) CUDA_OK(cudaMemcpyAsync(out, d_out, n * nc, cudaMemcpyDeviceToHost, s));
             if (hard) CUDA_OK(cudaMemcpyAsync(hard, d_hard, n * nc, cudaMemcpyDeviceToHost, s));
             if (iters) CUDA_OK(cudaMemcpyAsync(iters, d_it, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -54,8 +54,11 @@ namespace b200
         // Chooses / builds the layout for (precision, algorithm) under the current tuning (host only).
         const SegLayout &layout_for(int precision, int alg, int *residency, size_t *smem_bytes);
 
-        // Launches the tile kernel over n_frames frames on `stream` (0 = engine stream). Asynchronous.
-        void launch(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
+        // Launches the tile kernel over n_frames frames on `stream` (0 = engine stream).  Asynchronous unless may_block, which
+        // allows the one-off timed shape trials (they run and wait for trial kernels on `stream`).
+        void launch(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream, bool may_block = false);
+        // runs the one-off shape trials for (decoder type, current precision) and a job of n_frames now (blocking)
+        void prepare(const decoder_param &dp, uint64_t n_frames);
 
         // Blocking helpers used by the C ABI
         void decode_batch_host(const decoder_param &dp, const double *llr, int64_t n, double *llr_out, uint8_t *hard, int32_t *iters);
@@ -67,7 +70,7 @@ namespace b200
         void sim_point_log(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point, uint64_t frame0,
                            uint64_t n_frames, uint64_t counters[5], ldpc_b200_error_record *records, int64_t capacity, int64_t *n_errors);
         void sim_point_async(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
-                             uint64_t frame0, uint64_t n_frames, unsigned long long *d_counters, void *stream);
+                             uint64_t frame0, uint64_t n_frames, unsigned long long *d_counters, void *stream, bool may_block = false);
 
         // sustained shared-memory read bandwidth of the device in GB/s (LDS.128 streaming from every SM)
         double smem_probe();
@@ -94,7 +97,9 @@ namespace b200
         void maybe_autotune(int alg, const decoder_param &dp, uint64_t n_frames, void *stream);
         void launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
         DeviceLayout &device_layout(int fpc, int threads, bool idx16);
-        void ensure_state(size_t bytes);
+        void ensure_state(size_t bytes, void *stream);
+        void release_state(void *stream);
+        bool try_seg_layout(int lanes, int threads, int isz);
         static int channel_kind(const std::string &name);
 
         bool cuda_ready_ = false;
@@ -119,6 +124,8 @@ namespace b200
         unsigned long long *d_counters_ = nullptr;
         unsigned char *d_state_ = nullptr;
         size_t state_bytes_ = 0;
+        void *ev_state_ = nullptr; // recorded after every launch that uses the state block
+        bool state_used_ = false;
         // host-buffer batch decode pipeline (decode_batch_host): copy streams, per-buffer events, cached device buffers
         void *copy_in_ = nullptr, *copy_out_ = nullptr;
         void *ev_in_[2] = {nullptr, nullptr}, *ev_k_[2] = {nullptr, nullptr}, *ev_out_[2] = {nullptr, nullptr};

@@ -208,6 +208,14 @@ extern "C"
         });
     }
 
+    int ldpc_b200_prepare(ldpc_b200_ctx *ctx, decoder_param dp, uint64_t n_frames)
+    {
+        return guarded([&] {
+            if (!ctx) throw std::runtime_error("null argument");
+            ctx->eng->prepare(dp, n_frames);
+        });
+    }
+
     int ldpc_b200_get_edges(const ldpc_b200_ctx *ctx, int *rows, int *cols)
     {
         return guarded([&] {

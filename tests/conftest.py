@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 H_FILE = os.path.join(ROOT, "codes", "ref_h_n1152_m1024.txt")
 G_FILE = os.path.join(ROOT, "codes", "ref_g_k128_n1152.txt")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+H_IRREGULAR = os.path.join(GOLDEN, "irregular_h.txt")   # committed; written once by tests/golden/make_irregular_golden.py
 
 
 def large_code_files():
@@ -53,6 +54,22 @@ def golden_cases():
         name, field = key.split("/")
         cases.setdefault(name, {})[field] = z[key]
     return cases
+
+
+def _load_cases(path):
+    import numpy as np
+    z = np.load(path)
+    cases = {}
+    for key in z.files:
+        name, field = key.split("/")
+        cases.setdefault(name, {})[field] = z[key]
+    return cases
+
+
+@pytest.fixture(scope="session")
+def irregular_cases():
+    """Outputs of the unmodified reference decoder (oracle/_ref/dump_ref decode) on the irregular code."""
+    return _load_cases(os.path.join(GOLDEN, "irregular_cases.npz"))
 
 
 @pytest.fixture(scope="session")

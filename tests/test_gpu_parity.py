@@ -270,27 +270,39 @@ def test_cli_results_file(built_lib, tmp_path):
 
 
 @pytest.fixture(scope="module")
-def irregular_code(tmp_path_factory):
-    """A small irregular code that fits shared memory and exercises every node-update body: check degrees 2..13
-    (fixed-degree bodies 2..8 and the generic path), variable degrees 0..~25 (bodies 0..8 and the chunked path)."""
-    rng = np.random.default_rng(2024)
-    nc, mc = 420, 240
-    w = 1.0 / (1 + np.arange(nc)) ** 0.7          # skewed column popularity -> a wide spread of variable degrees
-    w[-3:] = 0                                    # three variables without any edge (degree 0)
-    w /= w.sum()
-    edges = []
-    for r in range(mc):
-        deg = 2 + (r % 12)
-        cols = rng.choice(nc, size=deg, replace=False, p=w)
-        edges += [(r, int(c)) for c in cols]
-    edges.append((mc - 1, nc - 4))                # make sure the last-but-three column exists with degree 1
-    edges = sorted(set(edges), key=lambda e: (e[0], rng.random()))   # rows grouped, columns in random file order
-    path = tmp_path_factory.mktemp("irr") / "irregular.txt"
-    with open(path, "w") as f:
-        f.write("puncture [3]: 0 5 9 \nshorten [2]: 17 33 \n")
-        f.write("\n".join(f"{r} {c}" for r, c in edges) + "\n")
-        f.write(f"{mc - 1} {nc - 1} 0\n")         # explicit zero-valued entry pins nc (stored as 1 by the reference: sparse.h:124)
-    return str(path)
+def irregular_code():
+    """A small irregular code that fits shared memory and exercises every node-update body: check degrees 2..15
+    (fixed-degree bodies 2..8 and the generic path), variable degrees 0..81 (bodies 0..16 and the chunked path).
+    Committed (tests/golden/irregular_h.txt) together with outputs of the unmodified reference decoder on it."""
+    from conftest import H_IRREGULAR
+    return H_IRREGULAR
+
+
+@pytest.mark.parametrize("tmem,idx16", [(0, 0), (1, 0), (0, 2)])
+def test_irregular_code_reference_golden(built_lib, irregular_code, irregular_cases, tmem, idx16):
+    """CUDA path vs the UNMODIFIED reference decoder's outputs (dump_ref decode) on the irregular code: min-sum bit-pattern
+    exact, BP within 1e-4 with identical iteration counts."""
+    from libldpc_b200 import api
+    ctx = api.Context(irregular_code, "", device=0)
+    ctx.set_tuning(precision=api.F64, residency=api.SMEM, tmem=tmem, idx16=idx16)
+    for name, case in irregular_cases.items():
+        it, et = [int(v) for v in case["cfg"]]
+        dec = str(case["names"][0])
+        out, hard, its = ctx.decode_batch(case["llr_in"], dec, it, bool(et))
+        assert np.array_equal(its, case["iters"]), name
+        if dec == "BP_MS":
+            assert np.array_equal(hard, case["co"]), name
+            assert np.array_equal(out.view(np.uint64), case["llr_out"].view(np.uint64)), name
+        else:
+            assert (hard == case["co"]).mean() >= 0.9999, name
+            assert _rel_err(out, case["llr_out"]).max() < BP_RTOL, name
+    ctx.set_tuning(residency=api.GLOBAL)
+    for name in ("ms_et50_easy", "ms_bsc", "ms_noet9"):
+        case = irregular_cases[name]
+        it, et = [int(v) for v in case["cfg"]]
+        out, hard, its = ctx.decode_batch(case["llr_in"], "BP_MS", it, bool(et))
+        assert np.array_equal(its, case["iters"]) and np.array_equal(out.view(np.uint64), case["llr_out"].view(np.uint64)), name
+    ctx.close()
 
 
 @pytest.mark.parametrize("tmem,idx16", [(0, 0), (1, 0), (0, 2)])
@@ -307,6 +319,10 @@ def test_irregular_code_all_bodies(built_lib, irregular_code, decoding, et, iter
     llr[:, oc.shorten] = 99999.9
     llr[2, ::5] = -0.0
     ro, rc, ri = oc.decode(llr, iters, et, decoding == "BP_MS")
+    if O.ref_available():   # the comparand is the reference itself wherever its build travelled along (it does to the GPU box)
+        r = O.ref_decode(irregular_code, decoding, iters, et, llr, tmp="/tmp/orc_gpu_irr")
+        assert np.array_equal(ro.view(np.uint64), r["llr_out"].view(np.uint64)) and np.array_equal(rc, r["co"]) and np.array_equal(ri, r["iters"])
+        ro, rc, ri = r["llr_out"], r["co"], r["iters"]
     out, hard, its = ctx.decode_batch(llr, decoding, iters, et)
     assert np.array_equal(its, ri)
     if decoding == "BP_MS":
@@ -432,3 +448,22 @@ def test_cli_multi_gpu_gives_identical_results(built_lib, tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
         rows.append([l.split()[:5] for l in out.read_text().split("\n")[1:] if l.strip()])
     assert rows[0] == rows[1] and len(rows[0]) == 3
+
+
+def test_cli_shards_on_one_gpu_give_identical_results(built_lib, tmp_path):
+    """R-independence on a one-GPU lease: the CUDA path run as two (and three) shard 'ranks' on the SAME device
+    (--devices 0,0: contiguous split of every round, one context + host thread per shard) produces the counters, hence the
+    results file (all columns but the frame time), of the single-range run — sum-product and min-sum, AWGN and BEC."""
+    import os, subprocess
+    from conftest import ROOT
+    cli = os.path.join(ROOT, "libldpc_b200", "ldpcsim")
+    for extra in (["-5.5", "-4.4", "0.5", "--decoding", "BP_MS", "--frame-error-count", "300", "--max-frames", "200000"],
+                  ["-5.5", "-4.9", "0.5", "--decoding", "BP", "--frame-error-count", "100", "--max-frames", "60000", "-i", "20"],
+                  ["0.80", "0.9", "0.05", "--channel", "BEC", "--frame-error-count", "200", "--max-frames", "200000"]):
+        rows = []
+        for devs in ("0", "0,0", "0,0,0"):
+            out = tmp_path / f"res_{len(rows)}.txt"
+            r = subprocess.run([cli, H_FILE, str(out)] + extra + ["-s", "4", "--devices", devs], capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout + r.stderr
+            rows.append([l.split()[:5] for l in out.read_text().split("\n")[1:] if l.strip()])
+        assert rows[0] == rows[1] == rows[2] and len(rows[0]) >= 2, rows

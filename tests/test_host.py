@@ -27,6 +27,15 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert re.search(rf" T {name}$", out, flags=re.M), name
 
 
+def test_library_exports_nothing_else(built_lib):
+    """-fvisibility=hidden + version script: the dynamic symbol table holds the reference's six symbols and the handle API only."""
+    import subprocess
+    from libldpc_b200 import api
+    out = subprocess.run(["nm", "-D", "--defined-only", api.lib_path()], capture_output=True, text=True, check=True).stdout
+    names = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    assert names == set(api.REFERENCE_SYMBOLS) | set(api.HANDLE_SYMBOLS), names ^ (set(api.REFERENCE_SYMBOLS) | set(api.HANDLE_SYMBOLS))
+
+
 def test_struct_layouts_match_reference():
     from libldpc_b200 import api
     assert ct.sizeof(api.decoder_param) == 16 and api.decoder_param.iterations.offset == 4 and api.decoder_param.type.offset == 8
