@@ -193,6 +193,9 @@ def run_ours(args):
             dist.barrier()
     ctx = api.Context(H_FILE, "", device=local)
     ctx.set_tuning(precision=api.F64)
+    # the one-off kernel-shape trials (blocking) happen here; the timed steps below are asynchronous launches
+    for et in (False, True):
+        ctx.prepare(DECODING, ITERS, et, nframes=FRAMES_PER_STEP)
     stream = torch.cuda.Stream()
     counters = torch.zeros(8, dtype=torch.int64, device="cuda")
     n_step = FRAMES_PER_STEP
@@ -284,6 +287,7 @@ def run_ours(args):
 
     # f32 message mode (reported, not the headline)
     ctx.set_tuning(precision=api.F32)
+    ctx.prepare(DECODING, ITERS, False, nframes=FRAMES_PER_STEP)
     step(40_000)
     ms_f32 = timed(max(args.steps // 2, 1), 40_001)
     ctx.set_tuning(precision=api.F64)

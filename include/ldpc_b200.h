@@ -161,6 +161,10 @@ LDPC_B200_API int ldpc_b200_get_puncture(const ldpc_b200_ctx *ctx, int *punct /*
 LDPC_B200_API int ldpc_b200_get_layout(ldpc_b200_ctx *ctx, int *edge_slot /*[nnz]*/, int *n_slots, int *frames_per_cta,
                          int *threads_per_cta, int *residency);
 
+/* message slots of the bit-sliced erasure kernel (for tests): slot % 32 is the shared-memory bank; edge k of 32 consecutive
+ * checks, and edge k of 32 consecutive variables, never share a bank (a 32-colouring of the edges) */
+LDPC_B200_API int ldpc_b200_get_bec_layout(ldpc_b200_ctx *ctx, int *edge_slot /*[nnz]*/, int *n_slots);
+
 /* GF(2) helpers on the host (reference: src/core/sparse.h:162-218,227-294) */
 LDPC_B200_API int ldpc_b200_rank(const ldpc_b200_ctx *ctx);
 LDPC_B200_API int ldpc_b200_encode(const ldpc_b200_ctx *ctx, const uint8_t *info /*[g_rows]*/, uint8_t *cw_full /*[nc]*/);
@@ -174,9 +178,24 @@ LDPC_B200_API int ldpc_b200_syndrome(const ldpc_b200_ctx *ctx, const uint8_t *wo
  * Decoder type/iterations/early termination come from decoder_param (reference semantics). */
 LDPC_B200_API int ldpc_b200_decode_batch(ldpc_b200_ctx *ctx, decoder_param dp, const double *llr, int64_t n_frames,
                            double *llr_out, uint8_t *hard, int32_t *iters);
+/* The same call with narrower encodings at the host <-> device boundary (the six-symbol decode() and the call above keep
+ * double in / byte-per-bit out, src/shared.cpp:47-65).  At 9216 B in + 1152 B out per frame of the n=1152 code the fp64 path
+ * is bound by the PCIe / host-memory path once several GPUs share a host; int8 LLRs + bit-packed decisions move 1152 + 144 B.
+ *   llr_type  LDPC_B200_LLR_F64: const double*  |  _F32: const float* (widened exactly)  |  _I8: const int8_t*, LLR =
+ *             value * llr_scale evaluated in double (exact when llr_scale is a power of two), i.e. the decoder runs on exactly
+ *             the doubles {value * llr_scale}: min-sum stays bit-identical to the reference fed those doubles
+ *   hard_bits [n_frames][ceil(nc/32)] uint32: decision of variable i = bit i%32 of word i/32 (may be NULL)
+ * llr_out / hard / iters as above (any may be NULL). */
+enum { LDPC_B200_LLR_F64 = 0, LDPC_B200_LLR_F32 = 1, LDPC_B200_LLR_I8 = 2 };
+LDPC_B200_API int ldpc_b200_decode_batch_ex(ldpc_b200_ctx *ctx, decoder_param dp, const void *llr, int llr_type, double llr_scale,
+                                            int64_t n_frames, double *llr_out, uint8_t *hard, uint32_t *hard_bits, int32_t *iters);
 /* Same with DEVICE buffers (already resident in HBM), asynchronous on `stream` (cudaStream_t). */
 LDPC_B200_API int ldpc_b200_decode_batch_device(ldpc_b200_ctx *ctx, decoder_param dp, const double *d_llr, int64_t n_frames,
                                   double *d_llr_out, uint8_t *d_hard, int32_t *d_iters, void *stream);
+
+LDPC_B200_API int ldpc_b200_decode_batch_device_ex(ldpc_b200_ctx *ctx, decoder_param dp, const void *d_llr, int llr_type, double llr_scale,
+                                                   int64_t n_frames, double *d_llr_out, uint8_t *d_hard, uint32_t *d_hard_bits,
+                                                   int32_t *d_iters, void *stream);
 
 /* BEC decode, HOST buffers: in[n][nc] in {0,1,'E'}, cw[n][nc] true bits (genie check of the
  * reference's vn_update, src/decoding/decoder.h:145-149). */
@@ -200,7 +219,7 @@ LDPC_B200_API int ldpc_b200_sim_point(ldpc_b200_ctx *ctx, decoder_param dp, cons
  * (up to `capacity` records, unordered; *n_errors receives the number of frames in error, which may exceed capacity).
  * A record names the GLOBAL frame index: because the channel is counter-based, ldpc_b200_channel(frame0 = record.frame,
  * n = 1) regenerates that frame's decoder input exactly and ldpc_b200_decode_batch replays the decoding, which yields
- * the failed bit / check indices and the syndrome weight (libldpc_b200/api.py: Context.error_report).  AWGN / BSC. */
+ * the failed bit / check indices and the syndrome weight (libldpc_b200/api.py: Context.error_report).  All three channels. */
 typedef struct
 {
     uint64_t frame;      /* global frame index of the sweep point */

@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "libldpc.so")
+    """libldpc.so beside this file; LDPC_B200_LIB names another build of the same library (debug / phase-timing builds)."""
+    return os.environ.get("LDPC_B200_LIB") or os.path.join(_HERE, "libldpc.so")
 
 
 class decoder_param(ct.Structure):  # reference: src/core/functions.h:107-112, pyLDPC/ldpc.py:16-19
@@ -55,6 +56,7 @@ ALLREDUCE_FN = ct.CFUNCTYPE(None, ct.POINTER(ct.c_uint64), ct.c_int, ct.c_void_p
 ROUND_FN = ct.CFUNCTYPE(ct.c_int, ct.c_uint32, ct.c_double, ct.c_uint64, ct.c_uint64, ct.POINTER(ct.c_uint64), ct.c_void_p)
 F64, F32 = 0, 1
 AUTO, SMEM, GLOBAL = 0, 1, 2
+LLR_F64, LLR_F32, LLR_I8 = 0, 1, 2
 
 REFERENCE_SYMBOLS = ("ldpc_setup", "simulate", "calculate_rank", "encode", "decode", "syndrome")
 HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device_count", "ldpc_b200_open", "ldpc_b200_close",
@@ -62,7 +64,7 @@ HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device
                   "ldpc_b200_get_puncture", "ldpc_b200_get_layout", "ldpc_b200_rank", "ldpc_b200_encode", "ldpc_b200_syndrome",
                   "ldpc_b200_decode_batch", "ldpc_b200_decode_batch_device", "ldpc_b200_decode_bec_batch", "ldpc_b200_channel",
                   "ldpc_b200_sim_point", "ldpc_b200_sim_point_async", "ldpc_b200_simulate", "ldpc_b200_simulate_ex", "ldpc_b200_get_stats",
-                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe", "ldpc_b200_sim_point_log", "ldpc_b200_prepare")
+                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe", "ldpc_b200_sim_point_log", "ldpc_b200_prepare", "ldpc_b200_decode_batch_ex", "ldpc_b200_decode_batch_device_ex", "ldpc_b200_get_bec_layout")
 
 _lib = None
 
@@ -92,10 +94,13 @@ def load_library(path=None):
     L.ldpc_b200_get_bit_pos.argtypes = [vp, iptr]
     L.ldpc_b200_get_puncture.argtypes = [vp, iptr, iptr]
     L.ldpc_b200_get_layout.argtypes = [vp, iptr, iptr, iptr, iptr, iptr]
+    L.ldpc_b200_get_bec_layout.argtypes = [vp, iptr, iptr]
     L.ldpc_b200_rank.argtypes = [vp]
     L.ldpc_b200_encode.argtypes = [vp, bptr, bptr]
     L.ldpc_b200_syndrome.argtypes = [vp, bptr, bptr]
     L.ldpc_b200_decode_batch.argtypes = [vp, decoder_param, dptr, i64, dptr, bptr, ct.POINTER(ct.c_int32)]
+    L.ldpc_b200_decode_batch_ex.argtypes = [vp, decoder_param, vp, ct.c_int, ct.c_double, i64, dptr, bptr, ct.POINTER(u32), ct.POINTER(ct.c_int32)]
+    L.ldpc_b200_decode_batch_device_ex.argtypes = [vp, decoder_param, vp, ct.c_int, ct.c_double, i64, vp, vp, vp, vp, vp]
     L.ldpc_b200_decode_batch_device.argtypes = [vp, decoder_param, vp, i64, vp, vp, vp, vp]
     L.ldpc_b200_decode_bec_batch.argtypes = [vp, decoder_param, bptr, bptr, i64, bptr, bptr, ct.POINTER(ct.c_int32)]
     L.ldpc_b200_channel.argtypes = [vp, ct.c_char_p, ct.c_double, u64, u32, u64, i64, bptr, dptr, bptr]
@@ -171,6 +176,12 @@ class Context:
         self._check(self.lib.ldpc_b200_get_layout(self._h, _p(es, ct.c_int), *[ct.byref(x) for x in v]))
         return dict(edge_slot=es, n_slots=v[0].value, frames_per_cta=v[1].value, threads_per_cta=v[2].value, residency=v[3].value)
 
+    def bec_layout(self):
+        es = np.empty(self.nnz, np.int32)
+        n = ct.c_int()
+        self._check(self.lib.ldpc_b200_get_bec_layout(self._h, _p(es, ct.c_int), ct.byref(n)))
+        return es, n.value
+
     def set_tuning(self, **kw):
         t = tuning()
         self._check(self.lib.ldpc_b200_get_tuning(self._h, ct.byref(t)))
@@ -216,6 +227,33 @@ class Context:
                                                     _p(out, ct.c_double), _p(hard, ct.c_uint8), _p(its, ct.c_int32)))
         return out, hard, its
 
+    def decode_batch_ex(self, llr, decoding="BP", iterations=50, early_term=True, scale=1.0, want_llr=False, want_hard=False, want_bits=True,
+                        out=None, hard=None, bits=None, its=None):
+        """Narrow encodings of decode_batch: llr [n, nc] float64 / float32 / int8 (LLR = int8 * scale); decisions bit-packed
+        (bits [n, ceil(nc/32)] uint32, variable i = bit i%32 of word i/32).  -> (llr_out | None, hard | None, bits | None, iters)."""
+        llr = np.ascontiguousarray(llr).reshape(-1, self.nc)
+        ty = {np.dtype(np.float64): LLR_F64, np.dtype(np.float32): LLR_F32, np.dtype(np.int8): LLR_I8}[llr.dtype]
+        n = llr.shape[0]
+        hw = (self.nc + 31) // 32
+        if out is None and want_llr:
+            out = np.empty((n, self.nc), np.float64)
+        if hard is None and want_hard:
+            hard = np.empty((n, self.nc), np.uint8)
+        if bits is None and want_bits:
+            bits = np.empty((n, hw), np.uint32)
+        if its is None:
+            its = np.empty(n, np.int32)
+        assert bits is None or (bits.dtype == np.uint32 and bits.size == n * hw and bits.flags.c_contiguous)
+        self._check(self.lib.ldpc_b200_decode_batch_ex(self._h, self._dp(decoding, iterations, early_term), llr.ctypes.data_as(ct.c_void_p), ty,
+                                                       float(scale), n, _p(out, ct.c_double), _p(hard, ct.c_uint8), _p(bits, ct.c_uint32),
+                                                       _p(its, ct.c_int32)))
+        return out, hard, bits, its
+
+    def unpack_bits(self, bits):
+        """bit-packed decisions [n, ceil(nc/32)] uint32 -> [n, nc] uint8"""
+        b = np.unpackbits(np.ascontiguousarray(bits).view(np.uint8), axis=1, bitorder="little")
+        return b[:, :self.nc]
+
     def decode_bec_batch(self, inp, cw, iterations=50, early_term=True):
         inp = np.ascontiguousarray(inp, np.uint8).reshape(-1, self.nc)
         cw = np.ascontiguousarray(cw, np.uint8).reshape(-1, self.nc)
@@ -258,7 +296,10 @@ class Context:
         """Replays ONE logged frame (the channel is counter-based, so its input is regenerated exactly) and returns what the
         reference's log_error prints: failed bit indices (transmitted positions), failed check indices, syndrome weight."""
         cw, llr = self.channel(channel, x, seed, point, frame, 1)
-        out, hard, its = self.decode_batch(llr, decoding, iterations, early_term)
+        if channel == "BEC":
+            out, hard, its = self.decode_bec_batch(llr, cw, iterations, early_term)
+        else:
+            out, hard, its = self.decode_batch(llr, decoding, iterations, early_term)
         r, c = self.edges()
         synd = np.zeros(self.mc, np.uint8)
         np.bitwise_xor.at(synd, r, hard[0][c])

@@ -30,6 +30,12 @@ namespace b200
         unsigned long long *counters;
         unsigned char *state;
         size_t state_stride;
+        // generator matrix by column (-G: random codewords u*G, src/sim/channel.cpp:177-191); g_rows = 0 -> all-zero word
+        const int32_t *g_col_ptr, *g_row;
+        int g_rows, g_cols;
+        // per-error diagnostics log (may be null): {global frame, bit errors | iterations << 32}
+        unsigned long long *err_log, *err_count;
+        unsigned long long err_cap;
     };
 
     __device__ __forceinline__ uint8_t bec_cn(uint8_t l, uint8_t r) { return (l == BEC_E || r == BEC_E) ? BEC_E : (uint8_t)((l != 0) ^ (r != 0)); }
@@ -72,7 +78,21 @@ namespace b200
                 return;
             }
             const unsigned long long frame = p.frame0 + gf;
-            for (int i = tid; i < nc; i += nthreads) cw[i * 32 + g] = 0; // all-zero codeword
+            // transmitted word: all-zero, or u*G with the information word of Philox stream 1 (same rule as the other kernels)
+            for (int i = tid; i < nc; i += nthreads)
+            {
+                uint32_t b = 0;
+                if (p.g_rows > 0 && i < p.g_cols)
+                    for (int q2 = p.g_col_ptr[i]; q2 < p.g_col_ptr[i + 1]; ++q2)
+                    {
+                        const int r = p.g_row[q2];
+                        const u32x4 w = channel_block(p.seed, p.point, 1, frame, (uint32_t)r >> 7);
+                        const uint32_t q4[4] = {w.x, w.y, w.z, w.w};
+                        b ^= q4[(r >> 5) & 3] >> (r & 31);
+                    }
+                cw[i * 32 + g] = (uint8_t)(b & 1u);
+            }
+            __syncthreads();
             const int nblk = (p.nct + 3) >> 2;
             for (int j = tid; j < nblk; j += nthreads)
             { // y = erasure w.p. eps else x (src/sim/channel.cpp:193-205)
@@ -82,11 +102,11 @@ namespace b200
                 for (int k = 0; k < 4; ++k)
                 {
                     const int t = 4 * j + k;
-                    if (t < p.nct) in[p.bit_pos[t] * 32 + g] = (w[k] < p.thr) ? BEC_E : (uint8_t)0;
+                    if (t < p.nct) in[p.bit_pos[t] * 32 + g] = (w[k] < p.thr) ? BEC_E : cw[p.bit_pos[t] * 32 + g];
                 }
             }
             for (int i = tid; i < p.n_punct; i += nthreads) in[p.punct[i] * 32 + g] = BEC_E; // channel.cpp:212-215
-            for (int i = tid; i < p.n_short; i += nthreads) in[p.shorten[i] * 32 + g] = 0;   // the (true) bit, channel.cpp:219-222
+            for (int i = tid; i < p.n_short; i += nthreads) in[p.shorten[i] * 32 + g] = cw[p.shorten[i] * 32 + g]; // the true bit, channel.cpp:219-222
         };
 
         auto retire_and_refill = [&](uint32_t mask, bool write_outputs)
@@ -215,6 +235,15 @@ namespace b200
                         atomicAdd(&s_cnt[3], (unsigned long long)ret);
                         atomicAdd(&s_cnt[4], (unsigned long long)it);
                         s_ret[f] = ret;
+                        if (e && p.err_log)
+                        {
+                            const unsigned long long slot = atomicAdd(p.err_count, 1ull);
+                            if (slot < p.err_cap)
+                            {
+                                p.err_log[2 * slot] = p.frame0 + s_frame[f];
+                                p.err_log[2 * slot + 1] = (unsigned long long)e | ((unsigned long long)(uint32_t)ret << 32);
+                            }
+                        }
                         fin = true;
                     }
                 }

@@ -431,4 +431,76 @@ namespace b200
         flatten(csegs, cn_max_segs, cn_seg);
         flatten(vsegs, vn_max_segs, vn_seg);
     }
+    // ------------------------------------------------------------------------------------------
+    // BecSliceLayout: bank-conflict-free message slots for the bit-sliced erasure kernel.
+    // The edges a warp touches in one shared-memory access are edge k of 32 consecutive checks (check phase) or of 32
+    // consecutive variables (variable phase).  Make those access groups the nodes of a bipartite multigraph (left: check
+    // groups, right: variable groups, one graph edge per code edge): every node has degree <= 32, so by Koenig's theorem the
+    // edges have a proper 32-colouring.  With slot % 32 = colour, no access of either phase hits a bank twice.
+    // ------------------------------------------------------------------------------------------
+    void BecSliceLayout::build(const HostCode &code)
+    {
+        const int C = 32;
+        const int md_c = std::max(code.max_cn_degree, 1), md_v = std::max(code.max_vn_degree, 1);
+        const int nl = ((code.mc + 31) / 32) * md_c, nr = ((code.nc + 31) / 32) * md_v;
+        std::vector<int> eu(code.nnz), ev(code.nnz); // graph endpoints of every code edge
+        for (int c = 0; c < code.mc; ++c)
+            for (int q = code.row_ptr[c]; q < code.row_ptr[c + 1]; ++q) eu[code.row_edge[q]] = (c / 32) * md_c + (q - code.row_ptr[c]);
+        for (int v = 0; v < code.nc; ++v)
+            for (int q = code.col_ptr[v]; q < code.col_ptr[v + 1]; ++q) ev[code.col_edge[q]] = (v / 32) * md_v + (q - code.col_ptr[v]);
+        std::vector<int> L((size_t)nl * C, -1), R((size_t)nr * C, -1), colour(code.nnz, -1), used(C, 0);
+        auto free_at = [&](const std::vector<int> &tab, int node) -> int
+        { // the free colour of `node` whose class is smallest so far (keeps the classes, hence the padding, balanced)
+            int best = -1;
+            for (int k = 0; k < C; ++k)
+                if (tab[(size_t)node * C + k] < 0 && (best < 0 || used[k] < used[best])) best = k;
+            if (best < 0) throw std::runtime_error("edge colouring: node of degree > 32");
+            return best;
+        };
+        std::vector<int> path;
+        for (int e = 0; e < code.nnz; ++e)
+        {
+            const int u = eu[e], v = ev[e];
+            const int a = free_at(L, u);
+            int b = -1;
+            if (R[(size_t)v * C + a] < 0) b = a;
+            else b = free_at(R, v);
+            if (a != b)
+            { // colour a is taken at v: flip a <-> b along the alternating path that starts at v (it cannot reach u: it enters
+              // left nodes through a-coloured edges and u has none)
+                path.clear();
+                int node = v, want = a;
+                bool right = true;
+                for (;;)
+                {
+                    const int f = right ? R[(size_t)node * C + want] : L[(size_t)node * C + want];
+                    if (f < 0) break;
+                    path.push_back(f);
+                    node = right ? eu[f] : ev[f];
+                    right = !right;
+                    want = (want == a) ? b : a;
+                }
+                for (int f : path) { L[(size_t)eu[f] * C + colour[f]] = -1; R[(size_t)ev[f] * C + colour[f]] = -1; }
+                for (int f : path)
+                {
+                    const int nc2 = (colour[f] == a) ? b : a;
+                    --used[colour[f]]; ++used[nc2];
+                    colour[f] = nc2;
+                    L[(size_t)eu[f] * C + nc2] = f; R[(size_t)ev[f] * C + nc2] = f;
+                }
+            }
+            colour[e] = a;
+            ++used[a];
+            L[(size_t)u * C + a] = e;
+            R[(size_t)v * C + a] = e;
+        }
+        std::vector<int> next(C, 0), slot(code.nnz);
+        for (int e = 0; e < code.nnz; ++e) slot[e] = C * next[colour[e]]++ + colour[e];
+        n_slots = C * *std::max_element(next.begin(), next.end());
+        if (n_slots > 65535) throw std::runtime_error("code too large for the bit-sliced erasure kernel");
+        edge_slot = slot;
+        row_slot.resize(code.nnz);
+        col_slot.resize(code.nnz);
+        for (int q = 0; q < code.nnz; ++q) { row_slot[q] = (uint16_t)slot[code.row_edge[q]]; col_slot[q] = (uint16_t)slot[code.col_edge[q]]; }
+    }
 } // namespace b200

@@ -106,4 +106,14 @@ namespace b200
         }
         void build(const HostCode &code, int lanes, int threads, int isz);
     };
+
+    // Message slots of the bit-sliced erasure kernel (bec_slice.cuh): a proper 32-colouring of the code's edges seen as
+    // the edges of the bipartite multigraph of warp access groups, slot % 32 = colour (code.cpp).
+    struct BecSliceLayout
+    {
+        int n_slots = 0;                       // 32 * size of the largest colour class
+        std::vector<uint16_t> row_slot, col_slot; // slots in the order of HostCode::row_edge / col_edge
+        std::vector<int> edge_slot;            // [nnz] file-order edge -> slot
+        void build(const HostCode &code);
+    };
 } // namespace b200

@@ -77,12 +77,14 @@ namespace b200
             return b + 16;
         }
 
-        size_t seg_smem_bytes(const SegLayout &l)
+        // pos_entries: transmitted (padded to a multiple of 4) + punctured + shortened positions, kept as uint16 beside the tables
+        size_t seg_smem_bytes(const SegLayout &l, size_t pos_entries)
         {
             const size_t rs = 16 * (size_t)l.lanes;
             size_t b = rs * ((size_t)l.n_slots + 2 * (size_t)l.n_pos);
             b += 16 * ((size_t)l.cn_max_segs + l.vn_max_segs) * l.warps;
             b += l.cn_idx.size() + l.vn_idx.size(); // both multiples of 16
+            b += (2 * pos_entries + 15) & ~(size_t)15;
             return b + 16;
         }
 
@@ -120,10 +122,10 @@ namespace b200
         cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
         if (ev_state_) cudaEventDestroy((cudaEvent_t)ev_state_);
         cudaFree(d_g_col_ptr_); cudaFree(d_g_row_);
-        cudaFree(d_bs_row_ptr_); cudaFree(d_bs_row_edge_); cudaFree(d_bs_col_ptr_); cudaFree(d_bs_col_edge_); cudaFree(d_bs_tx_flag_);
+        cudaFree(d_bs_row_ptr_); cudaFree(d_bs_row_slot_); cudaFree(d_bs_col_ptr_); cudaFree(d_bs_col_slot_); cudaFree(d_bs_tx_flag_);
         for (int b = 0; b < 2; ++b)
         {
-            cudaFree(db_in_[b]); cudaFree(db_out_[b]); cudaFree(db_hard_[b]); cudaFree(db_it_[b]);
+            cudaFree(db_in_[b]); cudaFree(db_out_[b]); cudaFree(db_hard_[b]); cudaFree(db_it_[b]); cudaFree(db_bits_[b]);
             if (ev_in_[b]) cudaEventDestroy((cudaEvent_t)ev_in_[b]);
             if (ev_k_[b]) cudaEventDestroy((cudaEvent_t)ev_k_[b]);
             if (ev_out_[b]) cudaEventDestroy((cudaEvent_t)ev_out_[b]);
@@ -222,9 +224,12 @@ namespace b200
             if (want_lanes != 1 && want_lanes != 2 && want_lanes != 4)
                 throw std::runtime_error("frames_per_cta / vector width must be 1, 2 or 4");
         }
-        const size_t limit = std::min<size_t>(smem_optin_ > 1024 ? smem_optin_ - 1024 : 0, (size_t)TILE_SMEM_OPTIN);
+        const size_t limit = std::min<size_t>(smem_optin_ > 2048 ? smem_optin_ - 2048 : 0, (size_t)TILE_SMEM_OPTIN);
         // information words of the frames in flight (random codewords through the generator matrix), 16-byte rounded
         auto u_bytes = [&](int lanes) -> size_t { return has_gen ? (((size_t)4 * lanes * vec * ((G.mc + 31) / 32)) + 15) & ~(size_t)15 : 0; };
+        size_t pos_entries = ((size_t)H.nct() + 3) & ~(size_t)3;
+        for (int v : H.puncture) if (v >= 0 && v < H.nc) ++pos_entries;
+        for (int v : H.shorten) if (v >= 0 && v < H.nc) ++pos_entries;
         if (tuning.residency != LDPC_B200_GLOBAL)
         {
             // 16-bit entries (record offset / 16) need every record offset of the layout below 2^16
@@ -235,7 +240,7 @@ namespace b200
                 bool i16 = tuning.idx16 == 2 && tuning.tmem == 0 && fits16(lanes);
                 if (i16 && !try_seg_layout(lanes, threads, 2)) i16 = false; // many distinct degrees: the padded layout can still exceed 16 bits
                 const SegLayout &l = get_seg_layout(lanes, threads, i16 ? 2 : 4);
-                const size_t need = seg_smem_bytes(l) + u_bytes(lanes);
+                const size_t need = seg_smem_bytes(l, pos_entries) + u_bytes(lanes);
                 if (need <= limit)
                 {
                     // Nothing pinned by the caller and the widest tile that fits is two lanes: the same frames as TWO
@@ -253,7 +258,7 @@ namespace b200
                         tuning.ctas <= 0 && fits16(1) && try_seg_layout(1, max_threads / 2, 2))
                     {
                         const SegLayout &l1 = get_seg_layout(1, max_threads / 2, 2);
-                        const size_t need1 = seg_smem_bytes(l1) + u_bytes(1);
+                        const size_t need1 = seg_smem_bytes(l1, pos_entries) + u_bytes(1);
                         if (2 * (need1 + 2048) <= smem_per_sm_)
                         {
                             *residency = LDPC_B200_SMEM;
@@ -399,6 +404,7 @@ namespace b200
         d->vn_idx = upload(l.vn_idx);
         std::vector<int32_t> tx, pu, sh;
         for (int v : H.bit_pos) tx.push_back((int32_t)l.var_pos[v]);
+        while (tx.size() % 4) tx.push_back(0); // the kernel fetches the positions of a Philox block (4 transmitted indices) with one 16-byte load
         for (int v : H.puncture) if (v >= 0 && v < H.nc) pu.push_back((int32_t)l.var_pos[v]);
         for (int v : H.shorten) if (v >= 0 && v < H.nc) sh.push_back((int32_t)l.var_pos[v]);
         d->tx_pos = upload(tx);
@@ -569,11 +575,12 @@ namespace b200
         kp.max_iter = (int)dp.iterations;
         kp.early_term = dp.earlyTerm ? 1 : 0;
         kp.kind = src.kind;
-        kp.llr_in = src.d_llr;
+        kp.llr_in = src.d_llr; kp.llr_in_f32 = src.d_llr_f32; kp.llr_in_i8 = src.d_llr_i8; kp.i8_scale = src.i8_scale;
         if (src.kind == SRC_AWGN)
         {
             kp.sigma2 = std::pow(10.0, -src.x / 10.0); // src/sim/channel.cpp:39-40
             kp.sigma = std::sqrt(kp.sigma2);
+            kp.llr_scale = 2.0 / kp.sigma2;
         }
         else if (src.kind == SRC_BSC)
         {
@@ -583,6 +590,7 @@ namespace b200
         }
         kp.seed = src.seed; kp.point = src.point; kp.frame0 = src.frame0; kp.n_frames = n_frames;
         kp.llr_out = sink.d_llr_out; kp.hard_out = sink.d_hard; kp.iters_out = sink.d_iters;
+        kp.hard_bits = sink.d_hard_bits; kp.hard_words = sink.hard_words;
         kp.counters = sink.d_counters ? sink.d_counters : d_counters_;
         kp.err_log = sink.d_err_log; kp.err_count = sink.d_err_count; kp.err_cap = sink.err_cap;
         if (c.residency == LDPC_B200_GLOBAL)
@@ -770,28 +778,46 @@ namespace b200
     void Engine::launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream)
     {
         cudaStream_t s = (cudaStream_t)stream;
-        // Sweep mode (frames generated on the device, only the counters leave it): the bit-sliced kernel, 32 frames per
-        // word, when one word's state (a bit per edge and per variable) fits shared memory; the byte-wise kernel below
-        // serves caller-supplied frames (decode API: per-frame outputs) and larger codes.
-        const size_t slice_group_bytes = 4 * ((size_t)H.nnz + H.nc + 8);
+        // Sweep mode (frames generated on the device, only the counters and the error log leave it): the bit-sliced kernel, 32
+        // frames per word, when one word's state (bit-planes per edge and per variable) fits shared memory; the byte-wise
+        // kernel below serves caller-supplied frames (decode API: per-frame outputs) and larger codes.
+        const bool use_gen = has_gen && !tuning.zero_codeword && !src.d_bec_in; // random codewords u*G (src/sim/channel.cpp:177-191)
+        const bool logging = sink.d_err_log != nullptr;
+        const bool slice_mode = !src.d_bec_in && !sink.d_bec_out && !sink.d_hard && !sink.d_iters && H.min_cn_degree >= 2 && H.max_cn_degree <= 32 &&
+                                H.max_vn_degree <= 32 * 64 && tuning.residency != LDPC_B200_GLOBAL;
         const size_t slice_limit = smem_optin_ > 2048 ? smem_optin_ - 2048 : 0;
-        if (!src.d_bec_in && !sink.d_bec_out && !sink.d_hard && !sink.d_iters && H.min_cn_degree >= 2 && slice_group_bytes <= slice_limit &&
-            tuning.residency != LDPC_B200_GLOBAL)
+        if (slice_mode)
+        {
+            if (!bs_layout_)
+            {
+                bs_layout_ = std::make_unique<BecSliceLayout>();
+                try { bs_layout_->build(H); }
+                catch (const std::exception &) { bs_layout_->n_slots = 0; } // too large / too dense: the byte-wise kernel serves it
+            }
+        }
+        const bool gen_variant = use_gen || logging;
+        const size_t n_slots = bs_layout_ ? (size_t)bs_layout_->n_slots : 0;
+        const size_t group_words = gen_variant ? 2 * n_slots + 3 * (size_t)H.nc + 40 : n_slots + (size_t)H.nc + 8;
+        const size_t slice_group_bytes = 4 * group_words;
+        // the information words of a 32-frame group are transposed in the (not yet used) message area
+        const bool scratch_ok = !use_gen || (size_t)(32 * 4 * ((G.mc + 127) / 128) + G.mc) <= n_slots;
+        if (slice_mode && n_slots > 0 && slice_group_bytes <= slice_limit && scratch_ok)
         {
             if (!d_bs_row_ptr_)
             {
-                std::vector<int32_t> rp(H.row_ptr.begin(), H.row_ptr.end()), re(H.row_edge.begin(), H.row_edge.end());
-                std::vector<int32_t> cp(H.col_ptr.begin(), H.col_ptr.end()), ce(H.col_edge.begin(), H.col_edge.end());
+                std::vector<int32_t> rp(H.row_ptr.begin(), H.row_ptr.end()), cp(H.col_ptr.begin(), H.col_ptr.end());
                 std::vector<uint8_t> tf(H.nc, 0);
                 for (int v : H.bit_pos) tf[v] = 1;
-                d_bs_row_ptr_ = upload(rp); d_bs_row_edge_ = upload(re); d_bs_col_ptr_ = upload(cp); d_bs_col_edge_ = upload(ce);
+                d_bs_row_ptr_ = upload(rp); d_bs_col_ptr_ = upload(cp);
+                d_bs_row_slot_ = upload(bs_layout_->row_slot); d_bs_col_slot_ = upload(bs_layout_->col_slot);
                 d_bs_tx_flag_ = upload(tf);
-                CUDA_OK(cudaFuncSetAttribute(bec_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_limit));
+                CUDA_OK(cudaFuncSetAttribute(bec_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_limit));
+                CUDA_OK(cudaFuncSetAttribute(bec_slice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_limit));
             }
             BecSliceParams bp{};
-            bp.row_ptr = d_bs_row_ptr_; bp.row_edge = d_bs_row_edge_; bp.col_ptr = d_bs_col_ptr_; bp.col_edge = d_bs_col_edge_;
+            bp.row_ptr = d_bs_row_ptr_; bp.row_slot = d_bs_row_slot_; bp.col_ptr = d_bs_col_ptr_; bp.col_slot = d_bs_col_slot_;
             bp.tx_var = d_bit_pos_; bp.punct = d_punct_; bp.shorten = d_short_; bp.tx_flag = d_bs_tx_flag_;
-            bp.nc = H.nc; bp.mc = H.mc; bp.nnz = H.nnz; bp.nct = H.nct();
+            bp.nc = H.nc; bp.mc = H.mc; bp.nnz = H.nnz; bp.nct = H.nct(); bp.n_slots = (int)n_slots;
             bp.n_punct = (int)H.puncture.size(); bp.n_short = (int)H.shorten.size();
             bp.max_iter = (int)dp.iterations; bp.early_term = dp.earlyTerm ? 1 : 0; bp.deg1_compat = tuning.bec_deg1_compat;
             {
@@ -800,14 +826,18 @@ namespace b200
             }
             bp.seed = src.seed; bp.point = src.point; bp.frame0 = src.frame0; bp.n_frames = n_frames;
             bp.counters = sink.d_counters ? sink.d_counters : d_counters_;
+            if (use_gen) { bp.g_col_ptr = d_g_col_ptr_; bp.g_row = d_g_row_; bp.g_rows = G.mc; bp.g_cols = G.nc; }
+            bp.err_log = sink.d_err_log; bp.err_count = sink.d_err_count; bp.err_cap = sink.err_cap;
             const uint64_t n_words = (n_frames + 31) / 32;
             int groups = (int)std::min<size_t>(8, slice_limit / slice_group_bytes);
             groups = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)groups, n_words));
             bp.groups_per_cta = groups;
+            bp.group_words = (int)group_words;
             int ctas = tuning.ctas > 0 ? tuning.ctas : sm_count_;
             const uint64_t need = (n_words + groups - 1) / groups;
             if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
-            bec_slice_kernel<<<ctas, groups * BEC_TPG, groups * slice_group_bytes, s>>>(bp);
+            if (gen_variant) bec_slice_kernel<true><<<ctas, groups * BEC_TPG, groups * slice_group_bytes, s>>>(bp);
+            else bec_slice_kernel<false><<<ctas, groups * BEC_TPG, groups * slice_group_bytes, s>>>(bp);
             CUDA_OK(cudaGetLastError());
             stats.launches += 1;
             stats.frames_per_cta = 32 * groups; stats.threads_per_cta = groups * BEC_TPG; stats.ctas = ctas;
@@ -833,6 +863,8 @@ namespace b200
         bp.seed = src.seed; bp.point = src.point; bp.frame0 = src.frame0; bp.n_frames = n_frames;
         bp.out = sink.d_bec_out; bp.hard = sink.d_hard; bp.iters_out = sink.d_iters;
         bp.counters = sink.d_counters ? sink.d_counters : d_counters_;
+        if (use_gen) { bp.g_col_ptr = d_g_col_ptr_; bp.g_row = d_g_row_; bp.g_rows = G.mc; bp.g_cols = G.nc; }
+        bp.err_log = sink.d_err_log; bp.err_count = sink.d_err_count; bp.err_cap = sink.err_cap;
         int ctas = tuning.ctas > 0 ? tuning.ctas : sm_count_;
         const uint64_t need = (n_frames + 31) / 32;
         if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
@@ -897,7 +929,6 @@ namespace b200
                                uint64_t n_frames, uint64_t counters[5], ldpc_b200_error_record *records, int64_t capacity, int64_t *n_errors)
     {
         const int kind = channel_kind(channel);
-        if (kind == SRC_BEC) throw std::runtime_error("the per-error log covers the AWGN and BSC sweeps");
         if (capacity < 0 || (capacity > 0 && !records)) throw std::runtime_error("bad error-log buffer");
         ensure_cuda();
         cudaStream_t s = (cudaStream_t)stream_;
@@ -945,15 +976,19 @@ namespace b200
     // kernel of chunk k and D2H of chunk k-1 overlap (kernels stay on ONE stream, so the per-CTA state block of
     // global residency is never shared by two launches).  Device buffers are cached in the engine.  With pinned
     // caller buffers the copies run at full PCIe rate; pageable buffers work too (the driver stages them).
-    void Engine::decode_batch_host(const decoder_param &dp, const double *llr, int64_t n, double *llr_out, uint8_t *hard, int32_t *iters)
+    void Engine::decode_batch_host(const decoder_param &dp, const void *llr, int llr_type, double llr_scale, int64_t n, double *llr_out, uint8_t *hard,
+                                   uint32_t *hard_bits, int32_t *iters)
     {
         if (n <= 0) return;
+        if (llr_type != LDPC_B200_LLR_F64 && llr_type != LDPC_B200_LLR_F32 && llr_type != LDPC_B200_LLR_I8) throw std::runtime_error("bad llr_type");
         ensure_cuda();
         cudaStream_t sk = (cudaStream_t)stream_;
         const size_t nc = H.nc;
+        const size_t esz = llr_type == LDPC_B200_LLR_F64 ? 8 : llr_type == LDPC_B200_LLR_F32 ? 4 : 1; // bytes per input LLR
+        const size_t hw = (nc + 31) / 32;                                                              // words per frame of packed decisions
         // chunk = whole waves of the persistent grid (CTAs x frames per CTA), about 32 MB of input: no partly filled last wave
         // per launch, and a short pipeline fill
-        int64_t chunk = std::max<int64_t>((int64_t)((32ull << 20) / (nc * sizeof(double))), 1), wave = 1;
+        int64_t chunk = std::max<int64_t>((int64_t)((32ull << 20) / (nc * esz)), 1), wave = 1;
         {
             const bool minsum = dp.type && std::string(dp.type) == "BP_MS";
             maybe_autotune(minsum ? ALG_MS : ALG_BP, dp, (uint64_t)n, sk);
@@ -1018,9 +1053,10 @@ namespace b200
         };
         for (int b = 0; b < 2; ++b)
         {
-            grow(db_in_[b], db_in_cap_[b], (size_t)chunk * nc * sizeof(double));
+            grow(db_in_[b], db_in_cap_[b], (size_t)chunk * nc * esz);
             if (llr_out) grow(db_out_[b], db_out_cap_[b], (size_t)chunk * nc * sizeof(double));
             if (hard) grow(db_hard_[b], db_hard_cap_[b], (size_t)chunk * nc);
+            if (hard_bits) grow(db_bits_[b], db_bits_cap_[b], (size_t)chunk * hw * sizeof(uint32_t));
             if (iters) grow(db_it_[b], db_it_cap_[b], (size_t)chunk * sizeof(int32_t));
         }
         unsigned long long h[5] = {0, 0, 0, 0, 0};
@@ -1034,22 +1070,27 @@ namespace b200
             const int b = (int)(k & 1);
             const int64_t m = pieces[pi];
             if (k >= 2) CUDA_OK(cudaStreamWaitEvent(si, (cudaEvent_t)ev_k_[b], 0)); // the kernel that read this input buffer is done
-            CUDA_OK(cudaMemcpyAsync(db_in_[b], llr + o * nc, m * nc * sizeof(double), cudaMemcpyHostToDevice, si));
+            CUDA_OK(cudaMemcpyAsync(db_in_[b], (const unsigned char *)llr + (size_t)o * nc * esz, (size_t)m * nc * esz, cudaMemcpyHostToDevice, si));
             CUDA_OK(cudaEventRecord((cudaEvent_t)ev_in_[b], si));
             CUDA_OK(cudaStreamWaitEvent(sk, (cudaEvent_t)ev_in_[b], 0));
             if (k >= 2) CUDA_OK(cudaStreamWaitEvent(sk, (cudaEvent_t)ev_out_[b], 0)); // the copy-out of this output buffer is done
             FrameSource src;
             src.kind = SRC_LLR;
-            src.d_llr = (const double *)db_in_[b];
+            if (llr_type == LDPC_B200_LLR_F64) src.d_llr = (const double *)db_in_[b];
+            else if (llr_type == LDPC_B200_LLR_F32) src.d_llr_f32 = (const float *)db_in_[b];
+            else { src.d_llr_i8 = (const int8_t *)db_in_[b]; src.i8_scale = llr_scale; }
             FrameSink sink;
             sink.d_llr_out = llr_out ? (double *)db_out_[b] : nullptr;
             sink.d_hard = hard ? (uint8_t *)db_hard_[b] : nullptr;
+            sink.d_hard_bits = hard_bits ? (uint32_t *)db_bits_[b] : nullptr;
+            sink.hard_words = (int)hw;
             sink.d_iters = iters ? (int32_t *)db_it_[b] : nullptr;
             launch(dp, src, sink, (uint64_t)m, sk);
             CUDA_OK(cudaEventRecord((cudaEvent_t)ev_k_[b], sk));
             CUDA_OK(cudaStreamWaitEvent(so, (cudaEvent_t)ev_k_[b], 0));
             if (llr_out) CUDA_OK(cudaMemcpyAsync(llr_out + o * nc, db_out_[b], m * nc * sizeof(double), cudaMemcpyDeviceToHost, so));
             if (hard) CUDA_OK(cudaMemcpyAsync(hard + o * nc, db_hard_[b], m * nc, cudaMemcpyDeviceToHost, so));
+            if (hard_bits) CUDA_OK(cudaMemcpyAsync(hard_bits + o * hw, db_bits_[b], m * hw * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
             if (iters) CUDA_OK(cudaMemcpyAsync(iters + o, db_it_[b], m * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
             CUDA_OK(cudaEventRecord((cudaEvent_t)ev_out_[b], so));
         }
@@ -1109,12 +1150,12 @@ namespace b200
 
     // Stand-alone channel kernel: the same generator code as the fused path, one thread per Philox block.
     __global__ void channel_kernel(int kind, int nc, int nct, const int32_t *__restrict__ bit_pos, const int32_t *__restrict__ punct, int n_punct,
-                                   const int32_t *__restrict__ shorten, int n_short, double sigma, double sigma2, double delta, uint32_t thr,
+                                   const int32_t *__restrict__ shorten, int n_short, double sigma, double llr_scale, double delta, uint32_t thr,
                                    uint64_t seed, uint32_t point, uint64_t frame0, int64_t n_frames, uint8_t *cw, double *llr, uint8_t *llr_u8,
                                    const int32_t *__restrict__ g_col_ptr, const int32_t *__restrict__ g_row, int g_rows, int g_cols)
     {
         // codeword bit of variable v in frame fr: parity of the Philox stream-1 information bits selected by column v of G
-        // (same rule as the fused kernel, tile4.cuh cw_bit); 0 without a generator matrix.  Used by AWGN / BSC only.
+        // (same rule as the fused kernels); 0 without a generator matrix.
         auto cw_bit = [&](int64_t fr, int v) -> uint32_t
         {
             if (g_rows <= 0 || v >= g_cols) return 0u;
@@ -1128,8 +1169,7 @@ namespace b200
             }
             return b & 1u;
         };
-        const int per = (kind == SRC_AWGN) ? 2 : 4;
-        const int nblk = (nct + per - 1) / per;
+        const int nblk = (nct + 3) / 4; // one Philox block serves four transmitted indices on every channel
         const int64_t total = n_frames * (int64_t)nblk;
         for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x)
         {
@@ -1138,23 +1178,18 @@ namespace b200
             const u32x4 r = channel_block(seed, point, 0, frame0 + fr, (uint32_t)j);
             const size_t base = (size_t)fr * nc;
             if (kind == SRC_AWGN)
-            {
-                const double u1 = ((double)((((uint64_t)r.y << 32) | r.x) >> 11) + 1.0) * 0x1p-53;
-                const double u2 = (double)((((uint64_t)r.w << 32) | r.z) >> 11) * 0x1p-53;
-                const double rad = sqrt(-2.0 * log(u1));
-                double sn, cs;
-                sincos(6.283185307179586 * u2, &sn, &cs);
-                const int t = 2 * j;
-                const uint32_t b0 = cw_bit(fr, bit_pos[t]);
-                const double y0 = __dadd_rn(__dmul_rn(rad * cs, sigma), b0 ? -1.0 : 1.0);
-                llr[base + bit_pos[t]] = __dmul_rn(2.0, y0) / sigma2;
-                if (cw) cw[base + bit_pos[t]] = (uint8_t)b0;
-                if (t + 1 < nct)
+            { // the same arithmetic as the fused path (tile4.cuh frame_pass)
+                float z[4];
+                normal_pair(r.x, r.y, z[0], z[1]);
+                normal_pair(r.z, r.w, z[2], z[3]);
+                for (int q = 0; q < 4; ++q)
                 {
-                    const uint32_t b1 = cw_bit(fr, bit_pos[t + 1]);
-                    const double y1 = __dadd_rn(__dmul_rn(rad * sn, sigma), b1 ? -1.0 : 1.0);
-                    llr[base + bit_pos[t + 1]] = __dmul_rn(2.0, y1) / sigma2;
-                    if (cw) cw[base + bit_pos[t + 1]] = (uint8_t)b1;
+                    const int t = 4 * j + q;
+                    if (t >= nct) break;
+                    const uint32_t b = cw_bit(fr, bit_pos[t]);
+                    const double y = __dadd_rn(__dmul_rn((double)z[q], sigma), b ? -1.0 : 1.0);
+                    llr[base + bit_pos[t]] = __dmul_rn(y, llr_scale);
+                    if (cw) cw[base + bit_pos[t]] = (uint8_t)b;
                 }
             }
             else
@@ -1172,9 +1207,10 @@ namespace b200
                         if (cw) cw[base + bit_pos[t]] = (uint8_t)b;
                     }
                     else
-                    {
-                        llr_u8[base + bit_pos[t]] = hit ? (uint8_t)'E' : (uint8_t)0;
-                        if (cw) cw[base + bit_pos[t]] = 0;
+                    { // y = 'E' w.p. eps else x (src/sim/channel.cpp:193-205)
+                        const uint32_t b = cw_bit(fr, bit_pos[t]);
+                        llr_u8[base + bit_pos[t]] = hit ? (uint8_t)'E' : (uint8_t)b;
+                        if (cw) cw[base + bit_pos[t]] = (uint8_t)b;
                     }
                 }
             }
@@ -1187,13 +1223,13 @@ namespace b200
                 }
                 for (int i = 0; i < n_short; ++i)
                 {
-                    if (kind == SRC_BEC) llr_u8[base + shorten[i]] = 0;
+                    if (kind == SRC_BEC) llr_u8[base + shorten[i]] = (uint8_t)cw_bit(fr, shorten[i]); // the true bit (channel.cpp:219-222)
                     else llr[base + shorten[i]] = (kind == SRC_AWGN) ? 99999.9 : delta;
                 }
                 if (cw)
-                { // non-transmitted positions carry their codeword bit too (all-zero for the erasure channel)
-                    for (int i = 0; i < n_punct; ++i) cw[base + punct[i]] = (kind == SRC_BEC) ? 0 : (uint8_t)cw_bit(fr, punct[i]);
-                    for (int i = 0; i < n_short; ++i) cw[base + shorten[i]] = (kind == SRC_BEC) ? 0 : (uint8_t)cw_bit(fr, shorten[i]);
+                { // non-transmitted positions carry their codeword bit too
+                    for (int i = 0; i < n_punct; ++i) cw[base + punct[i]] = (uint8_t)cw_bit(fr, punct[i]);
+                    for (int i = 0; i < n_short; ++i) cw[base + shorten[i]] = (uint8_t)cw_bit(fr, shorten[i]);
                 }
             }
         }
@@ -1222,7 +1258,7 @@ namespace b200
             thr = t <= 0 ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
         }
         channel_kernel<<<sm_count_ * 4, 256, 0, s>>>(kind, (int)nc, H.nct(), d_bit_pos_, d_punct_, (int)H.puncture.size(), d_short_,
-                                                     (int)H.shorten.size(), sigma, sigma2, delta, thr, seed, point, frame0, n, d_cw, d_llr, d_u8,
+                                                     (int)H.shorten.size(), sigma, 2.0 / sigma2, delta, thr, seed, point, frame0, n, d_cw, d_llr, d_u8,
                                                      d_g_col_ptr_, d_g_row_, (has_gen && !tuning.zero_codeword) ? G.mc : 0, has_gen ? G.nc : 0);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess && d_llr) e = cudaMemcpyAsync(llr, d_llr, n * nc * sizeof(double), cudaMemcpyDeviceToHost, s);

@@ -20,7 +20,10 @@ namespace b200
     struct FrameSource
     {
         int kind = 0;                // SRC_* of kernels.cuh
-        const double *d_llr = nullptr; // SRC_LLR: device [n][nc]
+        const double *d_llr = nullptr; // SRC_LLR: device [n][nc] ...
+        const float *d_llr_f32 = nullptr;  // ... or the same frames as binary32
+        const int8_t *d_llr_i8 = nullptr;  // ... or as quantised int8 (LLR = value * i8_scale)
+        double i8_scale = 1.0;
         const uint8_t *d_bec_in = nullptr, *d_bec_cw = nullptr; // BEC decode mode
         double x = 0;                // channel parameter (snr dB or epsilon)
         uint64_t seed = 0;
@@ -32,6 +35,8 @@ namespace b200
     {
         double *d_llr_out = nullptr;
         uint8_t *d_hard = nullptr;
+        uint32_t *d_hard_bits = nullptr; // bit-packed decisions, hard_words 32-bit words per frame
+        int hard_words = 0;
         uint8_t *d_bec_out = nullptr;
         int32_t *d_iters = nullptr;
         unsigned long long *d_counters = nullptr; // [5]; null -> engine scratch
@@ -61,7 +66,9 @@ namespace b200
         void prepare(const decoder_param &dp, uint64_t n_frames);
 
         // Blocking helpers used by the C ABI
-        void decode_batch_host(const decoder_param &dp, const double *llr, int64_t n, double *llr_out, uint8_t *hard, int32_t *iters);
+        // llr_type: LDPC_B200_LLR_F64 / _F32 / _I8 (element type of `llr`); hard_bits: bit-packed decisions, ceil(nc/32) words per frame
+        void decode_batch_host(const decoder_param &dp, const void *llr, int llr_type, double llr_scale, int64_t n, double *llr_out, uint8_t *hard,
+                               uint32_t *hard_bits, int32_t *iters);
         void decode_bec_host(const decoder_param &dp, const uint8_t *in, const uint8_t *cw, int64_t n, uint8_t *out, uint8_t *hard, int32_t *iters);
         void channel_host(const std::string &channel, double x, uint64_t seed, uint32_t point, uint64_t frame0, int64_t n,
                           uint8_t *cw, double *llr, uint8_t *llr_u8);
@@ -119,7 +126,9 @@ namespace b200
         int force_wide_ = -1; // autotune trials: -1 = use tuned_/default, 0/1 = force
         int32_t *d_bit_pos_ = nullptr, *d_punct_ = nullptr, *d_short_ = nullptr;
         int32_t *d_g_col_ptr_ = nullptr, *d_g_row_ = nullptr; // generator matrix by column (device)
-        int32_t *d_bs_row_ptr_ = nullptr, *d_bs_row_edge_ = nullptr, *d_bs_col_ptr_ = nullptr, *d_bs_col_edge_ = nullptr; // bit-sliced BEC kernel
+        int32_t *d_bs_row_ptr_ = nullptr, *d_bs_col_ptr_ = nullptr; // bit-sliced BEC kernel
+        uint16_t *d_bs_row_slot_ = nullptr, *d_bs_col_slot_ = nullptr;
+        std::unique_ptr<BecSliceLayout> bs_layout_;
         uint8_t *d_bs_tx_flag_ = nullptr;
         unsigned long long *d_counters_ = nullptr;
         unsigned char *d_state_ = nullptr;
@@ -130,7 +139,8 @@ namespace b200
         void *copy_in_ = nullptr, *copy_out_ = nullptr;
         void *ev_in_[2] = {nullptr, nullptr}, *ev_k_[2] = {nullptr, nullptr}, *ev_out_[2] = {nullptr, nullptr};
         void *db_in_[2] = {nullptr, nullptr}, *db_out_[2] = {nullptr, nullptr}, *db_hard_[2] = {nullptr, nullptr}, *db_it_[2] = {nullptr, nullptr};
-        size_t db_in_cap_[2] = {0, 0}, db_out_cap_[2] = {0, 0}, db_hard_cap_[2] = {0, 0}, db_it_cap_[2] = {0, 0};
+        void *db_bits_[2] = {nullptr, nullptr};
+        size_t db_in_cap_[2] = {0, 0}, db_out_cap_[2] = {0, 0}, db_hard_cap_[2] = {0, 0}, db_it_cap_[2] = {0, 0}, db_bits_cap_[2] = {0, 0};
     };
 
     // reference-semantics sweep driver (sim_driver.cpp)

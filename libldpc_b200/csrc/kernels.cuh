@@ -38,6 +38,51 @@ namespace b200
         return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     }
 
+    // Standard-normal pair of the channel specification (oracle/ldpc_oracle.c normal_pair_v2 is the same arithmetic, bit for
+    // bit): Box-Muller in binary32 with correctly rounded operations only (+, *, fma, 1/x, sqrt; explicit intrinsics so that
+    // nothing is contracted or reordered).  wr: 32 radius bits; wa: bits 7..0 extend the radius uniform to 40 bits (tails to
+    // 7.4 sigma), bits 31..8 are the angle (octant + 21-bit fraction).  ~60 instructions per pair, no library call, no fp64.
+    __device__ __forceinline__ void normal_pair(uint32_t wr, uint32_t wa, float &z0, float &z1)
+    {
+        const unsigned long long T = ((((unsigned long long)wr << 8) | (unsigned long long)(wa & 0xFFu)) << 1) | 1ull; // 2U+1 < 2^41
+        const uint32_t tb = __float_as_uint(__ull2float_rz(T)); // truncation: exponent 40 - lz, top 24 bits
+        float f = __uint_as_float((tb & 0x7FFFFFu) | 0x3F800000u);
+        int e = 168 - (int)(tb >> 23); // 41 - (exponent - 127): u1 ~ f 2^-e
+        const bool big = f > 1.41421354f;
+        f = big ? __fmul_rn(f, 0.5f) : f;
+        e = big ? e - 1 : e;
+        const float g = __fadd_rn(f, -1.0f);
+        const float s = __fmul_rn(g, __frcp_rn(__fadd_rn(2.0f, g)));
+        const float s2 = __fmul_rn(s, s);
+        float q = 0x1.c71c72p-4f;
+        q = __fmaf_rn(q, s2, 0x1.24924ap-3f);
+        q = __fmaf_rn(q, s2, 0x1.99999ap-3f);
+        q = __fmaf_rn(q, s2, 0x1.555556p-2f);
+        q = __fmaf_rn(q, s2, 1.0f);
+        const float lnf = __fmul_rn(__fmul_rn(2.0f, s), q);
+        const float n = __fmaf_rn((float)e, 0x1.62e430p-1f, -lnf);
+        const float r = __fsqrt_rn(__fmul_rn(2.0f, n));
+        const uint32_t a = wa >> 8, oct = a >> 21;
+        const float phi = __fmul_rn(__fadd_rn((float)(a & 0x1FFFFFu), 0.5f), 0x1.921fb6p-22f);
+        const float x2 = __fmul_rn(phi, phi);
+        float sp = 0x1.71de3ap-19f;
+        sp = __fmaf_rn(sp, x2, -0x1.a01a02p-13f);
+        sp = __fmaf_rn(sp, x2, 0x1.111112p-7f);
+        sp = __fmaf_rn(sp, x2, -0x1.555556p-3f);
+        const float sn0 = __fmaf_rn(__fmul_rn(phi, x2), sp, phi);
+        float cp = -0x1.27e4fcp-22f;
+        cp = __fmaf_rn(cp, x2, 0x1.a01a02p-16f);
+        cp = __fmaf_rn(cp, x2, -0x1.6c16c2p-10f);
+        cp = __fmaf_rn(cp, x2, 0x1.555556p-5f);
+        cp = __fmaf_rn(cp, x2, -0.5f);
+        const float cs0 = __fmaf_rn(cp, x2, 1.0f);
+        float c = (oct & 1u) ? sn0 : cs0, sn = (oct & 1u) ? cs0 : sn0;
+        if (oct & 2u) { const float t = c; c = -sn; sn = t; }
+        if (oct & 4u) { c = -c; sn = -sn; }
+        z0 = __fmul_rn(r, c);
+        z1 = __fmul_rn(r, sn);
+    }
+
     enum { SRC_LLR = 0, SRC_AWGN = 1, SRC_BSC = 2, SRC_BEC = 3 };
     enum { ALG_MS = 0, ALG_BP = 1 };
     constexpr uint32_t IDLE = 0xFFFFFFFFu;

@@ -138,7 +138,7 @@ extern "C"
                 for (int i = 0; i < nct; ++i) llrOut[i] = 0.0;
                 return 0;
             }
-            eng.decode_batch_host(decoderParams, in.data(), 1, out.data(), nullptr, &iters);
+            eng.decode_batch_host(decoderParams, in.data(), LDPC_B200_LLR_F64, 1.0, 1, out.data(), nullptr, nullptr, &iters);
             for (int i = 0; i < nct; ++i) llrOut[i] = out[eng.H.bit_pos[i]];
             return iters;
         }
@@ -259,6 +259,17 @@ extern "C"
         });
     }
 
+    int ldpc_b200_get_bec_layout(ldpc_b200_ctx *ctx, int *edge_slot, int *n_slots)
+    {
+        return guarded([&] {
+            if (!ctx) throw std::runtime_error("null argument");
+            b200::BecSliceLayout l;
+            l.build(ctx->eng->H);
+            if (edge_slot) for (int e = 0; e < ctx->eng->H.nnz; ++e) edge_slot[e] = l.edge_slot[e];
+            if (n_slots) *n_slots = l.n_slots;
+        });
+    }
+
     int ldpc_b200_rank(const ldpc_b200_ctx *ctx)
     {
         int r = -1;
@@ -292,7 +303,7 @@ extern "C"
     {
         return guarded([&] {
             if (!ctx || !llr) throw std::runtime_error("null argument");
-            ctx->eng->decode_batch_host(dp, llr, n_frames, llr_out, hard, iters);
+            ctx->eng->decode_batch_host(dp, llr, LDPC_B200_LLR_F64, 1.0, n_frames, llr_out, hard, nullptr, iters);
         });
     }
 
@@ -306,6 +317,33 @@ extern "C"
             src.d_llr = d_llr;
             b200::FrameSink sink;
             sink.d_llr_out = d_llr_out; sink.d_hard = d_hard; sink.d_iters = d_iters;
+            ctx->eng->launch(dp, src, sink, (uint64_t)n_frames, stream);
+        });
+    }
+
+    int ldpc_b200_decode_batch_ex(ldpc_b200_ctx *ctx, decoder_param dp, const void *llr, int llr_type, double llr_scale, int64_t n_frames,
+                                  double *llr_out, uint8_t *hard, uint32_t *hard_bits, int32_t *iters)
+    {
+        return guarded([&] {
+            if (!ctx || !llr) throw std::runtime_error("null argument");
+            ctx->eng->decode_batch_host(dp, llr, llr_type, llr_scale, n_frames, llr_out, hard, hard_bits, iters);
+        });
+    }
+
+    int ldpc_b200_decode_batch_device_ex(ldpc_b200_ctx *ctx, decoder_param dp, const void *d_llr, int llr_type, double llr_scale, int64_t n_frames,
+                                         double *d_llr_out, uint8_t *d_hard, uint32_t *d_hard_bits, int32_t *d_iters, void *stream)
+    {
+        return guarded([&] {
+            if (!ctx || !d_llr) throw std::runtime_error("null argument");
+            b200::FrameSource src;
+            src.kind = 0;
+            if (llr_type == LDPC_B200_LLR_F64) src.d_llr = (const double *)d_llr;
+            else if (llr_type == LDPC_B200_LLR_F32) src.d_llr_f32 = (const float *)d_llr;
+            else if (llr_type == LDPC_B200_LLR_I8) { src.d_llr_i8 = (const int8_t *)d_llr; src.i8_scale = llr_scale; }
+            else throw std::runtime_error("bad llr_type");
+            b200::FrameSink sink;
+            sink.d_llr_out = d_llr_out; sink.d_hard = d_hard; sink.d_iters = d_iters;
+            sink.d_hard_bits = d_hard_bits; sink.hard_words = (ctx->eng->H.nc + 31) / 32;
             ctx->eng->launch(dp, src, sink, (uint64_t)n_frames, stream);
         });
     }

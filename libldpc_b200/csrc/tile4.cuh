@@ -224,8 +224,11 @@ namespace b200
         int max_iter, early_term;
         // frame source
         int kind;
-        const double *llr_in; // SRC_LLR: [n_frames][nc]
-        double sigma, sigma2, delta;
+        const double *llr_in; // SRC_LLR: [n_frames][nc]; or one of the narrow encodings below (exactly one of the three is set)
+        const float *llr_in_f32;  // widened exactly to the decoder's type
+        const int8_t *llr_in_i8;  // quantised LLRs: value = i8 * i8_scale, evaluated in double (exact for a power-of-two scale)
+        double i8_scale;
+        double sigma, sigma2, delta, llr_scale; // llr_scale = 2 / sigma2
         uint32_t thr;
         uint64_t seed;
         uint32_t point;
@@ -233,6 +236,8 @@ namespace b200
         // sinks (indexed by frame - frame0); any may be null
         double *llr_out;
         uint8_t *hard_out;
+        uint32_t *hard_bits; // bit-packed hard decisions [n_frames][hard_words] (bit i%32 of word i/32)
+        int hard_words;
         int32_t *iters_out;
         unsigned long long *counters; // [5] fec, bec, frames, sum(ret iters), sum(executed iterations)
         // per-error diagnostics log (may be null): records {global frame, bit errors, iterations}, err_count = frames in error
@@ -278,11 +283,11 @@ namespace b200
         static constexpr int VEC = V::N, CS = 512;
 
         // CSRC: the old c2v values come from shared/global memory (0, 2) or from the thread's TMEM mirror at
-        // columns tc + 4k (1); TMW: new values are also written to that mirror.
+        // columns tc + 4k (1, 3); 2 and 3 force the fresh frame lanes `fz` to +0; TMW: new values are also written to the mirror.
         // nx: in = this node's index entries (byte offsets), out = those of the node at ip_next when `more`
         // (software prefetch: the load is in flight while this node is computed).
         // PAR: also return the syndrome bits (only early termination consumes them, decoder.cpp:66-72).
-        // fz (CSRC == 2 only): frame lanes of this vector that hold a fresh frame — their old c2v is +0 by definition
+        // fz (CSRC >= 2 only): frame lanes of this vector that hold a fresh frame — their old c2v is +0 by definition
         // (decoder.cpp:16-19) whatever the slots still contain, so a refill never has to clear the message array.
         template <int CSRC, bool TMW, bool PAR>
         static __device__ __forceinline__ uint32_t run(P out_sub, P c2v0, uint32_t (&nx)[D], P ip_next, bool more, uint32_t tc, uint32_t fz)
@@ -305,9 +310,9 @@ namespace b200
                 static_for<D>([&](auto k) {
                     const V o = VAcc<SMEM, T, 0>::ld(out_sub + eo[k.value]);
                     V c;
-                    if constexpr (CSRC == 1) { c = TmAcc<T>::ld(tc + 4 * k.value); tm_wait_ld(); }
+                    if constexpr (CSRC == 1 || CSRC == 3) { c = TmAcc<T>::ld(tc + 4 * k.value); tm_wait_ld(); }
                     else c = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
-                    if constexpr (CSRC == 2)
+                    if constexpr (CSRC >= 2)
                     {
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) c.e[e] = ((fz >> e) & 1u) ? T(0) : c.e[e];
@@ -339,11 +344,11 @@ namespace b200
             {
                 V v[D], r[D], c[D];
                 static_for<D>([&](auto k) {
-                    if constexpr (CSRC == 1) c[k.value] = TmAcc<T>::ld(tc + 4 * k.value);
+                    if constexpr (CSRC == 1 || CSRC == 3) c[k.value] = TmAcc<T>::ld(tc + 4 * k.value);
                     else c[k.value] = VAcc<SMEM, T, k.value * CS>::ld(c2v0);
                 });
-                if constexpr (CSRC == 1) tm_wait_ld();
-                if constexpr (CSRC == 2)
+                if constexpr (CSRC == 1 || CSRC == 3) tm_wait_ld();
+                if constexpr (CSRC >= 2)
                 {
 #pragma unroll
                     for (int k = 0; k < D; ++k)
@@ -607,13 +612,14 @@ namespace b200
         constexpr int TS = (int)sizeof(T), RS = 16 * LANES, ISZ = (int)sizeof(IdxT);
         constexpr uint32_t ALL = (FPC == 32) ? 0xFFFFFFFFu : ((1u << FPC) - 1u), VMASK = (1u << VEC) - 1u;
         extern __shared__ __align__(16) unsigned char dyn_smem[];
-        __shared__ unsigned long long s_frame[FPC], s_old[FPC];
-        __shared__ unsigned long long s_cnt[5];
+        struct LaneCnt { unsigned long long bec, ret, its; uint32_t fec, frames; }; // per frame lane, owned by lane g of warp 0 (no atomics)
+        __shared__ unsigned long long s_old[FPC];
+        __shared__ LaneCnt s_cnt[FPC];
         __shared__ uint32_t s_err[FPC];
+        __shared__ int s_ret[FPC];
         __shared__ uint32_t s_synd[2];
         __shared__ uint2 s_ctrl[2]; // {frames at the iteration limit, frames with >= 1 completed iteration}
-        __shared__ int s_ret[FPC];
-        __shared__ uint32_t s_active, s_skip, s_next, s_tmem;
+        __shared__ uint32_t s_tmem;
 
         const int tid = threadIdx.x, nthreads = blockDim.x;
         // the warp index through a broadcast: the compiler then keeps everything derived from it in uniform registers
@@ -624,6 +630,7 @@ namespace b200
         // ---- carve state and tables --------------------------------------------------------
         P c2v, out, llr, cn_seg, vn_seg, cn_idx, vn_idx;
         uint32_t a_u = (uint32_t)__cvta_generic_to_shared(dyn_smem); // information words of the frames in flight: [FPC][u_words]
+        uint32_t a_tx = 0, a_pu = 0, a_sh = 0;                       // shared-memory residency: position tables (uint16)
         if constexpr (SMEM)
         {
             uint32_t q = (uint32_t)__cvta_generic_to_shared(dyn_smem);
@@ -634,7 +641,16 @@ namespace b200
             const uint32_t a_vs = q; q += 16 * p.vn_max_segs * warps;
             const uint32_t a_ci = q; q += p.cn_idx_bytes;
             const uint32_t a_vi = q; q += p.vn_idx_bytes;
+            // positions of the transmitted / punctured / shortened variables as 16-bit entries: a refill reads them on its
+            // critical path (two L2 round trips per event when they sat in global memory)
+            a_tx = q; q += 2 * ((p.nct + 3) & ~3);
+            a_pu = q; q += 2 * p.n_punct;
+            a_sh = q; q += 2 * p.n_short;
+            q = (q + 15u) & ~15u;
             a_u = q;
+            for (int i = tid; i < ((p.nct + 3) & ~3); i += nthreads) sts_u16<0>(a_tx + 2 * i, (uint32_t)p.tx_pos[i]);
+            for (int i = tid; i < p.n_punct; i += nthreads) sts_u16<0>(a_pu + 2 * i, (uint32_t)p.punct_pos[i]);
+            for (int i = tid; i < p.n_short; i += nthreads) sts_u16<0>(a_sh + 2 * i, (uint32_t)p.short_pos[i]);
             for (int i = tid; i < 4 * p.cn_max_segs * warps; i += nthreads) sts_u32<0>(a_cs + 4 * i, p.cn_seg[i]);
             for (int i = tid; i < 4 * p.vn_max_segs * warps; i += nthreads) sts_u32<0>(a_vs + 4 * i, p.vn_seg[i]);
             for (int i = tid; i < (int)(p.cn_idx_bytes >> 2); i += nthreads) sts_u32<0>(a_ci + 4 * i, reinterpret_cast<const uint32_t *>(p.cn_idx)[i]);
@@ -664,18 +680,26 @@ namespace b200
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             tm_w = s_tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * p.tm_cols_per_warp;
         }
-        if (tid < 5) s_cnt[tid] = 0;
-        if (tid < FPC) { s_err[tid] = 0; s_frame[tid] = 0; s_old[tid] = 0; s_ret[tid] = 0; }
+        if (tid < FPC)
+        {
+            s_err[tid] = 0; s_old[tid] = 0; s_ret[tid] = 0;
+            s_cnt[tid].bec = 0; s_cnt[tid].ret = 0; s_cnt[tid].its = 0; s_cnt[tid].fec = 0; s_cnt[tid].frames = 0;
+        }
         if (tid == 0)
         {
-            s_next = 0; s_active = 0; s_skip = 0; s_synd[0] = 0; s_synd[1] = 0;
+            s_synd[0] = 0; s_synd[1] = 0;
             s_ctrl[0] = make_uint2(0, 0); s_ctrl[1] = make_uint2(0, 0);
         }
         __syncthreads();
 
-        // per-frame iteration counter: lane g of warp 0 owns frame lane g
+        // per-frame iteration counter and global frame index: lane g of warp 0 owns frame lane g
         int it = 0;
-        uint32_t active = 0, skip = 0; // CTA-uniform copies of s_active / s_skip
+        unsigned long long my_gf = 0;
+        // CTA-uniform scheduling state, kept in registers by every thread (no shared round trip): frame lanes in flight, lanes
+        // that sit out the next variable phase, and the CTA's frame cursor (its k-th frame is blockIdx.x + gridDim.x * k)
+        uint32_t active = 0, skip = 0;
+        unsigned long long next_k = 0;
+        const unsigned long long k_end = (blockIdx.x < p.n_frames) ? (p.n_frames - blockIdx.x + gridDim.x - 1) / gridDim.x : 0ull;
 #ifdef B200_PHASE_TIMING
         long long pt_refill = 0, pt_nrefill = 0, pt_rf[4] = {0, 0, 0, 0}; // stages: bit errors (+ arrival skew), bookkeeping, outputs, generate
 #endif
@@ -683,6 +707,7 @@ namespace b200
         // next variable phase read shared memory (and refresh the mirror).  CTA-uniform.
         bool cn_stale = true, vn_stale = true;
         uint32_t fresh = 0; // frame lanes refilled since the last check phase (CTA-uniform)
+
 
         // bit of the codeword of frame lane g at transmitted index t: parity of the information bits selected by
         // column tx_var[t] of the generator matrix (src/core/sparse.h:162-187); 0 without a generator matrix
@@ -700,109 +725,148 @@ namespace b200
             return b & 1u;
         };
 
-        // Writes the decoder input of global frame gf into frame lane g (all threads of the CTA
-        // cooperate), with the fresh-frame state: out = LLRin (c2v = +0 is implied by the `fresh` mask).
-        auto generate = [&](int g, unsigned long long gf)
+        // One pass over the transmitted positions of frame lane g (all threads of the CTA cooperate; thread <-> Philox block q
+        // <-> transmitted indices 4q .. 4q+3), doing either or both of
+        //   count  : bit errors of the lane's final decisions against the transmitted word (ldpcsim.cpp:184-190) -> s_err[g]
+        //   refill : the decoder input of global frame gf, with the fresh-frame state out = LLRin (c2v = +0 is implied by the
+        //            `fresh` mask: the message array is never cleared).
+        // Doing both in ONE pass needs no barrier in between: a thread reads the old posterior of exactly the positions it then
+        // overwrites.  (Caller-supplied LLRs are indexed by variable, not by transmitted index: they take separate passes.)
+        auto frame_pass = [&](int g, bool count, bool refill, unsigned long long gf)
         {
             const int eo = (g / VEC) * 16 + (g % VEC) * TS; // byte offset of lane g inside a record
-            const P dl = llr + eo, dout = out + eo; // c2v is not cleared: the next check phase takes a fresh lane's c2v as +0 (`fresh`)
+            const P dl = llr + eo, dout = out + eo;
             auto put = [&](int pos, T v)
             {
                 Acc<SMEM, T, 0>::st(dl + pos * RS, v);
                 Acc<SMEM, T, 0>::st(dout + pos * RS, v);
             };
-            if (p.kind == SRC_LLR)
-            {
-                const double *src = p.llr_in + (size_t)gf * p.nc;
-                for (int i = tid; i < p.nc; i += nthreads) put((int)p.var_pos[i], (T)src[i]);
-                return;
-            }
+            const bool has_g = p.g_rows > 0;
             const unsigned long long frame = p.frame0 + gf;
-            if (p.g_rows > 0)
-            { // fresh information word per frame from Philox stream 1 (bit k = bit k%32 of word k/32), cw = u*G
-                for (int w = tid; w < p.u_words; w += nthreads)
+            const bool gen = refill && p.kind != SRC_LLR;
+            uint32_t nerr = 0;
+            const int nblk = (p.nct + 3) >> 2;
+            for (int q = tid; q < nblk; q += nthreads)
+            {
+                int pos[4];
+                if constexpr (SMEM)
                 {
-                    const u32x4 r = channel_block(p.seed, p.point, 1, frame, (uint32_t)w >> 2);
-                    const uint32_t q4[4] = {r.x, r.y, r.z, r.w};
-                    uint32_t v = q4[w & 3];
-                    if (32 * w + 32 > p.g_rows) v &= (1u << (p.g_rows - 32 * w)) - 1u;
-                    sts_u32<0>(a_u + 4 * (g * p.u_words + w), v);
+                    const uint2 pw = WAcc<true, 0>::ld2(a_tx + 8 * q);
+                    pos[0] = (int)(pw.x & 0xFFFFu); pos[1] = (int)(pw.x >> 16); pos[2] = (int)(pw.y & 0xFFFFu); pos[3] = (int)(pw.y >> 16);
                 }
-                __syncthreads();
-            }
-            if (p.kind == SRC_AWGN)
-            { // y = sigma*z + x, x = 1 - 2*cw (BPSK), LLR = 2y/sigma^2 (src/sim/channel.cpp:56-68,88-92)
-                const int npairs = (p.nct + 1) >> 1;
-                for (int q = tid; q < npairs; q += nthreads)
+                else
                 {
-                    const u32x4 r = channel_block(p.seed, p.point, 0, frame, (uint32_t)q);
-                    const double u1 = ((double)((((uint64_t)r.y << 32) | r.x) >> 11) + 1.0) * 0x1p-53;
-                    const double u2 = (double)((((uint64_t)r.w << 32) | r.z) >> 11) * 0x1p-53;
-                    const double rad = sqrt(-2.0 * log(u1));
-                    double sn, cs;
-                    sincos(6.283185307179586 * u2, &sn, &cs);
-                    const int t = 2 * q;
-                    const double x0 = cw_bit(g, t) ? -1.0 : 1.0;
-                    const double y0 = __dadd_rn(__dmul_rn(rad * cs, p.sigma), x0);
-                    put(p.tx_pos[t], (T)(__dmul_rn(2.0, y0) / p.sigma2));
-                    if (t + 1 < p.nct)
-                    {
-                        const double x1 = cw_bit(g, t + 1) ? -1.0 : 1.0;
-                        const double y1 = __dadd_rn(__dmul_rn(rad * sn, p.sigma), x1);
-                        put(p.tx_pos[t + 1], (T)(__dmul_rn(2.0, y1) / p.sigma2));
-                    }
+                    const int4 ps = __ldg(reinterpret_cast<const int4 *>(p.tx_pos) + q); // padded to a multiple of 4 entries
+                    pos[0] = ps.x; pos[1] = ps.y; pos[2] = ps.z; pos[3] = ps.w;
                 }
-                for (int i = tid; i < p.n_punct; i += nthreads) put(p.punct_pos[i], T(0));
-                for (int i = tid; i < p.n_short; i += nthreads) put(p.short_pos[i], (T)99999.9);
-            }
-            else
-            { // BSC: y = x ^ Bernoulli(eps), LLR = delta*(1-2y) (src/sim/channel.cpp:123-162)
-                const int nblk = (p.nct + 3) >> 2;
-                for (int q = tid; q < nblk; q += nthreads)
+                const int t0 = 4 * q, nv = min(4, p.nct - t0);
+                if (count)
                 {
-                    const u32x4 r = channel_block(p.seed, p.point, 0, frame, (uint32_t)q);
-                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                    {
-                        const int t = 4 * q + k;
-                        if (t < p.nct) put(p.tx_pos[t], (T)((((w[k] < p.thr) ? 1u : 0u) ^ cw_bit(g, t)) ? -p.delta : p.delta));
+                        if (k < nv) nerr += ((Acc<SMEM, T, 0>::ld(dout + pos[k] * RS) <= T(0)) ? 1u : 0u) ^ ((has_g && !refill) ? cw_bit(g, t0 + k) : 0u);
+                }
+                if (gen)
+                {
+                    const u32x4 r = channel_block(p.seed, p.point, 0, frame, (uint32_t)q);
+                    if (p.kind == SRC_AWGN)
+                    { // y = sigma*z + x, x = 1 - 2*cw (BPSK), LLR = 2y/sigma^2 (src/sim/channel.cpp:56-68,88-92), evaluated as
+                      // y * (2/sigma^2) with the factor rounded once on the host (channel specification, oracle orc_channel_frame)
+                        float z[4];
+                        normal_pair(r.x, r.y, z[0], z[1]);
+                        normal_pair(r.z, r.w, z[2], z[3]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < nv)
+                            {
+                                const double x = (has_g && cw_bit(g, t0 + k)) ? -1.0 : 1.0;
+                                const double y = __dadd_rn(__dmul_rn((double)z[k], p.sigma), x);
+                                put(pos[k], (T)__dmul_rn(y, p.llr_scale));
+                            }
+                    }
+                    else
+                    { // BSC: y = x ^ Bernoulli(eps), LLR = delta*(1-2y) (src/sim/channel.cpp:123-162)
+                        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < nv) put(pos[k], (T)((((w[k] < p.thr) ? 1u : 0u) ^ (has_g ? cw_bit(g, t0 + k) : 0u)) ? -p.delta : p.delta));
                     }
                 }
-                for (int i = tid; i < p.n_punct; i += nthreads) put(p.punct_pos[i], T(0));
-                for (int i = tid; i < p.n_short; i += nthreads) put(p.short_pos[i], (T)p.delta);
+            }
+            if (gen)
+            {
+                const T sv = (T)(p.kind == SRC_AWGN ? 99999.9 : p.delta);
+                if constexpr (SMEM)
+                {
+                    for (int i = tid; i < p.n_punct; i += nthreads) put((int)lds_u16<0>(a_pu + 2 * i), T(0));
+                    for (int i = tid; i < p.n_short; i += nthreads) put((int)lds_u16<0>(a_sh + 2 * i), sv);
+                }
+                else
+                {
+                    for (int i = tid; i < p.n_punct; i += nthreads) put(p.punct_pos[i], T(0));
+                    for (int i = tid; i < p.n_short; i += nthreads) put(p.short_pos[i], sv);
+                }
+            }
+            else if (refill)
+            {
+                if (p.llr_in_f32)
+                {
+                    const float *src = p.llr_in_f32 + (size_t)gf * p.nc;
+                    for (int i = tid; i < p.nc; i += nthreads) put((int)p.var_pos[i], (T)src[i]);
+                }
+                else if (p.llr_in_i8)
+                {
+                    const int8_t *src = p.llr_in_i8 + (size_t)gf * p.nc;
+                    for (int i = tid; i < p.nc; i += nthreads) put((int)p.var_pos[i], (T)__dmul_rn((double)src[i], p.i8_scale));
+                }
+                else
+                {
+                    const double *src = p.llr_in + (size_t)gf * p.nc;
+                    for (int i = tid; i < p.nc; i += nthreads) put((int)p.var_pos[i], (T)src[i]);
+                }
+            }
+            if (count)
+            {
+                nerr = __reduce_add_sync(0xffffffffu, nerr);
+                if (lane == 0 && nerr) atomicAdd(&s_err[g], nerr);
+            }
+        };
+        // fresh information word of frame gf from Philox stream 1 (bit k = bit k%32 of word k/32) into lane g's slot; cw = u*G
+        auto draw_info_word = [&](int g, unsigned long long gf)
+        {
+            for (int w = tid; w < p.u_words; w += nthreads)
+            {
+                const u32x4 r = channel_block(p.seed, p.point, 1, p.frame0 + gf, (uint32_t)w >> 2);
+                const uint32_t q4[4] = {r.x, r.y, r.z, r.w};
+                uint32_t v = q4[w & 3];
+                if (32 * w + 32 > p.g_rows) v &= (1u << (p.g_rows - 32 * w)) - 1u;
+                sts_u32<0>(a_u + 4 * (g * p.u_words + w), v);
             }
         };
 
         // Retires the frame lanes in `mask` and hands each a new frame if any is left.
         //   synd / started : syndrome flags and ">= 1 iteration done" flags valid for this decision
         //   as_skip        : the new frames must sit out the variable phase that follows
+        // Which lanes get a frame is plain arithmetic on CTA-uniform registers; the counters live in per-lane shared rows that
+        // only lane g of warp 0 touches.  Sweeps (frames made on the device, no per-frame outputs, all-zero codeword) take ONE
+        // fused count + refill pass and ONE barrier per event; decode-API launches and -G sweeps take the staged route.
         auto retire_and_refill = [&](uint32_t mask, uint32_t synd, uint32_t started, bool as_skip, bool first_fill)
         {
 #ifdef B200_PHASE_TIMING
             const long long rf0 = clock64();
 #endif
-            if (!first_fill)
-            { // bit errors of the final decisions over the transmitted positions vs the transmitted codeword (ldpcsim.cpp:184-190)
-                for (int g = 0; g < FPC; ++g)
-                    if ((mask >> g) & 1u)
-                    {
-                        const P src = out + (g / VEC) * 16 + (g % VEC) * TS;
-                        uint32_t n = 0;
-                        for (int i = tid; i < p.nct; i += nthreads)
-                            n += ((Acc<SMEM, T, 0>::ld(src + p.tx_pos[i] * RS) <= T(0)) ? 1u : 0u) ^ cw_bit(g, i);
-                        n = __reduce_add_sync(0xffffffffu, n);
-                        if (lane == 0 && n) atomicAdd(&s_err[g], n);
-                    }
-                __syncthreads();
-            }
-#ifdef B200_PHASE_TIMING
-            const long long rf1 = clock64();
-            pt_rf[0] += rf1 - rf0;
-#endif
-            if (warp == 0)
+            const unsigned long long left = k_end - next_k;
+            const uint32_t n_new = (uint32_t)min((unsigned long long)__popc(mask), left);
+            uint32_t gm = 0; // the lanes that receive a frame: the lowest n_new set bits of `mask`
+#pragma unroll
+            for (int g = 0; g < FPC; ++g)
+                if (((mask >> g) & 1u) && (uint32_t)__popc(mask & ((1u << g) - 1u)) < n_new) gm |= 1u << g;
+            auto new_frame = [&](int g) { return (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * (next_k + (unsigned long long)__popc(mask & ((1u << g) - 1u))); };
+            const bool outputs = !first_fill && (p.llr_out || p.hard_out || p.hard_bits || p.iters_out);
+            const bool fused = p.kind != SRC_LLR && p.g_rows <= 0 && !outputs;
+            auto bookkeeping = [&]()
             {
-                bool got = false;
+                if (warp != 0) return;
                 const bool mine = lane < FPC && ((mask >> lane) & 1u);
                 if (mine && !first_fill)
                 {
@@ -810,75 +874,94 @@ namespace b200
                     const int ret = conv ? it - 1 : p.max_iter; // the reference breaks before ++I (decoder.cpp:66-77)
                     const uint32_t e = s_err[lane];
                     s_err[lane] = 0;
-                    atomicAdd(&s_cnt[0], (unsigned long long)(e ? 1 : 0));
-                    atomicAdd(&s_cnt[1], (unsigned long long)e);
-                    atomicAdd(&s_cnt[2], 1ull);
-                    atomicAdd(&s_cnt[3], (unsigned long long)ret);
-                    atomicAdd(&s_cnt[4], (unsigned long long)it);
+                    LaneCnt c = s_cnt[lane];
+                    c.fec += e ? 1u : 0u; c.bec += e; c.frames += 1u; c.ret += (unsigned long long)ret; c.its += (unsigned long long)it;
+                    s_cnt[lane] = c;
                     s_ret[lane] = ret;
-                    s_old[lane] = s_frame[lane];
+                    s_old[lane] = my_gf;
                     if (e && p.err_log)
                     { // the frame can be regenerated from its global index (counter-based channel): that is the whole record
                         const unsigned long long slot = atomicAdd(p.err_count, 1ull);
                         if (slot < p.err_cap)
                         {
-                            p.err_log[2 * slot] = p.frame0 + s_frame[lane];
+                            p.err_log[2 * slot] = p.frame0 + my_gf;
                             p.err_log[2 * slot + 1] = (unsigned long long)e | ((unsigned long long)(uint32_t)ret << 32);
                         }
                     }
                 }
                 if (mine)
                 {
-                    const uint32_t k = s_next + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                    const unsigned long long gf = (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * k;
-                    got = gf < p.n_frames; // frame indices grow with k: the lanes that get one form a prefix of `mask`
-                    if (got) s_frame[lane] = gf;
                     it = 0;
+                    if ((gm >> lane) & 1u) my_gf = new_frame(lane);
                 }
-                const uint32_t gm = __ballot_sync(0xffffffffu, got);
-                if (lane == 0)
-                {
-                    s_next += (uint32_t)__popc(gm);
-                    s_active = (active & ~mask) | gm;
-                    s_skip = as_skip ? gm : 0u;
-                }
-            }
-            __syncthreads();
-#ifdef B200_PHASE_TIMING
-            const long long rf2 = clock64();
-            pt_rf[1] += rf2 - rf1;
-#endif
-            const uint32_t new_active = s_active;
-            if (!first_fill && (p.llr_out || p.hard_out || p.iters_out))
+            };
+            // Up to two rounds of ONE frame_pass call site (a second inlined copy would double the cold code):
+            //   fused : round 0 = count + refill, then the barrier and the bookkeeping
+            //   staged: round 0 = count (skipped on the first fill); bookkeeping, outputs, information words; round 1 = refill
+#pragma unroll 1
+            for (int round = 0; round < (fused ? 1 : 2); ++round)
             {
-                for (int g = 0; g < FPC; ++g)
-                    if ((mask >> g) & 1u)
-                    {
-                        const int eo = (g / VEC) * 16 + (g % VEC) * TS;
-                        const size_t o = (size_t)s_old[g] * p.nc;
-                        for (int i = tid; i < p.nc; i += nthreads)
+                const bool count = round == 0 && !first_fill, refill = fused || round == 1;
+                if (count || refill)
+                {
+#pragma unroll 1
+                    for (int g = 0; g < FPC; ++g)
+                        if ((mask >> g) & 1u)
                         {
-                            const T v = Acc<SMEM, T, 0>::ld(out + eo + p.var_pos[i] * RS);
-                            if (p.llr_out) p.llr_out[o + i] = (double)v;
-                            if (p.hard_out) p.hard_out[o + i] = (v <= T(0)) ? 1 : 0; // decoder.cpp:58
+                            const bool rf = refill && ((gm >> g) & 1u);
+                            if (count || rf) frame_pass(g, count, rf, new_frame(g));
                         }
-                        if (tid == 0 && p.iters_out) p.iters_out[s_old[g]] = s_ret[g];
+                    __syncthreads();
+                }
+#ifdef B200_PHASE_TIMING
+                if (round == 0) pt_rf[0] += clock64() - rf0;
+#endif
+                if (round == 0) bookkeeping();
+                if (!fused && round == 0)
+                {
+                    if (outputs)
+                    {
+                        __syncthreads();
+                        for (int g = 0; g < FPC; ++g)
+                            if ((mask >> g) & 1u)
+                            {
+                                const int eo = (g / VEC) * 16 + (g % VEC) * TS;
+                                const unsigned long long fr = s_old[g];
+                                const size_t o = (size_t)fr * p.nc;
+                                if (p.llr_out || p.hard_out)
+                                    for (int i = tid; i < p.nc; i += nthreads)
+                                    {
+                                        const T v = Acc<SMEM, T, 0>::ld(out + eo + p.var_pos[i] * RS);
+                                        if (p.llr_out) p.llr_out[o + i] = (double)v;
+                                        if (p.hard_out) p.hard_out[o + i] = (v <= T(0)) ? 1 : 0; // decoder.cpp:58
+                                    }
+                                if (p.hard_bits)
+                                { // bit-packed decisions: bit i%32 of word i/32, rows of hard_words 32-bit words per frame
+                                    uint32_t *dst = p.hard_bits + (size_t)fr * p.hard_words;
+                                    for (int i0 = 32 * warp; i0 < p.nc; i0 += 32 * (nthreads >> 5))
+                                    {
+                                        const int i = i0 + lane;
+                                        const bool one = i < p.nc && Acc<SMEM, T, 0>::ld(out + eo + p.var_pos[i] * RS) <= T(0);
+                                        const uint32_t wbits = __ballot_sync(0xffffffffu, one);
+                                        if (lane == 0) dst[i0 >> 5] = wbits;
+                                    }
+                                }
+                                if (tid == 0 && p.iters_out) p.iters_out[fr] = s_ret[g];
+                            }
                     }
-                __syncthreads();
+                    __syncthreads(); // the old posteriors and information words have been consumed
+                    if (p.g_rows > 0 && gm)
+                    {
+                        for (int g = 0; g < FPC; ++g)
+                            if ((gm >> g) & 1u) draw_info_word(g, new_frame(g));
+                        __syncthreads();
+                    }
+                }
             }
-#ifdef B200_PHASE_TIMING
-            const long long rf3 = clock64();
-            pt_rf[2] += rf3 - rf2;
-#endif
-            for (int g = 0; g < FPC; ++g)
-                if (((mask & new_active) >> g) & 1u) generate(g, s_frame[g]);
-            __syncthreads();
-#ifdef B200_PHASE_TIMING
-            pt_rf[3] += clock64() - rf3;
-#endif
-            active = new_active;
-            skip = s_skip;
-            fresh |= mask & new_active;
+            next_k += n_new;
+            active = (active & ~mask) | gm;
+            skip = as_skip ? gm : 0u;
+            fresh |= gm;
             cn_stale = true;
             vn_stale = true;
 #ifdef B200_PHASE_TIMING
@@ -886,8 +969,6 @@ namespace b200
             pt_nrefill += 1;
 #endif
         };
-
-        retire_and_refill(ALL, 0, 0, false, true);
 
         const P c2v_lane = c2v + lane * 16, c2v_sub = c2v + sub * 16, out_sub = out + sub * 16;
         const P out_lane = out + lane * 16, llr_lane = llr + lane * 16;
@@ -898,23 +979,28 @@ namespace b200
         __shared__ long long s_pt[2][32]; // work-end time stamps of the warps (a barrier releases at their maximum)
         long long pt_vcyc[3] = {0, 0, 0}, pt_vtask[3] = {0, 0, 0};
 #endif
-        for (uint32_t L = 0;; ++L)
+        // The loop advances by HALF iterations (even h: check phase, odd h: variable phase) so that the retire / refill event
+        // has exactly ONE call site, at the top of a half: a frame lane found finished is recorded as pending and handled when
+        // the next half begins.  (The event is ~1 k instructions of cold code; inlined at three sites it no longer shared the
+        // 32 KB instruction cache with the decode loop and every event paid for instruction fetches from L2.)
+        uint32_t pend_mask = ALL, pend_synd = 0, pend_started = 0; // the initial fill is the first event
+        bool pend_skip = false, pend_first = true, pend_clear = false;
+        int par_i = 1; // parity of the iteration in progress (double-buffered control words); the first check half makes it 0
+#ifdef B200_PHASE_TIMING
+        long long pt1 = 0, pt2 = 0;
+#endif
+        for (uint32_t h = 0;; ++h)
         {
-            const int par_i = (int)(L & 1u);
-            if (!active) break; // CTA-uniform
-
-            // ---- without early termination a frame at the iteration limit retires here, before a
-            //      check phase is spent on it (its result is fixed: decoder.cpp:22,74-77)
-            if (!ET || !p.early_term)
+            if (pend_mask)
             {
-                const uint32_t lim = s_ctrl[par_i].x & active;
-                if (lim)
-                {
-                    retire_and_refill(lim, 0, 0, false, false);
-                    if (warp == 0 && lane == 0) s_ctrl[par_i].x &= ~lim;
-                    if (!active) break;
-                }
+                retire_and_refill(pend_mask, pend_synd, pend_started, pend_skip, pend_first);
+                if (pend_clear && warp == 0 && lane == 0) s_ctrl[par_i ^ 1].x &= ~pend_mask; // consumed (everyone read it before the event's barriers)
+                pend_mask = 0; pend_first = false; pend_clear = false;
             }
+            if (!(h & 1u))
+            {
+            if (!active) break; // CTA-uniform
+            par_i ^= 1;
 
             // ---- check-node phase (+ syndrome of the previous iteration's decisions) ----------
             uint32_t bad = 0;
@@ -976,7 +1062,7 @@ namespace b200
                         P ip = ib + j * 16;
                         for (; nt > 0; --nt)
                         {
-                            bad |= cn4_any<T, IdxT, SMEM, LANES, ALG>(out_sub, c2v0, ip, deg, CSRC == 2 ? fz : 0u) & keep;
+                            bad |= cn4_any<T, IdxT, SMEM, LANES, ALG>(out_sub, c2v0, ip, deg, CSRC >= 2 ? fz : 0u) & keep;
                             c2v0 += deg * 512;
                             ip += NPW * st;
                         }
@@ -987,9 +1073,10 @@ namespace b200
                 }
                 if constexpr (TM) tm_wait_st();
             };
-            // right after a refill: old c2v from memory with the fresh lanes forced to +0; otherwise the fast source
+            // right after a refill the fresh lanes' old c2v is forced to +0 (the mirror itself never goes stale: the check
+            // phase is the only writer of c2v and writes through)
             if (!cn_stale) cn_phase(std::integral_constant<int, TM ? 1 : 0>{});
-            else cn_phase(std::integral_constant<int, 2>{});
+            else cn_phase(std::integral_constant<int, TM ? 3 : 2>{});
             cn_stale = false;
             fresh = 0;
             // syndrome flags per frame lane: frame = sub*VEC + e
@@ -999,22 +1086,26 @@ namespace b200
                 if (lane == 0 && m) atomicOr(&s_synd[par_i], m);
             }
 #ifdef B200_PHASE_TIMING
-            const long long pt1 = clock64();
+            pt1 = clock64();
             if (lane == 0) s_pt[0][warp] = pt1;
 #endif
             __syncthreads(); // B
 #ifdef B200_PHASE_TIMING
-            long long pt2 = 0; // release time of barrier B = arrival of the last warp
+            pt2 = 0; // release time of barrier B = arrival of the last warp
             for (int w = 0; w < warps; ++w) pt2 = max(pt2, s_pt[0][w]);
 #endif
 
-            // ---- decision: converged (decoder.cpp:66-72) or out of iterations ---------------------
+            // ---- decision: converged (decoder.cpp:66-72) or out of iterations: retired when the variable half begins; the
+            //      new frames sit out that variable phase ---------------------
             {
                 const uint32_t synd = s_synd[par_i];
                 const uint2 ctrl = s_ctrl[par_i];
                 const uint32_t done = active & (((ET && p.early_term) ? (~synd & ctrl.y) : 0u) | ctrl.x);
-                if (done) retire_and_refill(done, synd, ctrl.y, true, false);
+                if (done) { pend_mask = done; pend_synd = synd; pend_started = ctrl.y; pend_skip = true; }
             }
+            }
+            else
+            {
             // bookkeeping for the variable phase that follows and the next decision
             const uint32_t live = active & ~skip;
             if (warp == 0)
@@ -1156,6 +1247,14 @@ namespace b200
             if (pt_rel) { pt_cn += pt1 - pt_rel; pt_wb += pt2 - pt1; pt_vn += pt3 - pt2; pt_wa += pt4 - pt3; ++pt_n; }
             pt_rel = pt4;
 #endif
+            // ---- without early termination a frame at the iteration limit retires before a check phase is spent on it
+            //      (its result is fixed: decoder.cpp:22,74-77); its successor joins the next check phase
+            if (!ET || !p.early_term)
+            {
+                const uint32_t lim = s_ctrl[par_i ^ 1].x & active;
+                if (lim) { pend_mask = lim; pend_synd = 0; pend_started = 0; pend_skip = false; pend_clear = true; }
+            }
+            }
         }
 #ifdef B200_PHASE_TIMING
         if (blockIdx.x == 0 && lane == 0)
@@ -1172,7 +1271,15 @@ namespace b200
 #endif
 
         __syncthreads();
-        if (tid < 5 && s_cnt[tid]) atomicAdd(&p.counters[tid], s_cnt[tid]);
+        if (tid < FPC)
+        {
+            const LaneCnt c = s_cnt[tid];
+            if (c.fec) atomicAdd(&p.counters[0], (unsigned long long)c.fec);
+            if (c.bec) atomicAdd(&p.counters[1], c.bec);
+            if (c.frames) atomicAdd(&p.counters[2], (unsigned long long)c.frames);
+            if (c.ret) atomicAdd(&p.counters[3], c.ret);
+            if (c.its) atomicAdd(&p.counters[4], c.its);
+        }
         if constexpr (TM)
         {
             if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(p.tm_alloc_cols) : "memory");

@@ -16,7 +16,7 @@ namespace b200
     // 32-bit byte offsets.
     // lanes = warp lanes per node (frames per CTA = lanes * 16/sizeof(T)).
 
-    constexpr int TILE_SMEM_OPTIN = 232448 - 1024; // 227 KB minus the kernel's static shared memory
+    constexpr int TILE_SMEM_OPTIN = 232448 - 2048; // 227 KB minus the kernel's static shared memory (scheduling state, a copy of the arguments)
 
     template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
     void prepare_tile_one()

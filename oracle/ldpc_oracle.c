@@ -390,17 +390,70 @@ static void philox_block(uint64_t seed, uint32_t point, uint32_t stream, uint64_
     orc_philox4x32_10(ctr, key, out);
 }
 
-void orc_normal_pair(uint64_t seed, uint32_t point, uint64_t frame, uint32_t j, double z[2])
+/* Standard-normal pair of the channel specification, version 2: Box-Muller evaluated in IEEE binary32 with nothing but
+ * correctly rounded operations (+, *, fma, 1/x, sqrt) in a fixed order, so that this C restatement and the CUDA kernel
+ * (libldpc_b200/csrc/kernels.cuh normal_pair) produce the SAME bits.  Input: two Philox words.
+ *   radius: 40 uniform bits U = wr:wa[7:0], u1 = (U + 1/2) 2^-40 in (0,1) (tails out to 7.4 sigma);
+ *           -ln u1 = e ln 2 - ln f with f in (0.7071, 1.4142] the truncated 24-bit mantissa of 2U+1,
+ *           ln f = 2 atanh(s), s = (f-1)/(f+1), odd series up to s^9 (|s| <= 0.1716: truncation 2e-9 relative)
+ *   angle : 24 bits: octant wa[31:29], phi = (wa[28:8] + 1/2) 2^-21 pi/4 in (0, pi/4), Taylor sine / cosine (<= 2e-9),
+ *           octants by swap / sign (the grid of phi is symmetric, so the angle stays exactly uniform on it). */
+static void normal_pair_v2(uint32_t wr, uint32_t wa, float z[2])
+{
+    const uint64_t T = ((((uint64_t)wr << 8) | (uint64_t)(wa & 0xFFu)) << 1) | 1ull; /* 2U+1 < 2^41 */
+    const int lz = __builtin_clzll(T) - 23;                                           /* 0..40 */
+    const uint32_t m = (uint32_t)((T << lz) >> 17);                                   /* top 24 bits, truncated */
+    float f = (float)m * 0x1p-23f;                                                    /* [1,2), exact */
+    int e = lz + 1;                                                                   /* u1 ~ f 2^-e */
+    if (f > 1.41421354f) { f = f * 0.5f; e -= 1; }
+    const float g = f - 1.0f;                                                         /* exact */
+    const float s = g * (1.0f / (2.0f + g));
+    const float s2 = s * s;
+    float q = 0x1.c71c72p-4f;                                                         /* 1/9 */
+    q = fmaf(q, s2, 0x1.24924ap-3f);                                                  /* 1/7 */
+    q = fmaf(q, s2, 0x1.99999ap-3f);                                                  /* 1/5 */
+    q = fmaf(q, s2, 0x1.555556p-2f);                                                  /* 1/3 */
+    q = fmaf(q, s2, 1.0f);
+    const float lnf = (2.0f * s) * q;
+    const float n = fmaf((float)e, 0x1.62e430p-1f, -lnf);                             /* -ln u1 > 0 */
+    const float r = sqrtf(2.0f * n);
+    const uint32_t a = wa >> 8, oct = a >> 21;
+    const float phi = ((float)(a & 0x1FFFFFu) + 0.5f) * 0x1.921fb6p-22f;              /* pi/4 * 2^-21 */
+    const float x2 = phi * phi;
+    float sp = 0x1.71de3ap-19f;                                                       /* 1/9! */
+    sp = fmaf(sp, x2, -0x1.a01a02p-13f);                                              /* -1/7! */
+    sp = fmaf(sp, x2, 0x1.111112p-7f);                                                /* 1/5! */
+    sp = fmaf(sp, x2, -0x1.555556p-3f);                                               /* -1/3! */
+    const float sn0 = fmaf(phi * x2, sp, phi);
+    float cp = -0x1.27e4fcp-22f;                                                      /* -1/10! */
+    cp = fmaf(cp, x2, 0x1.a01a02p-16f);                                               /* 1/8! */
+    cp = fmaf(cp, x2, -0x1.6c16c2p-10f);                                              /* -1/6! */
+    cp = fmaf(cp, x2, 0x1.555556p-5f);                                                /* 1/4! */
+    cp = fmaf(cp, x2, -0.5f);
+    const float cs0 = fmaf(cp, x2, 1.0f);
+    float c = (oct & 1u) ? sn0 : cs0, sn = (oct & 1u) ? cs0 : sn0;                    /* theta = pi/2 - phi in odd octants */
+    if (oct & 2u) { const float t = c; c = -sn; sn = t; }                             /* + pi/2 */
+    if (oct & 4u) { c = -c; sn = -sn; }                                               /* + pi */
+    z[0] = r * c;
+    z[1] = r * sn;
+}
+
+void orc_normal_from_words(uint32_t wr, uint32_t wa, double z[2])
+{
+    float a[2];
+    normal_pair_v2(wr, wa, a);
+    z[0] = a[0]; z[1] = a[1];
+}
+
+/* normals of transmitted indices 4j .. 4j+3 of a frame: one Philox block, words (0,1) -> first pair, (2,3) -> second */
+void orc_normal_block(uint64_t seed, uint32_t point, uint64_t frame, uint32_t j, double z[4])
 {
     uint32_t x[4];
+    float a[2], b[2];
     philox_block(seed, point, 0, frame, j, x);
-    const double two_m53 = 1.0 / 9007199254740992.0;
-    double u1 = ((double)((((uint64_t)x[1] << 32) | x[0]) >> 11) + 1.0) * two_m53; /* (0,1] */
-    double u2 = (double)((((uint64_t)x[3] << 32) | x[2]) >> 11) * two_m53;         /* [0,1) */
-    double r = sqrt(-2.0 * log(u1));
-    double a = 6.283185307179586 * u2;
-    z[0] = r * cos(a);
-    z[1] = r * sin(a);
+    normal_pair_v2(x[0], x[1], a);
+    normal_pair_v2(x[2], x[3], b);
+    z[0] = a[0]; z[1] = a[1]; z[2] = b[0]; z[3] = b[1];
 }
 
 static uint32_t prob_threshold(double p)
@@ -432,17 +485,23 @@ void orc_channel_frame(const orc_code *c, const orc_code *g, int kind, double x,
     {
         double sigma2 = pow(10, -x / 10), sigma = sqrt(sigma2); /* channel.cpp:39-41 */
         double *y = (double *)malloc(sizeof(double) * (c->nct + 1));
-        for (int t = 0; t < c->nct; t += 2)
+        for (int t = 0; t < c->nct; t += 4)
         {
-            double z[2];
-            orc_normal_pair(seed, point, frame, (uint32_t)t >> 1, z);
-            for (int k = 0; k < 2 && t + k < c->nct; ++k)
+            double z[4];
+            orc_normal_block(seed, point, frame, (uint32_t)t >> 2, z);
+            for (int k = 0; k < 4 && t + k < c->nct; ++k)
             {
                 double xs = 1 - 2 * (int)cw[c->bit_pos[t + k]]; /* channel.cpp:58 */
                 y[t + k] = z[k] * sigma + xs;                    /* channel.cpp:66: normal(0,sigma)() + x */
             }
         }
-        orc_llr_awgn(c, y, sigma2, llr_f64);
+        /* LLR rule of channel.cpp:70-93 with 2y/sigma^2 evaluated as y * (2/sigma^2), the factor rounded once (what the kernel does) */
+        {
+            const double scale = 2.0 / sigma2;
+            for (int i = 0; i < c->n_punct; ++i) llr_f64[c->punct[i]] = 0.0;
+            for (int i = 0; i < c->n_short; ++i) llr_f64[c->shorten[i]] = 99999.9;
+            for (int t = 0; t < c->nct; ++t) llr_f64[c->bit_pos[t]] = y[t] * scale;
+        }
         free(y);
     }
     else

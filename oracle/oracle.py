@@ -69,7 +69,8 @@ def lib():
         L.orc_rank.argtypes = [P]
         L.orc_philox4x32_10.argtypes = [ct.POINTER(ct.c_uint32)] * 3
         L.orc_channel_frame.argtypes = [P, P, ct.c_int, ct.c_double, ct.c_uint64, ct.c_uint32, ct.c_uint64, bp, dp, bp]
-        L.orc_normal_pair.argtypes = [ct.c_uint64, ct.c_uint32, ct.c_uint64, ct.c_uint32, dp]
+        L.orc_normal_block.argtypes = [ct.c_uint64, ct.c_uint32, ct.c_uint64, ct.c_uint32, dp]
+        L.orc_normal_from_words.argtypes = [ct.c_uint32, ct.c_uint32, dp]
         L.orc_sim_point.argtypes = [P, P, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_double, ct.c_uint64,
                                     ct.c_uint32, ct.c_uint64, ct.c_uint64, ct.c_int, ct.POINTER(ct.c_uint64)]
         _lib = L
@@ -196,9 +197,16 @@ def philox4x32_10(ctr, key):
     return [int(v) for v in o]
 
 
-def normal_pair(seed, point, frame, j):
+def normal_block(seed, point, frame, j):
+    """The four standard normals of transmitted indices 4j..4j+3 (channel specification v2)."""
+    z = np.zeros(4)
+    lib().orc_normal_block(int(seed), int(point), int(frame), int(j), _dp(z))
+    return z
+
+
+def normal_from_words(wr, wa):
     z = np.zeros(2)
-    lib().orc_normal_pair(int(seed), int(point), int(frame), int(j), _dp(z))
+    lib().orc_normal_from_words(int(wr), int(wa), _dp(z))
     return z
 
 

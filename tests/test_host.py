@@ -176,3 +176,28 @@ def test_public_header_is_plain_c(tmp_path):
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert subprocess.run([str(tmp_path / (src + ".out"))]).returncode == 0
+
+
+@pytest.mark.parametrize("which", ["h", "irregular"])
+def test_bec_slice_layout_is_bank_conflict_free(built_lib, which):
+    """Message slots of the bit-sliced erasure kernel: a permutation into [0, n_slots) whose bank (slot % 32) is distinct
+    over edge k of every 32 consecutive checks and of every 32 consecutive variables (Koenig edge colouring), with little
+    padding."""
+    from libldpc_b200 import api
+    from conftest import H_IRREGULAR
+    ctx = api.Context(H_FILE if which == "h" else H_IRREGULAR, "", device=-1)
+    slot, n_slots = ctx.bec_layout()
+    r, c = ctx.edges()
+    assert len(set(slot.tolist())) == ctx.nnz and slot.min() >= 0 and slot.max() < n_slots and n_slots % 32 == 0
+    assert n_slots <= 1.25 * ctx.nnz + 32 * 32
+    for node, size in ((r, ctx.mc), (c, ctx.nc)):
+        k = np.zeros(ctx.nnz, np.int64)          # index of the edge within its node, file order
+        seen = np.zeros(size, np.int64)
+        for e in range(ctx.nnz):
+            k[e] = seen[node[e]]
+            seen[node[e]] += 1
+        groups = {}
+        for e in range(ctx.nnz):
+            groups.setdefault((node[e] // 32, k[e]), []).append(slot[e] % 32)
+        assert all(len(b) == len(set(b)) for b in groups.values())
+    ctx.close()
