@@ -69,6 +69,27 @@ HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device
 _lib = None
 
 
+class _Missing:
+    """Stands in for a symbol an older build of the library lacks (A/B runs against earlier builds): calling it raises."""
+    def __init__(self, name):
+        self.name, self.argtypes, self.restype = name, None, None
+
+    def __call__(self, *a):
+        raise RuntimeError(f"{self.name} is not exported by this build of libldpc.so")
+
+
+class _Tolerant:
+    def __init__(self, lib):
+        object.__setattr__(self, "_lib", lib)
+        object.__setattr__(self, "_missing", {})
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._lib, name)
+        except AttributeError:
+            return self._missing.setdefault(name, _Missing(name))
+
+
 def load_library(path=None):
     """Loads libldpc.so and declares the prototypes.  Raises if the library has not been built."""
     global _lib
@@ -77,7 +98,7 @@ def load_library(path=None):
     p = path or lib_path()
     if not os.path.exists(p):
         raise RuntimeError(f"{p} is missing: build it with `python -m libldpc_b200.build` (there is no fallback path)")
-    L = ct.CDLL(p)
+    L = _Tolerant(ct.CDLL(p))
     vp, i64, u64, u32 = ct.c_void_p, ct.c_int64, ct.c_uint64, ct.c_uint32
     dptr, bptr, iptr = ct.POINTER(ct.c_double), ct.POINTER(ct.c_uint8), ct.POINTER(ct.c_int)
     L.ldpc_b200_last_error.restype = ct.c_char_p

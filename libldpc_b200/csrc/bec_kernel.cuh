@@ -101,7 +101,7 @@ namespace b200
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                 {
-                    const int t = 4 * j + k;
+                    const int t = j + k * nblk; // value k of block j <-> transmitted index j + k*nblk (channel specification)
                     if (t < p.nct) in[p.bit_pos[t] * 32 + g] = (w[k] < p.thr) ? BEC_E : cw[p.bit_pos[t] * 32 + g];
                 }
             }

@@ -123,18 +123,18 @@ namespace b200
                 uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
 #pragma unroll 4
                 for (int f = 0; f < 32; ++f)
-                { // same stream as the byte-wise path: counter (block q, frame), values 4q .. 4q+3
+                { // same stream as the byte-wise path: counter (block q, frame)
                     const u32x4 r = channel_block(p.seed, p.point, 0, p.frame0 + f0 + f, (uint32_t)q);
                     e0 |= (r.x < p.thr ? 1u : 0u) << f;
                     e1 |= (r.y < p.thr ? 1u : 0u) << f;
                     e2 |= (r.z < p.thr ? 1u : 0u) << f;
                     e3 |= (r.w < p.thr ? 1u : 0u) << f;
                 }
-                const int t = 4 * q;
-                er[p.tx_var[t]] = e0;
-                if (t + 1 < p.nct) er[p.tx_var[t + 1]] = e1;
-                if (t + 2 < p.nct) er[p.tx_var[t + 2]] = e2;
-                if (t + 3 < p.nct) er[p.tx_var[t + 3]] = e3;
+                // value k of block q <-> transmitted index q + k*nblk (channel specification): neighbouring threads, neighbouring words
+                er[p.tx_var[q]] = e0;
+                if (q + nblk < p.nct) er[p.tx_var[q + nblk]] = e1;
+                if (q + 2 * nblk < p.nct) er[p.tx_var[q + 2 * nblk]] = e2;
+                if (q + 3 * nblk < p.nct) er[p.tx_var[q + 3 * nblk]] = e3;
             }
             group_barrier(gs + 1);
             // ---- v2c of iteration 0 = the channel value (decoder.cpp:96-99): known iff received, never wrong ----

@@ -404,7 +404,6 @@ namespace b200
         d->vn_idx = upload(l.vn_idx);
         std::vector<int32_t> tx, pu, sh;
         for (int v : H.bit_pos) tx.push_back((int32_t)l.var_pos[v]);
-        while (tx.size() % 4) tx.push_back(0); // the kernel fetches the positions of a Philox block (4 transmitted indices) with one 16-byte load
         for (int v : H.puncture) if (v >= 0 && v < H.nc) pu.push_back((int32_t)l.var_pos[v]);
         for (int v : H.shorten) if (v >= 0 && v < H.nc) sh.push_back((int32_t)l.var_pos[v]);
         d->tx_pos = upload(tx);
@@ -1169,7 +1168,7 @@ namespace b200
             }
             return b & 1u;
         };
-        const int nblk = (nct + 3) / 4; // one Philox block serves four transmitted indices on every channel
+        const int nblk = (nct + 3) / 4; // value q of Philox block j serves the transmitted index j + q*nblk, on every channel
         const int64_t total = n_frames * (int64_t)nblk;
         for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x)
         {
@@ -1184,7 +1183,7 @@ namespace b200
                 normal_pair(r.z, r.w, z[2], z[3]);
                 for (int q = 0; q < 4; ++q)
                 {
-                    const int t = 4 * j + q;
+                    const int t = j + q * nblk;
                     if (t >= nct) break;
                     const uint32_t b = cw_bit(fr, bit_pos[t]);
                     const double y = __dadd_rn(__dmul_rn((double)z[q], sigma), b ? -1.0 : 1.0);
@@ -1197,7 +1196,7 @@ namespace b200
                 const uint32_t w[4] = {r.x, r.y, r.z, r.w};
                 for (int q = 0; q < 4; ++q)
                 {
-                    const int t = 4 * j + q;
+                    const int t = j + q * nblk;
                     if (t >= nct) break;
                     const bool hit = w[q] < thr;
                     if (kind == SRC_BSC)

@@ -648,7 +648,7 @@ namespace b200
             a_sh = q; q += 2 * p.n_short;
             q = (q + 15u) & ~15u;
             a_u = q;
-            for (int i = tid; i < ((p.nct + 3) & ~3); i += nthreads) sts_u16<0>(a_tx + 2 * i, (uint32_t)p.tx_pos[i]);
+            for (int i = tid; i < p.nct; i += nthreads) sts_u16<0>(a_tx + 2 * i, (uint32_t)p.tx_pos[i]);
             for (int i = tid; i < p.n_punct; i += nthreads) sts_u16<0>(a_pu + 2 * i, (uint32_t)p.punct_pos[i]);
             for (int i = tid; i < p.n_short; i += nthreads) sts_u16<0>(a_sh + 2 * i, (uint32_t)p.short_pos[i]);
             for (int i = tid; i < 4 * p.cn_max_segs * warps; i += nthreads) sts_u32<0>(a_cs + 4 * i, p.cn_seg[i]);
@@ -745,26 +745,30 @@ namespace b200
             const unsigned long long frame = p.frame0 + gf;
             const bool gen = refill && p.kind != SRC_LLR;
             uint32_t nerr = 0;
+#ifdef B200_PHASE_TIMING
+            const long long fp0 = clock64();
+#endif
             const int nblk = (p.nct + 3) >> 2;
             for (int q = tid; q < nblk; q += nthreads)
             {
+                // value k of Philox block q belongs to the transmitted index q + k*nblk: for every k the threads of a warp then
+                // touch neighbouring transmitted indices, i.e. (mostly) neighbouring records — with 4q + k they strode four
+                // records apart and every one of the pass's scattered loads / stores was a 16-way bank conflict
                 int pos[4];
-                if constexpr (SMEM)
+                bool ok[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
                 {
-                    const uint2 pw = WAcc<true, 0>::ld2(a_tx + 8 * q);
-                    pos[0] = (int)(pw.x & 0xFFFFu); pos[1] = (int)(pw.x >> 16); pos[2] = (int)(pw.y & 0xFFFFu); pos[3] = (int)(pw.y >> 16);
+                    const int t = q + k * nblk;
+                    ok[k] = t < p.nct;
+                    if constexpr (SMEM) pos[k] = ok[k] ? (int)lds_u16<0>(a_tx + 2 * t) : 0;
+                    else pos[k] = ok[k] ? __ldg(p.tx_pos + t) : 0;
                 }
-                else
-                {
-                    const int4 ps = __ldg(reinterpret_cast<const int4 *>(p.tx_pos) + q); // padded to a multiple of 4 entries
-                    pos[0] = ps.x; pos[1] = ps.y; pos[2] = ps.z; pos[3] = ps.w;
-                }
-                const int t0 = 4 * q, nv = min(4, p.nct - t0);
                 if (count)
                 {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (k < nv) nerr += ((Acc<SMEM, T, 0>::ld(dout + pos[k] * RS) <= T(0)) ? 1u : 0u) ^ ((has_g && !refill) ? cw_bit(g, t0 + k) : 0u);
+                        if (ok[k]) nerr += ((Acc<SMEM, T, 0>::ld(dout + pos[k] * RS) <= T(0)) ? 1u : 0u) ^ ((has_g && !refill) ? cw_bit(g, q + k * nblk) : 0u);
                 }
                 if (gen)
                 {
@@ -777,9 +781,9 @@ namespace b200
                         normal_pair(r.z, r.w, z[2], z[3]);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < nv)
+                            if (ok[k])
                             {
-                                const double x = (has_g && cw_bit(g, t0 + k)) ? -1.0 : 1.0;
+                                const double x = (has_g && cw_bit(g, q + k * nblk)) ? -1.0 : 1.0;
                                 const double y = __dadd_rn(__dmul_rn((double)z[k], p.sigma), x);
                                 put(pos[k], (T)__dmul_rn(y, p.llr_scale));
                             }
@@ -789,10 +793,14 @@ namespace b200
                         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < nv) put(pos[k], (T)((((w[k] < p.thr) ? 1u : 0u) ^ (has_g ? cw_bit(g, t0 + k) : 0u)) ? -p.delta : p.delta));
+                            if (ok[k]) put(pos[k], (T)((((w[k] < p.thr) ? 1u : 0u) ^ (has_g ? cw_bit(g, q + k * nblk) : 0u)) ? -p.delta : p.delta));
                     }
                 }
             }
+#ifdef B200_PHASE_TIMING
+            const long long fp1 = clock64();
+            pt_rf[1] += fp1 - fp0;
+#endif
             if (gen)
             {
                 const T sv = (T)(p.kind == SRC_AWGN ? 99999.9 : p.delta);
@@ -825,11 +833,18 @@ namespace b200
                     for (int i = tid; i < p.nc; i += nthreads) put((int)p.var_pos[i], (T)src[i]);
                 }
             }
+#ifdef B200_PHASE_TIMING
+            const long long fp2 = clock64();
+            pt_rf[2] += fp2 - fp1;
+#endif
             if (count)
             {
                 nerr = __reduce_add_sync(0xffffffffu, nerr);
                 if (lane == 0 && nerr) atomicAdd(&s_err[g], nerr);
             }
+#ifdef B200_PHASE_TIMING
+            pt_rf[3] += clock64() - fp2;
+#endif
         };
         // fresh information word of frame gf from Philox stream 1 (bit k = bit k%32 of word k/32) into lane g's slot; cw = u*G
         auto draw_info_word = [&](int g, unsigned long long gf)
@@ -1261,7 +1276,7 @@ namespace b200
             printf("warp %2d: iterations %lld  check work %lld  wait-B %lld  decision+variable work %lld  wait-A %lld  (cycles per iteration, from barrier release); check segments/it %lld tasks/it %lld header cycles/seg %lld\n", warp, pt_n,
                    pt_cn / pt_n, pt_wb / pt_n, pt_vn / pt_n, pt_wa / pt_n, pt_nseg / pt_n, pt_ntask / pt_n, pt_hdr / (pt_nseg ? pt_nseg : 1));
         if (blockIdx.x == 0 && tid == 0)
-            printf("refills: %lld events, %lld cycles each (bit errors %lld, bookkeeping %lld, outputs %lld, generate %lld); iterations %lld\n", pt_nrefill,
+            printf("refills: %lld events, %lld cycles each (pass + barrier %lld: block loop %lld, punctured/shortened %lld, count reduce %lld); iterations %lld\n", pt_nrefill,
                    pt_refill / (pt_nrefill ? pt_nrefill : 1), pt_rf[0] / (pt_nrefill ? pt_nrefill : 1), pt_rf[1] / (pt_nrefill ? pt_nrefill : 1),
                    pt_rf[2] / (pt_nrefill ? pt_nrefill : 1), pt_rf[3] / (pt_nrefill ? pt_nrefill : 1), pt_n);
         if (blockIdx.x == 0 && lane == 0)

@@ -445,7 +445,8 @@ void orc_normal_from_words(uint32_t wr, uint32_t wa, double z[2])
     z[0] = a[0]; z[1] = a[1];
 }
 
-/* normals of transmitted indices 4j .. 4j+3 of a frame: one Philox block, words (0,1) -> first pair, (2,3) -> second */
+/* the four normals of Philox block j of a frame (transmitted indices j, j+nb, j+2nb, j+3nb with nb = ceil(nct/4) blocks per
+ * frame: a warp of the kernel then touches neighbouring positions): words (0,1) -> first pair, (2,3) -> second */
 void orc_normal_block(uint64_t seed, uint32_t point, uint64_t frame, uint32_t j, double z[4])
 {
     uint32_t x[4];
@@ -485,14 +486,17 @@ void orc_channel_frame(const orc_code *c, const orc_code *g, int kind, double x,
     {
         double sigma2 = pow(10, -x / 10), sigma = sqrt(sigma2); /* channel.cpp:39-41 */
         double *y = (double *)malloc(sizeof(double) * (c->nct + 1));
-        for (int t = 0; t < c->nct; t += 4)
+        const int nb = (c->nct + 3) / 4; /* Philox block q serves the transmitted indices q, q+nb, q+2nb, q+3nb */
+        for (int q = 0; q < nb; ++q)
         {
             double z[4];
-            orc_normal_block(seed, point, frame, (uint32_t)t >> 2, z);
-            for (int k = 0; k < 4 && t + k < c->nct; ++k)
+            orc_normal_block(seed, point, frame, (uint32_t)q, z);
+            for (int k = 0; k < 4; ++k)
             {
-                double xs = 1 - 2 * (int)cw[c->bit_pos[t + k]]; /* channel.cpp:58 */
-                y[t + k] = z[k] * sigma + xs;                    /* channel.cpp:66: normal(0,sigma)() + x */
+                const int t = q + k * nb;
+                if (t >= c->nct) continue;
+                double xs = 1 - 2 * (int)cw[c->bit_pos[t]]; /* channel.cpp:58 */
+                y[t] = z[k] * sigma + xs;                    /* channel.cpp:66: normal(0,sigma)() + x */
             }
         }
         /* LLR rule of channel.cpp:70-93 with 2y/sigma^2 evaluated as y * (2/sigma^2), the factor rounded once (what the kernel does) */
@@ -508,11 +512,12 @@ void orc_channel_frame(const orc_code *c, const orc_code *g, int kind, double x,
     {
         uint32_t thr = prob_threshold(x);
         uint8_t *y = (uint8_t *)malloc(c->nct + 1);
+        const int nb = (c->nct + 3) / 4; /* value k of Philox block q belongs to the transmitted index q + k*nb */
         for (int t = 0; t < c->nct; ++t)
         {
             uint32_t w[4];
-            philox_block(seed, point, 0, frame, (uint32_t)t >> 2, w);
-            int hit = w[t & 3] < thr;
+            philox_block(seed, point, 0, frame, (uint32_t)(t % nb), w);
+            int hit = w[t / nb] < thr;
             uint8_t b = cw[c->bit_pos[t]];
             if (kind == ORC_BSC) y[t] = b ^ (uint8_t)hit;            /* channel.cpp:131 */
             else y[t] = hit ? ORC_ERASURE : b;                       /* channel.cpp:201 */

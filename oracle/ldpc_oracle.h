@@ -77,7 +77,8 @@ enum { ORC_AWGN = 1, ORC_BSC = 2, ORC_BEC = 3 };
  * AWGN/BSC write llr_f64[nc]; BEC writes llr_u8[nc].  cw[nc] always written. */
 void orc_channel_frame(const orc_code *c, const orc_code *g, int kind, double x, uint64_t seed,
                        uint32_t point, uint64_t frame, uint8_t *cw, double *llr_f64, uint8_t *llr_u8);
-/* the four standard normals the AWGN channel uses for transmitted indices 4j .. 4j+3 of (seed, point, frame): Box-Muller in
+/* the four standard normals of Philox block j of (seed, point, frame) — the AWGN channel uses them for the transmitted
+ * indices j, j+nb, j+2nb, j+3nb, nb = ceil(nct/4) — Box-Muller in
  * exactly specified binary32 arithmetic (the CUDA kernel produces the same bits) */
 void orc_normal_block(uint64_t seed, uint32_t point, uint64_t frame, uint32_t j, double z[4]);
 /* the same from two raw 32-bit words (radius word, angle word) — for accuracy tests of the evaluation */

@@ -198,7 +198,7 @@ def philox4x32_10(ctr, key):
 
 
 def normal_block(seed, point, frame, j):
-    """The four standard normals of transmitted indices 4j..4j+3 (channel specification v2)."""
+    """The four standard normals of Philox block j (channel specification v2)."""
     z = np.zeros(4)
     lib().orc_normal_block(int(seed), int(point), int(frame), int(j), _dp(z))
     return z

@@ -18,7 +18,8 @@ ctx.set_tuning(precision=api.F32 if mode == "ms32" else api.F64, frames_per_cta=
 if os.environ.get("PAIR") == "1":
     ctx.set_tuning(frames_per_cta=4 if mode == "ms32" else 2, threads_per_cta=256, idx16=2, ctas=296)
 dec = "BP" if mode == "bp" else "BP_MS"
+snr = float(os.environ.get("SNR", "-4.5"))   # e.g. SNR=3 with mode et: the refill-dominated regime
 for i in range(3):
-    r = ctx.sim_point("AWGN", -4.5, seed=0, point=0, frame0=i * frames, nframes=frames, decoding=dec, iterations=50, early_term=(mode == "et"))
+    r = ctx.sim_point("AWGN", snr, seed=0, point=0, frame0=i * frames, nframes=frames, decoding=dec, iterations=50, early_term=(mode == "et"))
     print(r)
 print(ctx.stats())
