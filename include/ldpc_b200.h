@@ -267,6 +267,9 @@ LDPC_B200_API int ldpc_b200_get_stats(const ldpc_b200_ctx *ctx, ldpc_b200_stats 
 /* Measurement aid: sustained shared-memory read bandwidth of the context's device in GB/s (a conflict-free
  * LDS.128 streaming kernel on every SM) — the roofline that bounds the shared-memory-resident decode kernel. */
 LDPC_B200_API int ldpc_b200_smem_probe(ldpc_b200_ctx *ctx, double *gb_per_s);
+/* Measurement aid: sustained FP64 instruction rate in G thread-instructions/s (independent DFMA chains on every SM) — the
+ * roofline of the fp64 sum-product kernel, which is bound by the FP64 pipe. */
+LDPC_B200_API int ldpc_b200_fp64_probe(ldpc_b200_ctx *ctx, double *ginst_per_s);
 LDPC_B200_API int ldpc_b200_reset_stats(ldpc_b200_ctx *ctx);
 
 #ifdef __cplusplus

@@ -64,7 +64,7 @@ HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device
                   "ldpc_b200_get_puncture", "ldpc_b200_get_layout", "ldpc_b200_rank", "ldpc_b200_encode", "ldpc_b200_syndrome",
                   "ldpc_b200_decode_batch", "ldpc_b200_decode_batch_device", "ldpc_b200_decode_bec_batch", "ldpc_b200_channel",
                   "ldpc_b200_sim_point", "ldpc_b200_sim_point_async", "ldpc_b200_simulate", "ldpc_b200_simulate_ex", "ldpc_b200_get_stats",
-                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe", "ldpc_b200_sim_point_log", "ldpc_b200_prepare", "ldpc_b200_decode_batch_ex", "ldpc_b200_decode_batch_device_ex", "ldpc_b200_get_bec_layout")
+                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe", "ldpc_b200_sim_point_log", "ldpc_b200_prepare", "ldpc_b200_decode_batch_ex", "ldpc_b200_decode_batch_device_ex", "ldpc_b200_get_bec_layout", "ldpc_b200_fp64_probe")
 
 _lib = None
 
@@ -134,6 +134,7 @@ def load_library(path=None):
     L.ldpc_b200_get_stats.argtypes = [vp, ct.POINTER(stats)]
     L.ldpc_b200_reset_stats.argtypes = [vp]
     L.ldpc_b200_smem_probe.argtypes = [vp, ct.POINTER(ct.c_double)]
+    L.ldpc_b200_fp64_probe.argtypes = [vp, ct.POINTER(ct.c_double)]
     L.ldpc_b200_sim_point_log.argtypes = [vp, decoder_param, ct.c_char_p, ct.c_double, u64, u32, u64, u64, ct.POINTER(u64), ct.POINTER(error_record),
                                           i64, ct.POINTER(i64)]
     if path is None:
@@ -364,6 +365,12 @@ class Context:
         """Sustained shared-memory read bandwidth of this device, GB/s."""
         v = ct.c_double()
         self._check(self.lib.ldpc_b200_smem_probe(self._h, ct.byref(v)))
+        return float(v.value)
+
+    def fp64_probe(self):
+        """Sustained FP64 instruction rate of this device, G thread-instructions/s."""
+        v = ct.c_double()
+        self._check(self.lib.ldpc_b200_fp64_probe(self._h, ct.byref(v)))
         return float(v.value)
 
     def stats(self, reset=False):

@@ -79,8 +79,18 @@ namespace b200
         void sim_point_async(const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point,
                              uint64_t frame0, uint64_t n_frames, unsigned long long *d_counters, void *stream, bool may_block = false);
 
+        // Pipelined rounds of the sweep driver: a round is launched into one of two slots (device counters, a pinned host copy,
+        // an event) and collected later, so the next round is already running while the host reads the previous one.
+        void round_launch(int slot, const decoder_param &dp, const std::string &channel, double x, uint64_t seed, uint32_t point, uint64_t frame0,
+                          uint64_t n_frames);
+        void round_collect(int slot, uint64_t counters[5]);
+        // frames of one full wave of the persistent grid for this decoder type under the current tuning (rounds are sized in waves)
+        uint64_t wave_frames(const decoder_param &dp, const std::string &channel);
+
         // sustained shared-memory read bandwidth of the device in GB/s (LDS.128 streaming from every SM)
         double smem_probe();
+        // sustained FP64 instruction rate of the device in G thread-instructions/s (DFMA streaming from every SM)
+        double fp64_probe();
 
         void ensure_cuda();
         void *engine_stream() const { return stream_; }
@@ -102,6 +112,13 @@ namespace b200
         void autotune_global(int alg, const decoder_param &dp, void *stream);
         void autotune_pair(int alg, const decoder_param &dp, void *stream);
         void maybe_autotune(int alg, const decoder_param &dp, uint64_t n_frames, void *stream);
+        // outcomes of the shape trials are remembered across processes: $LDPC_B200_TUNE_CACHE (a directory; "off" disables) or
+        // ~/.cache/libldpc_b200, one small text file per (code, device)
+        std::string tune_cache_file();
+        void tune_cache_load();
+        void tune_cache_store();
+        bool tune_cache_loaded_ = false;
+        std::string device_name_;
         void launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
         DeviceLayout &device_layout(int fpc, int threads, bool idx16);
         void ensure_state(size_t bytes, void *stream);
@@ -131,6 +148,8 @@ namespace b200
         std::unique_ptr<BecSliceLayout> bs_layout_;
         uint8_t *d_bs_tx_flag_ = nullptr;
         unsigned long long *d_counters_ = nullptr;
+        unsigned long long *d_round_[2] = {nullptr, nullptr}, *h_round_[2] = {nullptr, nullptr}; // sweep rounds in flight
+        void *ev_round_[2] = {nullptr, nullptr}, *ev_round0_[2] = {nullptr, nullptr}, *ev_rdone_[2] = {nullptr, nullptr};
         unsigned char *d_state_ = nullptr;
         size_t state_bytes_ = 0;
         void *ev_state_ = nullptr; // recorded after every launch that uses the state block

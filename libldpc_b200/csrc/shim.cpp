@@ -433,6 +433,14 @@ extern "C"
         });
     }
 
+    int ldpc_b200_fp64_probe(ldpc_b200_ctx *ctx, double *ginst_per_s)
+    {
+        return guarded([&] {
+            if (!ctx || !ginst_per_s) throw std::runtime_error("null argument");
+            *ginst_per_s = ctx->eng->fp64_probe();
+        });
+    }
+
     int ldpc_b200_get_stats(const ldpc_b200_ctx *ctx, ldpc_b200_stats *s)
     {
         return guarded([&] {

@@ -1,8 +1,8 @@
 // Monte-Carlo sweep driver with the reference's observable behaviour
 // (src/sim/ldpcsim.cpp:97-263): half-open x list, reversed order for BSC/BEC, per-point counters,
 // stop rule fec >= minFec || frames >= maxFrames || *stopFlag, results-file layout, console table,
-// sim_results_t fill.  Frames are processed in rounds on the GPU instead of one at a time; every
-// frame of a completed round is counted.  The frame -> Philox substream mapping depends only on
+// sim_results_t fill.  Frames are processed in (pipelined) rounds on the GPU instead of one at a time; every
+// frame of every launched round is counted.  The frame -> Philox substream mapping depends only on
 // (seed, point, global frame index), and each round's frame range is split contiguously over
 // `world` ranks, so the totals do not depend on the number of GPUs.
 #include <algorithm>
@@ -44,31 +44,59 @@ namespace b200
             std::cout << "========+================+=========+============+============+===========+==============" << std::endl;
         }
 
-        const uint64_t round0 = 8192, round_cap = 1ull << 22;
+        // Rounds.  A round is a contiguous range of global frame indices, split contiguously over the ranks.  Its size is a
+        // multiple of 9472 = 148 x 64 frames — whole waves of every persistent-grid shape of the kernels (148 or 296 CTAs x 2 ... 16
+        // frames) for 1, 2, 4 or 8 ranks — doubling while no error has been seen and then steered towards the remaining error
+        // budget.  The rounds are PIPELINED: round k+1 is issued before the counters of round k are read (two slots on the
+        // engine's stream), so the device never waits for the host, the all-reduce or the results file; the stop rule therefore
+        // acts one round late and every frame of every issued round is counted (bounded overshoot, unbiased).  The schedule
+        // depends only on reduced counters — not on the number of ranks or shards, the kernel shape or who processes the
+        // frames (GPU launch or injected callback) — so 1 GPU and N GPUs produce the same counters.
+        const bool pipelined = round_fn == nullptr;
+        if (pipelined && ch != "BEC") eng.prepare(dp, max_frames); // the one-off shape trial (large jobs only)
+        const uint64_t wave = 9472;
+        auto whole_waves = [&](uint64_t n) { return std::max<uint64_t>((n + wave / 2) / wave, 1) * wave; };
+        const uint64_t round0 = wave, round_cap = whole_waves(1ull << 22);
         for (size_t i = 0; i < xs.size(); ++i)
         {
-            uint64_t fec = 0, bec = 0, frames = 0, iters = 0, cursor = 0;
+            uint64_t fec = 0, bec = 0, frames = 0, iters = 0, cursor = 0; // cursor: frames launched so far
             uint64_t round = round0;
             const auto t0 = std::chrono::high_resolution_clock::now();
-            bool stop = false;
-            while (!stop)
+            bool stop = false, stopped = false;
+            struct Pending { bool live = false; uint64_t n_this = 0, lo = 0, hi = 0; } pend[2];
+            int k = 0;
+            auto launch_round = [&](int slot) -> bool
+            { // launches the next round into `slot` unless the frame budget is used up
+                const uint64_t n_this = std::min<uint64_t>(round, max_frames > cursor ? max_frames - cursor : 0);
+                if (n_this == 0) return false;
+                Pending &pd = pend[slot];
+                pd.live = true;
+                pd.n_this = n_this;
+                pd.lo = cursor + n_this * (uint64_t)rank / (uint64_t)world;
+                pd.hi = cursor + n_this * (uint64_t)(rank + 1) / (uint64_t)world;
+                cursor += n_this;
+                if (pipelined && pd.hi > pd.lo) eng.round_launch(slot, dp, ch, xs[i], cp.seed, (uint32_t)i, pd.lo, pd.hi - pd.lo);
+                return true;
+            };
+            launch_round(0);
+            while (pend[k & 1].live)
             {
-                const uint64_t n_this = std::min<uint64_t>(round, max_frames > frames ? max_frames - frames : 0);
-                if (n_this == 0) break;
-                const uint64_t lo = cursor + n_this * (uint64_t)rank / (uint64_t)world;
-                const uint64_t hi = cursor + n_this * (uint64_t)(rank + 1) / (uint64_t)world;
+                Pending &pd = pend[k & 1];
+                // keep the device busy: the following round goes out before this one is read (not known to be needed yet)
+                if (!stop) launch_round((k + 1) & 1);
                 uint64_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (hi > lo)
+                if (pd.hi > pd.lo)
                 {
                     if (round_fn)
                     {
-                        if (round_fn((uint32_t)i, xs[i], lo, hi - lo, c, user) != 0) throw std::runtime_error("round callback failed");
+                        if (round_fn((uint32_t)i, xs[i], pd.lo, pd.hi - pd.lo, c, user) != 0) throw std::runtime_error("round callback failed");
                     }
-                    else eng.sim_point(dp, ch, xs[i], cp.seed, (uint32_t)i, lo, hi - lo, c, nullptr);
+                    else eng.round_collect(k & 1, c);
                 }
+                pd.live = false;
                 c[5] = (stop_flag && *stop_flag) ? 1 : 0;
                 if (world > 1) allreduce(c, 8, user);
-                cursor += n_this;
+                stopped = stopped || c[5] != 0; // the REDUCED flag: every rank leaves the sweep at the same place
                 fec += c[0]; bec += c[1]; frames += c[2]; iters += c[3];
                 const bool new_errors = c[0] > 0;
                 if (new_errors)
@@ -104,16 +132,17 @@ namespace b200
                         results->frames[i] = frames;
                     }
                 }
-                stop = (fec >= min_fec) || (frames >= max_frames) || c[5]; // ldpcsim.cpp:255
-                if (fec == 0) round = std::min(round * 2, round_cap);
+                stop = stop || (fec >= min_fec) || (frames >= max_frames) || stopped; // ldpcsim.cpp:255
+                if (fec == 0) round = std::min(whole_waves(round * 2), round_cap);
                 else
                 {
                     const double need = (double)(min_fec > fec ? min_fec - fec : 0) * ((double)frames / (double)fec) * 1.2;
-                    round = (uint64_t)std::min<double>(std::max<double>(need, (double)round0), (double)round_cap);
+                    round = whole_waves((uint64_t)std::min<double>(std::max<double>(need, (double)round0), (double)round_cap));
                 }
+                ++k;
             }
             if (lead && !quiet) printf("\n");
-            if (stop_flag && *stop_flag) break;
+            if (stopped) break;
         }
         return 0;
     }

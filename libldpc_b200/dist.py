@@ -18,13 +18,23 @@ def shard_range(frame0, n_frames, rank, world):
 
 def make_allreduce(device=None, group=None):
     """Returns a Python callable (values_ptr, n, user) -> None summing a uint64 array over ranks."""
+    buf = {}
+
     def _allreduce(ptr, n, _user):
-        arr = np.ctypeslib.as_array(ptr, shape=(n,))
-        t = torch.from_numpy(arr.astype(np.int64))
+        # the sweep driver's rounds are pipelined (the next round is already running on the GPU while this is called), so this
+        # small host round trip is off the device's critical path; the staging tensors are allocated once
+        arr = np.ctypeslib.as_array(ptr, shape=(n,)).view(np.int64)
+        if n not in buf:
+            host = torch.empty(n, dtype=torch.int64, pin_memory=device is not None)
+            buf[n] = (host, torch.empty(n, dtype=torch.int64, device=device) if device is not None else host)
+        host, t = buf[n]
+        host.numpy()[:] = arr
         if device is not None:
-            t = t.to(device)
+            t.copy_(host, non_blocking=True)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        arr[:] = t.cpu().numpy().astype(np.uint64)
+        if device is not None:
+            host.copy_(t)
+        arr[:] = host.numpy()
     return _allreduce
 
 

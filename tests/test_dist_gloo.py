@@ -42,8 +42,12 @@ def _run(world, tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT, h=H_FILE, out=str(tmp_path / "res_w")))
     procs = []
+    import socket
+    with socket.socket() as sk:          # a free port per run (a fixed one can linger in TIME_WAIT between the two runs)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     for r in range(world):
-        env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", OMP_NUM_THREADS="2")
+        env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = []
     for p in procs:
