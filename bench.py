@@ -35,7 +35,7 @@ METRIC = "decoded coded Gb/s @50 iters"
 UNIT = "Gb/s"
 WORKLOAD = ("h.txt n=1024 k=128 (1152x1024, nnz 3456), AWGN Es/sigma^2=-4.5 dB, BP_MS min-sum, -i 50, "
             "fixed 50 iterations/frame (--no-early-term)")
-FP64_PER_BOXPLUS = 87                    # FP64 instructions of one pairwise box-plus in the kernel's SASS (profiles/r1/ncu_bp_smem_v2_summary.txt)
+FP64_PER_BOXPLUS = 50                    # FP64 instructions of one pairwise box-plus (fallback; the per-code figures come from ncu, profiles/roofline_traffic.json)
 I8_SCALE = 0.25                          # LLR = int8 * 0.25 on the narrow e2e path (exact in double)
 
 
@@ -225,11 +225,15 @@ def run_configs(api, smem_peak, fp64_peak, hbm_peak, traffic):
             e.update(extra)
         out[name] = e
 
-    def fp64_block(ctx, edge_it, ms):
-        per_edge_it = FP64_PER_BOXPLUS * boxplus_per_iteration(ctx.nnz, ctx.mc) / ctx.nnz + 2.0
+    def fp64_block(ctx, edge_it, ms, key):
+        # FP64 instructions the kernel executes per edge-iteration on this code: counted by ncu (smsp__inst_executed_pipe_fp64.sum of
+        # one launch, profiles/traffic.py); the formula is the fallback when that file is missing
+        per_edge_it = traffic.get("_fp64_thread_instructions_per_edge_iteration", {}).get(
+            key, FP64_PER_BOXPLUS * boxplus_per_iteration(ctx.nnz, ctx.mc) / ctx.nnz + 2.0)
         ach = edge_it * per_edge_it / (ms * 1e-3) / 1e9
         return {"fp64_pipe": {"bound": "fp64_pipe", "achieved": ach, "peak": fp64_peak, "unit": "G thread-instructions/s", "frac": ach / fp64_peak,
                               "fp64_instructions_per_edge_iteration": per_edge_it,
+                              "note": "pipe utilisation: FP64 instructions the kernel executes (ncu count per edge-iteration x edge-iterations of this run) over the measured DFMA issue rate",
                               "peak_source": "ldpc_b200_fp64_probe in this run (independent DFMA chains on every SM)"}}
 
     launches = 0
@@ -238,10 +242,10 @@ def run_configs(api, smem_peak, fp64_peak, hbm_peak, traffic):
     ctx.set_tuning(precision=api.F64)
     ms, fr, ed, st, l = measure(ctx, "AWGN", [SNR_DB], "BP", False, 148 * 4 * 64)
     launches += l
-    entry("C1_bp_fixed50", ctx, ms, fr, ed, st, "smem", "configs[0] h.txt, AWGN -4.5 dB, BP (sum-product, fp64), 50 fixed iterations", fp64_block(ctx, ed, ms))
+    entry("C1_bp_fixed50", ctx, ms, fr, ed, st, "smem", "configs[0] h.txt, AWGN -4.5 dB, BP (sum-product, fp64), 50 fixed iterations", fp64_block(ctx, ed, ms, "C1_bp_fixed50"))
     ms, fr, ed, st, l = measure(ctx, "AWGN", [0.0, 0.5, 1.0, 1.5, 2.0, 2.5, 3.0, 3.5], "BP", True, 148 * 4 * 256)
     launches += l
-    entry("C1_et_sweep", ctx, ms, fr, ed, st, "smem", "configs[0] h.txt, AWGN 0 ... 3.5 dB step 0.5 (8 points), BP, -i 50, early termination", fp64_block(ctx, ed, ms))
+    entry("C1_et_sweep", ctx, ms, fr, ed, st, "smem", "configs[0] h.txt, AWGN 0 ... 3.5 dB step 0.5 (8 points), BP, -i 50, early termination", fp64_block(ctx, ed, ms, "C1_bp_fixed50"))
     ms, fr, ed, st, l = measure(ctx, "AWGN", [-6.0, -5.5, -5.0, -4.5, -4.0, -3.5], "BP_MS", True, 148 * 4 * 256)
     launches += l
     entry("C2_et", ctx, ms, fr, ed, st, "smem", "configs[1] h.txt, AWGN -6 ... -3.5 dB step 0.5 (6 points), BP_MS, -i 50, early termination")
@@ -266,7 +270,7 @@ def run_configs(api, smem_peak, fp64_peak, hbm_peak, traffic):
     ms, fr, ed, st, l = measure(ctx, "AWGN", [1.0], "BP", False, 2048)
     launches += l
     entry("C4_dvbs2_bp_noet", ctx, ms, fr, ed, st, "hbm", "configs[3] DVB-S2-shaped IRA code n=64800 r=1/2 (nnz 226799), AWGN +1 dB, BP fp64, --no-early-term",
-          fp64_block(ctx, ed, ms))
+          fp64_block(ctx, ed, ms, "C4_dvbs2_bp_noet"))
     ctx.close()
     return out, launches
 

@@ -127,7 +127,14 @@ typedef struct
                              small enough for them */
     int zero_codeword;    /* 0 (default) = with a generator matrix loaded the sweep transmits random codewords like the
                              reference's -G; 1 = always the all-zero codeword */
+    int schedule;         /* LDPC_B200_FLOODING (default: the reference's schedule, src/decoding/decoder.cpp:11-78) | LDPC_B200_LAYERED
+                             (opt-in: the legacy tree's layer loop, gpu/device/kernel.cpp:52-75; results differ from the flooding
+                             reference by design; AWGN / BSC sweeps with the all-zero codeword and the batch decode call) */
+    int layered_ms_scale64; /* layered schedule, BP_MS only: check outputs are multiplied by this / 64 (normalised min-sum; 0 or 64 = the
+                               reference's plain min-sum, 48 = 0.75).  Plain min-sum is unstable under the layered schedule on
+                               codes with many punctured / high-degree columns (profiles/r2/layered.md) */
 } ldpc_b200_tuning;
+enum { LDPC_B200_FLOODING = 0, LDPC_B200_LAYERED = 1 };
 
 LDPC_B200_API const char *ldpc_b200_last_error(void);
 LDPC_B200_API const char *ldpc_b200_version(void);
@@ -151,6 +158,15 @@ LDPC_B200_API int ldpc_b200_get_tuning(const ldpc_b200_ctx *ctx, ldpc_b200_tunin
  * never block and use the cached outcome or the default shape.  Call ldpc_b200_prepare once (blocking) to have the trial
  * done before a stream of asynchronous launches; n_frames = the size of the job (jobs below ~20000 frames skip the trial). */
 LDPC_B200_API int ldpc_b200_prepare(ldpc_b200_ctx *ctx, decoder_param dp, uint64_t n_frames);
+
+/* Layers of the layered schedule: n_layers lists of check indices (layer l = layer_check[layer_ptr[l] .. layer_ptr[l+1])), every
+ * check in exactly one layer, no two checks of a layer sharing a variable.  n_layers = 0 selects the built-in first-fit layering
+ * (one layer per block row on quasi-cyclic codes).  ldpc_b200_load_layers reads the legacy tree's layer file (gpu/ldpc/ldpc.cpp:
+ * 111-138: "nl: N", then per layer "cn[i]: W" and W check indices).  ldpc_b200_get_layers returns the layering in use
+ * (layer_of[mc]; the return value is the number of layers, negative on failure). */
+LDPC_B200_API int ldpc_b200_set_layers(ldpc_b200_ctx *ctx, int n_layers, const int *layer_ptr, const int *layer_check);
+LDPC_B200_API int ldpc_b200_load_layers(ldpc_b200_ctx *ctx, const char *layer_file);
+LDPC_B200_API int ldpc_b200_get_layers(ldpc_b200_ctx *ctx, int *layer_of /*[mc]*/);
 
 /* host-side views of the loaded code (file order; sizes from ldpc_b200_info) */
 LDPC_B200_API int ldpc_b200_get_edges(const ldpc_b200_ctx *ctx, int *rows /*[nnz]*/, int *cols /*[nnz]*/);

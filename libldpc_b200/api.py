@@ -39,7 +39,7 @@ class code_info(ct.Structure):
 
 
 class tuning(ct.Structure):
-    _fields_ = [(k, ct.c_int) for k in ("precision", "residency", "frames_per_cta", "threads_per_cta", "ctas", "bec_deg1_compat", "tmem", "idx16", "zero_codeword")]
+    _fields_ = [(k, ct.c_int) for k in ("precision", "residency", "frames_per_cta", "threads_per_cta", "ctas", "bec_deg1_compat", "tmem", "idx16", "zero_codeword", "schedule", "layered_ms_scale64")]
 
 
 class error_record(ct.Structure):  # ldpc_b200_error_record
@@ -57,6 +57,7 @@ ROUND_FN = ct.CFUNCTYPE(ct.c_int, ct.c_uint32, ct.c_double, ct.c_uint64, ct.c_ui
 F64, F32 = 0, 1
 AUTO, SMEM, GLOBAL = 0, 1, 2
 LLR_F64, LLR_F32, LLR_I8 = 0, 1, 2
+FLOODING, LAYERED = 0, 1
 
 REFERENCE_SYMBOLS = ("ldpc_setup", "simulate", "calculate_rank", "encode", "decode", "syndrome")
 HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device_count", "ldpc_b200_open", "ldpc_b200_close",
@@ -64,7 +65,7 @@ HANDLE_SYMBOLS = ("ldpc_b200_last_error", "ldpc_b200_version", "ldpc_b200_device
                   "ldpc_b200_get_puncture", "ldpc_b200_get_layout", "ldpc_b200_rank", "ldpc_b200_encode", "ldpc_b200_syndrome",
                   "ldpc_b200_decode_batch", "ldpc_b200_decode_batch_device", "ldpc_b200_decode_bec_batch", "ldpc_b200_channel",
                   "ldpc_b200_sim_point", "ldpc_b200_sim_point_async", "ldpc_b200_simulate", "ldpc_b200_simulate_ex", "ldpc_b200_get_stats",
-                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe", "ldpc_b200_sim_point_log", "ldpc_b200_prepare", "ldpc_b200_decode_batch_ex", "ldpc_b200_decode_batch_device_ex", "ldpc_b200_get_bec_layout", "ldpc_b200_fp64_probe")
+                  "ldpc_b200_reset_stats", "ldpc_b200_smem_probe", "ldpc_b200_sim_point_log", "ldpc_b200_prepare", "ldpc_b200_decode_batch_ex", "ldpc_b200_decode_batch_device_ex", "ldpc_b200_get_bec_layout", "ldpc_b200_fp64_probe", "ldpc_b200_set_layers", "ldpc_b200_load_layers", "ldpc_b200_get_layers")
 
 _lib = None
 
@@ -116,6 +117,9 @@ def load_library(path=None):
     L.ldpc_b200_get_puncture.argtypes = [vp, iptr, iptr]
     L.ldpc_b200_get_layout.argtypes = [vp, iptr, iptr, iptr, iptr, iptr]
     L.ldpc_b200_get_bec_layout.argtypes = [vp, iptr, iptr]
+    L.ldpc_b200_set_layers.argtypes = [vp, ct.c_int, iptr, iptr]
+    L.ldpc_b200_load_layers.argtypes = [vp, ct.c_char_p]
+    L.ldpc_b200_get_layers.argtypes = [vp, iptr]
     L.ldpc_b200_rank.argtypes = [vp]
     L.ldpc_b200_encode.argtypes = [vp, bptr, bptr]
     L.ldpc_b200_syndrome.argtypes = [vp, bptr, bptr]
@@ -203,6 +207,27 @@ class Context:
         n = ct.c_int()
         self._check(self.lib.ldpc_b200_get_bec_layout(self._h, _p(es, ct.c_int), ct.byref(n)))
         return es, n.value
+
+    def set_layers(self, layers=None):
+        """Layers of the layered schedule: a list of check-index lists, or None for the built-in first-fit layering."""
+        if not layers:
+            self._check(self.lib.ldpc_b200_set_layers(self._h, 0, None, None))
+            return
+        ptr = np.zeros(len(layers) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(l) for l in layers])
+        chk = np.ascontiguousarray(np.concatenate([np.asarray(l, np.int32) for l in layers]), np.int32)
+        self._check(self.lib.ldpc_b200_set_layers(self._h, len(layers), _p(ptr, ct.c_int), _p(chk, ct.c_int)))
+
+    def load_layers(self, path):
+        self._check(self.lib.ldpc_b200_load_layers(self._h, str(path).encode()))
+
+    def layers(self):
+        """The layering in use as a list of check-index arrays."""
+        lo = np.zeros(self.mc, np.int32)
+        n = self.lib.ldpc_b200_get_layers(self._h, _p(lo, ct.c_int))
+        if n < 0:
+            raise RuntimeError(self.lib.ldpc_b200_last_error().decode())
+        return [np.nonzero(lo == l)[0].astype(np.int32) for l in range(n)]
 
     def set_tuning(self, **kw):
         t = tuning()

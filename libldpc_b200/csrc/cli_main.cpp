@@ -45,6 +45,9 @@ namespace
         "--precision         \tB200 only: message arithmetic \"f64\" (bit-exact with the reference, default) or \"f32\"\n"
         "--device            \tB200 only: CUDA device index (Default: 0)\n"
         "--gpus              \tB200 only: number of GPUs to shard every round of frames over, starting at --device (Default: 1, 0 = all)\n"
+        "--schedule          \tB200 only: \"flooding\" (the reference's schedule, default) or \"layered\" (opt-in; results differ by design)\n"
+        "--ms-scale          \tB200 only: with --schedule layered and BP_MS: normalisation factor of the check outputs in 1/64 steps (Default: 1 = plain min-sum)\n"
+        "--layers            \tB200 only: layer file for --schedule layered (legacy format: nl: N / cn[i]: W / W check indices); default: built-in layering\n"
         "--devices           \tB200 only: explicit device list for the shards, e.g. 0,1,2,3 (an index may repeat: several shards on one GPU)\n";
 
     bool looks_numeric(const std::string &s)
@@ -122,7 +125,8 @@ int main(int argc, char **argv)
     unsigned long seed = 0, max_frames = (unsigned long)10e9, fec = 50;
     bool early_term = true;
     int device = 0, gpus = 1;
-    std::string device_list;
+    std::string device_list, schedule = "flooding", layer_file;
+    double ms_scale = 1.0;
     std::vector<std::string> pos;
     try
     {
@@ -149,6 +153,9 @@ int main(int argc, char **argv)
             else if (a == "--device") device = std::stoi(value());
             else if (a == "--gpus") gpus = std::stoi(value());
             else if (a == "--devices") device_list = value();
+            else if (a == "--schedule") schedule = value();
+            else if (a == "--layers") layer_file = value();
+            else if (a == "--ms-scale") ms_scale = std::stod(value());
             else if (a.size() > 1 && a[0] == '-' && !looks_numeric(a)) throw std::runtime_error("Unknown argument: " + a);
             else pos.push_back(a);
         }
@@ -157,6 +164,7 @@ int main(int argc, char **argv)
         const double snr[3] = {std::stod(pos[2]), std::stod(pos[3]), std::stod(pos[4])};
         if (snr[0] > snr[1]) throw std::runtime_error("snr min > snr max");
         if (precision != "f64" && precision != "f32") throw std::runtime_error("--precision must be f64 or f32");
+        if (schedule != "flooding" && schedule != "layered") throw std::runtime_error("--schedule must be flooding or layered");
 
         std::vector<int> devices;
         if (!device_list.empty()) devices = parse_devices(device_list);
@@ -177,7 +185,15 @@ int main(int argc, char **argv)
         ldpc_b200_tuning tn;
         ldpc_b200_get_tuning(ctx, &tn);
         tn.precision = precision == "f32" ? LDPC_B200_F32 : LDPC_B200_F64;
+        tn.schedule = schedule == "layered" ? LDPC_B200_LAYERED : LDPC_B200_FLOODING;
+        if (tn.schedule == LDPC_B200_LAYERED) tn.zero_codeword = 1; // the layered sweep transmits the all-zero word
+        tn.layered_ms_scale64 = (int)(ms_scale * 64.0 + 0.5);
         ldpc_b200_set_tuning(ctx, &tn);
+        if (!layer_file.empty() && ldpc_b200_load_layers(ctx, layer_file.c_str()) != 0)
+        {
+            std::cout << "Error: layers: " << ldpc_b200_last_error() << std::endl;
+            return EXIT_FAILURE;
+        }
         ldpc_b200_code_info H;
         ldpc_b200_info(ctx, &H);
         std::vector<int> puncture(std::max(H.n_punct, 1)), shorten(std::max(H.n_short, 1));
@@ -205,6 +221,8 @@ int main(int argc, char **argv)
         std::cout << "== Decoder Parameters\n Type: " << dp.type << "\n Iterations: " << dp.iterations << "\n Early Termination: " << dp.earlyTerm << "\n";
         std::cout << "== Channel Parameters\n Type: " << cp.type << "\n Seed: " << cp.seed << "\n Range: Min: " << cp.xRange[0] << ", Max: " << cp.xRange[1]
                   << ", Step: " << cp.xRange[2] << "\n";
+        if (tn.schedule == LDPC_B200_LAYERED)
+            std::cout << "== Schedule\n layered (" << ldpc_b200_get_layers(ctx, nullptr) << " layers" << (layer_file.empty() ? ", built-in layering" : (", " + layer_file)) << ")\n";
         std::cout << "== Simulation Parameters\n Threads: " << sp.threads << "\n FEC: " << sp.fec << "\n Max Frames: " << sp.maxFrames
                   << "\n Output File: " << sp.resultFile << "\n" << std::endl;
         std::cout << bar << std::endl;
@@ -219,6 +237,7 @@ int main(int argc, char **argv)
                 ldpc_b200_ctx *c = ldpc_b200_open(pos[0].c_str(), gen.c_str(), devices[g]);
                 if (!c) { std::cout << "Error: ldpc_code(): " << ldpc_b200_last_error() << std::endl; return EXIT_FAILURE; }
                 ldpc_b200_set_tuning(c, &tn);
+                if (!layer_file.empty()) ldpc_b200_load_layers(c, layer_file.c_str());
                 m.ctxs.push_back(c);
             }
             std::cout << "GPUs: " << devices.size() << " shards on devices ";

@@ -503,4 +503,149 @@ namespace b200
         col_slot.resize(code.nnz);
         for (int q = 0; q < code.nnz; ++q) { row_slot[q] = (uint16_t)slot[code.row_edge[q]]; col_slot[q] = (uint16_t)slot[code.col_edge[q]]; }
     }
+
+    // ------------------------------------------------------------------------------------------
+    // layered schedule
+    // ------------------------------------------------------------------------------------------
+    std::vector<std::vector<int>> auto_layers(const HostCode &code)
+    {
+        std::vector<std::vector<int>> layers;
+        std::vector<std::vector<uint8_t>> occ; // occ[l][v]: variable v is used by a check of layer l
+        for (int i = 0; i < code.mc; ++i)
+        {
+            size_t l = 0;
+            for (;; ++l)
+            {
+                if (l == layers.size()) { layers.emplace_back(); occ.emplace_back(code.nc, 0); }
+                bool clash = false;
+                for (int q = code.row_ptr[i]; q < code.row_ptr[i + 1] && !clash; ++q) clash = occ[l][code.e_col[code.row_edge[q]]] != 0;
+                if (!clash) break;
+            }
+            for (int q = code.row_ptr[i]; q < code.row_ptr[i + 1]; ++q) occ[l][code.e_col[code.row_edge[q]]] = 1;
+            layers[l].push_back(i);
+        }
+        return layers;
+    }
+
+    std::vector<std::vector<int>> read_layer_file(const std::string &path)
+    {
+        std::ifstream f(path);
+        if (!f.good()) throw std::runtime_error("can not open layer file for reading");
+        std::string tok;
+        auto after_colon = [&](const char *what) -> long
+        { // "<key>: <value>"
+            std::string line;
+            while (std::getline(f, line))
+            {
+                const size_t c = line.find(':');
+                if (c == std::string::npos) continue;
+                return std::stol(line.substr(c + 1));
+            }
+            throw std::runtime_error(std::string("layer file: missing ") + what);
+        };
+        const long nl = after_colon("nl");
+        if (nl < 1 || nl > (1 << 20)) throw std::runtime_error("layer file: bad layer count");
+        std::vector<std::vector<int>> layers((size_t)nl);
+        for (long l = 0; l < nl; ++l)
+        {
+            const long w = after_colon("cn[i]");
+            if (w < 0) throw std::runtime_error("layer file: bad layer size");
+            layers[l].resize((size_t)w);
+            for (long k = 0; k < w; ++k)
+                if (!(f >> layers[l][k])) throw std::runtime_error("layer file: truncated layer");
+            std::string rest;
+            std::getline(f, rest);
+        }
+        return layers;
+    }
+
+    void validate_layers(const HostCode &code, const std::vector<std::vector<int>> &layers)
+    {
+        std::vector<int> seen(code.nc, -1), used(code.mc, 0);
+        for (size_t l = 0; l < layers.size(); ++l)
+            for (int chk : layers[l])
+            {
+                if (chk < 0 || chk >= code.mc) throw std::runtime_error("layers: check index out of range");
+                if (used[chk]++) throw std::runtime_error("layers: a check appears twice");
+                for (int q = code.row_ptr[chk]; q < code.row_ptr[chk + 1]; ++q)
+                {
+                    const int v = code.e_col[code.row_edge[q]];
+                    if (seen[v] == (int)l)
+                        throw std::runtime_error("layers: two checks of one layer share a variable (the in-place layered update needs disjoint checks per layer)");
+                    seen[v] = (int)l;
+                }
+            }
+        for (int i = 0; i < code.mc; ++i)
+            if (!used[i]) throw std::runtime_error("layers: a check belongs to no layer");
+    }
+
+    void LayeredLayout::build(const HostCode &code, const std::vector<std::vector<int>> &layers, int lanes_, int threads_)
+    {
+        if (lanes_ != 1 && lanes_ != 2 && lanes_ != 4) throw std::runtime_error("lanes per node must be 1, 2 or 4");
+        if (threads_ < 32 || threads_ > 512 || threads_ % 32) throw std::runtime_error("threads_per_cta must be a multiple of 32 <= 512");
+        if (code.max_cn_degree > 64) throw std::runtime_error("check degree > 64 not supported");
+        if (code.min_cn_degree < 2) throw std::runtime_error("check nodes of degree < 2 are not supported (undefined in the reference)");
+        validate_layers(code, layers);
+        lanes = lanes_; threads = threads_; warps = threads / 32; npw = 32 / lanes; n_layers = (int)layers.size();
+        struct Seg { int deg, cnt, ntasks; uint32_t base; };
+        std::vector<std::vector<Seg>> lists((size_t)n_layers * warps);
+        std::vector<std::vector<std::vector<int>>> nodes((size_t)n_layers * warps); // per list, per task: the checks
+        edge_slot.assign(code.nnz, -1);
+        uint32_t next = 0;
+        max_segs = 1;
+        for (int l = 0; l < n_layers; ++l)
+        {
+            std::vector<int> order(layers[l]);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                return code.row_ptr[a + 1] - code.row_ptr[a] > code.row_ptr[b + 1] - code.row_ptr[b]; });
+            // tasks of npw equal-degree checks, dealt to the least loaded warp (load in edges)
+            std::vector<long> load(warps, 0);
+            for (size_t i = 0; i < order.size();)
+            {
+                const int deg = code.row_ptr[order[i] + 1] - code.row_ptr[order[i]];
+                std::vector<int> task;
+                while (i < order.size() && code.row_ptr[order[i] + 1] - code.row_ptr[order[i]] == deg && (int)task.size() < npw) task.push_back(order[i++]);
+                const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                load[w] += deg;
+                auto &lst = lists[(size_t)l * warps + w];
+                auto &nds = nodes[(size_t)l * warps + w];
+                if (!lst.empty() && lst.back().deg == deg && lst.back().cnt == (int)task.size() && lst.back().cnt == npw && lst.back().ntasks < 65535) ++lst.back().ntasks;
+                else lst.push_back({deg, (int)task.size(), 1, 0u});
+                nds.push_back(std::move(task));
+            }
+            for (int w = 0; w < warps; ++w)
+            {
+                auto &lst = lists[(size_t)l * warps + w];
+                auto &nds = nodes[(size_t)l * warps + w];
+                max_segs = std::max<int>(max_segs, (int)lst.size() + 1);
+                size_t t0 = 0;
+                for (Seg &sg : lst)
+                {
+                    sg.base = next;
+                    for (int t = 0; t < sg.ntasks; ++t)
+                        for (int j = 0; j < (int)nds[t0 + t].size(); ++j)
+                        {
+                            const int row = nds[t0 + t][j];
+                            for (int k = 0; k < sg.deg; ++k)
+                                edge_slot[code.row_edge[code.row_ptr[row] + k]] = (int)(sg.base + ((uint32_t)t * sg.deg + k) * npw + j);
+                        }
+                    next += (uint32_t)sg.ntasks * sg.deg * npw;
+                    t0 += sg.ntasks;
+                }
+            }
+        }
+        n_slots = (int)next;
+        if ((size_t)n_slots * 16 * lanes >= (1ull << 32) || (size_t)code.nc * 16 * lanes >= (1ull << 32)) throw std::runtime_error("layout too large");
+        idx.assign(std::max(n_slots, 1), 0);
+        for (int e = 0; e < code.nnz; ++e) idx[edge_slot[e]] = (uint32_t)code.e_col[e] * (uint32_t)(16 * lanes);
+        seg.assign((size_t)4 * n_layers * warps * max_segs, 0);
+        for (size_t li = 0; li < lists.size(); ++li)
+            for (size_t sgi = 0; sgi < lists[li].size(); ++sgi)
+            {
+                const Seg &g = lists[li][sgi];
+                uint32_t *d = &seg[4 * (li * max_segs + sgi)];
+                d[0] = (uint32_t)g.deg | ((uint32_t)g.cnt << 8) | ((uint32_t)g.ntasks << 16);
+                d[1] = g.base;
+            }
+    }
 } // namespace b200

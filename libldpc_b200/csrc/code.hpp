@@ -116,4 +116,23 @@ namespace b200
         std::vector<int> edge_slot;            // [nnz] file-order edge -> slot
         void build(const HostCode &code);
     };
+
+    // Layered schedule (layered.cuh).  `layers` partitions the checks; no two checks of a layer may share a variable.
+    // Per (layer, warp) a run-length list of warp tasks (npw checks of equal degree each); message slots are numbered in list
+    // order, slot of edge k of node j of task t = segment base + (t*deg + k)*npw + j; idx[slot] = byte offset of the posterior
+    // record the edge gathers (variable id * 16 * lanes).
+    struct LayeredLayout
+    {
+        int lanes = 0, threads = 0, warps = 0, npw = 0, n_layers = 0, max_segs = 0, n_slots = 0;
+        std::vector<uint32_t> seg; // [(layer*warps + warp)*max_segs + s][4] = {degree | nodes << 8 | tasks << 16, first slot, 0, 0}
+        std::vector<uint32_t> idx; // [n_slots]
+        std::vector<int> edge_slot;
+        void build(const HostCode &code, const std::vector<std::vector<int>> &layers, int lanes, int threads);
+    };
+    // first-fit layers: check i joins the first layer none of whose checks shares a variable with it
+    std::vector<std::vector<int>> auto_layers(const HostCode &code);
+    // legacy layer file (gpu/ldpc/ldpc.cpp:111-138): "nl: N", then per layer "cn[i]: W" followed by W check indices
+    std::vector<std::vector<int>> read_layer_file(const std::string &path);
+    // throws unless `layers` is a partition of the checks in which no layer holds two checks sharing a variable
+    void validate_layers(const HostCode &code, const std::vector<std::vector<int>> &layers);
 } // namespace b200

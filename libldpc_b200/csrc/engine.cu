@@ -13,6 +13,7 @@
 #include "tile_launch.cuh"
 #include "bec_kernel.cuh"
 #include "bec_slice.cuh"
+#include "layered.cuh"
 
 namespace b200
 {
@@ -33,6 +34,13 @@ namespace b200
         {
             cudaFree(cn_desc); cudaFree(vn_desc); cudaFree(cn_col); cudaFree(vn_slot); cudaFree(vn_id);
         }
+    };
+
+    struct DeviceLayered
+    {
+        uint32_t *seg = nullptr, *idx = nullptr;
+        const LayeredLayout *host = nullptr;
+        ~DeviceLayered() { cudaFree(seg); cudaFree(idx); }
     };
 
     struct DeviceSegLayout
@@ -121,6 +129,7 @@ namespace b200
         cudaSetDevice(device);
         dev_layouts_.clear();
         dev_seg_layouts_.clear();
+        dev_lay_.clear();
         cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
         if (ev_state_) cudaEventDestroy((cudaEvent_t)ev_state_);
         cudaFree(d_g_col_ptr_); cudaFree(d_g_row_);
@@ -604,6 +613,11 @@ namespace b200
             return;
         }
 
+        if (tuning.schedule == LDPC_B200_LAYERED)
+        {
+            launch_layered(dp, src, sink, n_frames, s);
+            return;
+        }
         const int alg = minsum ? ALG_MS : ALG_BP;
         // the one-off shape trials time kernels and wait for them: only on the blocking entry points.  The asynchronous ones
         // (caller stream, possibly under graph capture) use the cached outcome or the default shape.
@@ -884,6 +898,104 @@ namespace b200
         force_pair_ = -1;
         if (std::getenv("LDPC_B200_DEBUG")) fprintf(stderr, "[autotune_pair] one CTA/SM %.1f frames/ms, two CTAs/SM %.1f frames/ms\n", rate[0], rate[1]);
         pair_tuned_[key] = rate[1] > 1.01 * rate[0] ? 1 : 0;
+    }
+
+    void Engine::set_layers(std::vector<std::vector<int>> layers)
+    {
+        if (!layers.empty()) validate_layers(H, layers);
+        layers_ = std::move(layers);
+        dev_lay_.clear();
+        lay_layouts_.clear();
+    }
+
+    const std::vector<std::vector<int>> &Engine::layers()
+    {
+        if (layers_.empty()) layers_ = auto_layers(H);
+        return layers_;
+    }
+
+    // Layered schedule (opt-in, tuning.schedule): layered.cuh.  Global residency, frames in lock step per CTA.
+    void Engine::launch_layered(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream)
+    {
+        cudaStream_t s = (cudaStream_t)stream;
+        if (src.d_llr_f32 || src.d_llr_i8 || sink.d_hard_bits) throw std::runtime_error("layered schedule: the narrow encodings are served by the flooding path only");
+        if (has_gen && !tuning.zero_codeword && src.kind != SRC_LLR)
+            throw std::runtime_error("layered schedule: sweeps transmit the all-zero codeword (set tuning.zero_codeword = 1 with a generator matrix loaded)");
+        const bool minsum = dp.type && std::string(dp.type) == "BP_MS";
+        const int vec = tuning.precision == LDPC_B200_F32 ? 4 : 2;
+        int lanes = 4;
+        if (tuning.frames_per_cta > 0)
+        {
+            if (tuning.frames_per_cta != 2 * vec && tuning.frames_per_cta != 4 * vec) throw std::runtime_error("layered schedule: frames_per_cta / vector width must be 2 or 4");
+            lanes = tuning.frames_per_cta / vec;
+        }
+        const int threads = tuning.threads_per_cta > 0 ? std::min(tuning.threads_per_cta, 512) : 256;
+        auto key = std::make_pair(lanes, threads);
+        auto it = dev_lay_.find(key);
+        if (it == dev_lay_.end())
+        {
+            auto l = std::make_unique<LayeredLayout>();
+            l->build(H, layers(), lanes, threads);
+            auto d = std::make_unique<DeviceLayered>();
+            d->host = l.get();
+            d->seg = upload(l->seg);
+            d->idx = upload(l->idx);
+            lay_layouts_[key] = std::move(l);
+            it = dev_lay_.emplace(key, std::move(d)).first;
+        }
+        const LayeredLayout &l = *it->second->host;
+        LayParams lp{};
+        lp.seg = it->second->seg; lp.idx = it->second->idx;
+        lp.n_layers = l.n_layers; lp.max_segs = l.max_segs; lp.n_slots = l.n_slots;
+        lp.nc = H.nc; lp.nct = H.nct(); lp.n_punct = (int)H.puncture.size(); lp.n_short = (int)H.shorten.size();
+        lp.tx_var = d_bit_pos_; lp.punct = d_punct_; lp.shorten = d_short_;
+        lp.max_iter = (int)dp.iterations; lp.early_term = dp.earlyTerm ? 1 : 0; lp.kind = src.kind;
+        lp.llr_in = src.d_llr;
+        if (src.kind == SRC_AWGN)
+        {
+            const double sigma2 = std::pow(10.0, -src.x / 10.0);
+            lp.sigma = std::sqrt(sigma2);
+            lp.llr_scale = 2.0 / sigma2;
+        }
+        else if (src.kind == SRC_BSC)
+        {
+            lp.delta = std::log((1 - src.x) / src.x);
+            double t = std::floor(src.x * 4294967296.0);
+            lp.thr = t <= 0 ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+        }
+        lp.ms_scale = (tuning.layered_ms_scale64 > 0 ? tuning.layered_ms_scale64 : 64) / 64.0;
+        lp.seed = src.seed; lp.point = src.point; lp.frame0 = src.frame0; lp.n_frames = n_frames;
+        lp.llr_out = sink.d_llr_out; lp.hard_out = sink.d_hard; lp.iters_out = sink.d_iters;
+        lp.counters = sink.d_counters ? sink.d_counters : d_counters_;
+        lp.err_log = sink.d_err_log; lp.err_count = sink.d_err_count; lp.err_cap = sink.err_cap;
+        const int fpc = lanes * vec;
+        int per_sm = 1;
+        {
+            const bool f32 = tuning.precision == LDPC_B200_F32;
+            per_sm = f32 ? (minsum ? layered_occupancy<float, ALG_MS>(lanes, threads) : layered_occupancy<float, ALG_BP>(lanes, threads))
+                         : (minsum ? layered_occupancy<double, ALG_MS>(lanes, threads) : layered_occupancy<double, ALG_BP>(lanes, threads));
+            if (per_sm < 1) throw std::runtime_error("layered kernel does not fit on this device");
+        }
+        int ctas = tuning.ctas > 0 ? tuning.ctas : sm_count_ * per_sm;
+        const uint64_t need = (n_frames + fpc - 1) / fpc;
+        if ((uint64_t)ctas > need) ctas = (int)std::max<uint64_t>(need, 1);
+        lp.state_stride = ((16 * (size_t)lanes * ((size_t)l.n_slots + (size_t)H.nc)) + 255) & ~(size_t)255;
+        ensure_state(lp.state_stride * ctas, s);
+        lp.state = d_state_;
+        if (tuning.precision == LDPC_B200_F32)
+        {
+            if (minsum) run_layered_kernel<float, ALG_MS>(lp, lanes, ctas, threads, s);
+            else run_layered_kernel<float, ALG_BP>(lp, lanes, ctas, threads, s);
+        }
+        else
+        {
+            if (minsum) run_layered_kernel<double, ALG_MS>(lp, lanes, ctas, threads, s);
+            else run_layered_kernel<double, ALG_BP>(lp, lanes, ctas, threads, s);
+        }
+        release_state(s);
+        stats.launches += 1;
+        stats.frames_per_cta = fpc; stats.threads_per_cta = threads; stats.ctas = ctas;
+        stats.residency = LDPC_B200_GLOBAL; stats.precision = tuning.precision; stats.smem_bytes = 0;
     }
 
     void Engine::launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream)

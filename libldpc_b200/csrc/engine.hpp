@@ -14,6 +14,7 @@
 
 namespace b200
 {
+    struct DeviceLayered;    // device-resident LayeredLayout (engine.cu; layered schedule)
     struct DeviceLayout;     // device-resident TileLayout (engine.cu; erasure decoder)
     struct DeviceSegLayout;  // device-resident SegLayout (engine.cu; tile4 kernel)
 
@@ -87,6 +88,10 @@ namespace b200
         // frames of one full wave of the persistent grid for this decoder type under the current tuning (rounds are sized in waves)
         uint64_t wave_frames(const decoder_param &dp, const std::string &channel);
 
+        // layered schedule: the layering in use (empty = built-in first-fit layering, made on first use)
+        void set_layers(std::vector<std::vector<int>> layers);
+        const std::vector<std::vector<int>> &layers();
+
         // sustained shared-memory read bandwidth of the device in GB/s (LDS.128 streaming from every SM)
         double smem_probe();
         // sustained FP64 instruction rate of the device in G thread-instructions/s (DFMA streaming from every SM)
@@ -119,6 +124,10 @@ namespace b200
         void tune_cache_store();
         bool tune_cache_loaded_ = false;
         std::string device_name_;
+        void launch_layered(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
+        std::vector<std::vector<int>> layers_;
+        std::map<std::pair<int, int>, std::unique_ptr<LayeredLayout>> lay_layouts_;
+        std::map<std::pair<int, int>, std::unique_ptr<DeviceLayered>> dev_lay_;
         void launch_bec(const decoder_param &dp, const FrameSource &src, const FrameSink &sink, uint64_t n_frames, void *stream);
         DeviceLayout &device_layout(int fpc, int threads, bool idx16);
         void ensure_state(size_t bytes, void *stream);

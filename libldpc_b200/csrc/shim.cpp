@@ -196,6 +196,8 @@ extern "C"
             if (!ctx || !t) throw std::runtime_error("null argument");
             if (t->precision != LDPC_B200_F64 && t->precision != LDPC_B200_F32) throw std::runtime_error("bad precision");
             if (t->residency < 0 || t->residency > 2) throw std::runtime_error("bad residency");
+            if (t->schedule != LDPC_B200_FLOODING && t->schedule != LDPC_B200_LAYERED) throw std::runtime_error("bad schedule");
+            if (t->layered_ms_scale64 < 0 || t->layered_ms_scale64 > 64) throw std::runtime_error("layered_ms_scale64 must be 0 .. 64");
             ctx->eng->tuning = *t;
         });
     }
@@ -214,6 +216,38 @@ extern "C"
             if (!ctx) throw std::runtime_error("null argument");
             ctx->eng->prepare(dp, n_frames);
         });
+    }
+
+    int ldpc_b200_set_layers(ldpc_b200_ctx *ctx, int n_layers, const int *layer_ptr, const int *layer_check)
+    {
+        return guarded([&] {
+            if (!ctx || n_layers < 0 || (n_layers > 0 && (!layer_ptr || !layer_check))) throw std::runtime_error("bad argument");
+            std::vector<std::vector<int>> layers((size_t)n_layers);
+            for (int l = 0; l < n_layers; ++l) layers[l].assign(layer_check + layer_ptr[l], layer_check + layer_ptr[l + 1]);
+            ctx->eng->set_layers(std::move(layers));
+        });
+    }
+
+    int ldpc_b200_load_layers(ldpc_b200_ctx *ctx, const char *layer_file)
+    {
+        return guarded([&] {
+            if (!ctx || !layer_file) throw std::runtime_error("null argument");
+            ctx->eng->set_layers(b200::read_layer_file(layer_file));
+        });
+    }
+
+    int ldpc_b200_get_layers(ldpc_b200_ctx *ctx, int *layer_of)
+    {
+        int n = -1;
+        guarded([&] {
+            if (!ctx) throw std::runtime_error("null argument");
+            const auto &layers = ctx->eng->layers();
+            if (layer_of)
+                for (size_t l = 0; l < layers.size(); ++l)
+                    for (int c : layers[l]) layer_of[c] = (int)l;
+            n = (int)layers.size();
+        });
+        return n;
     }
 
     int ldpc_b200_get_edges(const ldpc_b200_ctx *ctx, int *rows, int *cols)

@@ -205,6 +205,114 @@ int orc_decode(const orc_code *c, const double *llr_in, int iterations, int earl
     return I;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Layered schedule — the legacy tree's layer loop (gpu/device/kernel.cpp:52-75: per layer a check  */
+/* update of the layer's checks, then the a-posteriori values, then the early-termination test)    */
+/* with the check-node rules of the live decoder (forward/backward recursion, box-plus / min-sum). */
+/* This is the SPECIFICATION of the opt-in layered mode of the CUDA path; it differs from the      */
+/* flooding reference by design.  Deviations from the legacy kernels, all stated in DESIGN.md:     */
+/*   - the posterior of a variable is updated in place by the checks of the layer                  */
+/*     (out = (out - c2v_old) + c2v_new) instead of being re-summed over all its edges after every */
+/*     layer (kernel.cpp:272-296): mathematically the same value; a layer must not contain two     */
+/*     checks sharing a variable (orc_layers_valid)                                                */
+/*   - early termination is tested once per iteration, after the last layer (the legacy code tests */
+/*     after every layer, kernel.cpp:62-69)                                                        */
+/* layers: layer_ptr[nl+1], layer_check[]; the checks of a layer in any order (they are independent).*/
+/* ------------------------------------------------------------------------------------------ */
+int orc_layers_valid(const orc_code *c, int nl, const int *layer_ptr, const int *layer_check)
+{
+    int *seen = (int *)malloc(sizeof(int) * c->nc), *used = (int *)calloc(c->mc, sizeof(int));
+    int ok = 1;
+    for (int i = 0; i < c->nc; ++i) seen[i] = -1;
+    for (int l = 0; l < nl && ok; ++l)
+        for (int q = layer_ptr[l]; q < layer_ptr[l + 1] && ok; ++q)
+        {
+            const int chk = layer_check[q];
+            if (chk < 0 || chk >= c->mc || used[chk]++) { ok = 0; break; }
+            for (int k = c->row_ptr[chk]; k < c->row_ptr[chk + 1]; ++k)
+            {
+                const int v = c->e_col[c->row_edge[k]];
+                if (seen[v] == l) { ok = 0; break; }
+                seen[v] = l;
+            }
+        }
+    for (int i = 0; i < c->mc && ok; ++i) if (!used[i]) ok = 0; /* every check in exactly one layer */
+    free(seen); free(used);
+    return ok;
+}
+
+int orc_decode_layered(const orc_code *c, int nl, const int *layer_ptr, const int *layer_check, const double *llr_in, int iterations,
+                       int early_term, int minsum, double ms_scale, double *llr_out, uint8_t *co)
+{
+    double (*f)(double, double) = minsum ? f_minsum : f_jacobian;
+    double *c2v = (double *)calloc(c->nnz + 1, sizeof(double)); /* +0: the first visit of a check reads the posterior itself */
+    double *F = (double *)calloc(c->max_degree + 2, sizeof(double));
+    double *B = (double *)calloc(c->max_degree + 2, sizeof(double));
+    double *v = (double *)calloc(c->max_degree + 2, sizeof(double));
+    for (int i = 0; i < c->nc; ++i) { llr_out[i] = llr_in[i]; co[i] = 0; }
+    int I = 0;
+    while (I < iterations)
+    {
+        for (int l = 0; l < nl; ++l)
+            for (int q = layer_ptr[l]; q < layer_ptr[l + 1]; ++q)
+            {
+                const int *cn = c->row_edge + c->row_ptr[layer_check[q]];
+                const int cw = c->row_ptr[layer_check[q] + 1] - c->row_ptr[layer_check[q]];
+                if (cw < 2) continue;
+                for (int j = 0; j < cw; ++j) v[j] = llr_out[c->e_col[cn[j]]] - c2v[cn[j]]; /* the v2c of kernel.cpp:290-294 */
+                F[0] = v[0];
+                B[cw - 1] = v[cw - 1];
+                for (int j = 1; j < cw; ++j)
+                {
+                    F[j] = f(F[j - 1], v[j]);
+                    B[cw - 1 - j] = f(B[cw - j], v[cw - j - 1]);
+                }
+                for (int j = 0; j < cw; ++j)
+                {
+                    double r = (j == 0) ? B[1] : (j == cw - 1) ? F[cw - 2] : f(F[j - 1], B[j + 1]);
+                    if (minsum) r *= ms_scale; /* normalised min-sum (1 = plain: exact) */
+                    c2v[cn[j]] = r;
+                    llr_out[c->e_col[cn[j]]] = v[j] + r;
+                }
+            }
+        for (int i = 0; i < c->nc; ++i) co[i] = (llr_out[i] <= 0); /* kernel.cpp:284 */
+        if (early_term && orc_is_codeword(c, co)) break;           /* before ++I, like the live decoder */
+        ++I;
+    }
+    for (int i = 0; i < c->nc; ++i) co[i] = (llr_out[i] <= 0);
+    free(c2v); free(F); free(B); free(v);
+    return I;
+}
+
+/* Layers in the sense of orc_layers_valid by first fit: check i joins the first layer none of whose checks shares a
+ * variable with it.  Quasi-cyclic codes come out with (at most) one layer per block row.  Returns the number of layers;
+ * layer_of[mc]. */
+int orc_auto_layers(const orc_code *c, int *layer_of)
+{
+    int nl = 0, cap = 16;
+    uint8_t **occ = (uint8_t **)malloc(sizeof(uint8_t *) * cap); /* occ[l][v] = variable v already used by layer l */
+    for (int i = 0; i < c->mc; ++i)
+    {
+        int l = 0;
+        for (;; ++l)
+        {
+            if (l == nl)
+            {
+                if (nl == cap) { cap *= 2; occ = (uint8_t **)realloc(occ, sizeof(uint8_t *) * cap); }
+                occ[nl++] = (uint8_t *)calloc(c->nc, 1);
+            }
+            int clash = 0;
+            for (int k = c->row_ptr[i]; k < c->row_ptr[i + 1] && !clash; ++k) clash = occ[l][c->e_col[c->row_edge[k]]];
+            if (!clash) break;
+        }
+        for (int k = c->row_ptr[i]; k < c->row_ptr[i + 1]; ++k) occ[l][c->e_col[c->row_edge[k]]] = 1;
+        layer_of[i] = l;
+    }
+    for (int l = 0; l < nl; ++l) free(occ[l]);
+    free(occ);
+    return nl;
+}
+
 /* BEC decoder — decoder.h:145-155 (vn_update, cn_update), decoder.cpp:91-192 */
 static inline uint8_t bec_cn(uint8_t l, uint8_t r)
 {

@@ -93,4 +93,10 @@ void orc_sim_point(const orc_code *c, const orc_code *g, int kind, int minsum, i
 #ifdef __cplusplus
 }
 #endif
+/* layered schedule (specification of the opt-in layered mode; legacy tree gpu/device/kernel.cpp:52-75) */
+int orc_layers_valid(const orc_code *c, int nl, const int *layer_ptr, const int *layer_check);
+int orc_decode_layered(const orc_code *c, int nl, const int *layer_ptr, const int *layer_check, const double *llr_in, int iterations,
+                       int early_term, int minsum, double ms_scale, double *llr_out, uint8_t *co);
+int orc_auto_layers(const orc_code *c, int *layer_of);
+
 #endif

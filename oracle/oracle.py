@@ -67,6 +67,13 @@ def lib():
         L.orc_multiply_right.argtypes = [P, bp, bp]
         L.orc_rank.restype = ct.c_int
         L.orc_rank.argtypes = [P]
+        ip = ct.POINTER(ct.c_int)
+        L.orc_layers_valid.restype = ct.c_int
+        L.orc_layers_valid.argtypes = [P, ct.c_int, ip, ip]
+        L.orc_decode_layered.restype = ct.c_int
+        L.orc_decode_layered.argtypes = [P, ct.c_int, ip, ip, dp, ct.c_int, ct.c_int, ct.c_int, ct.c_double, dp, bp]
+        L.orc_auto_layers.restype = ct.c_int
+        L.orc_auto_layers.argtypes = [P, ip]
         L.orc_philox4x32_10.argtypes = [ct.POINTER(ct.c_uint32)] * 3
         L.orc_channel_frame.argtypes = [P, P, ct.c_int, ct.c_double, ct.c_uint64, ct.c_uint32, ct.c_uint64, bp, dp, bp]
         L.orc_normal_block.argtypes = [ct.c_uint64, ct.c_uint32, ct.c_uint64, ct.c_uint32, dp]
@@ -127,6 +134,38 @@ class Code:
             its[t] = L.orc_decode(self._p, _dp(x[t]), iterations, int(early_term), int(minsum), _dp(out[t]), _bp(co[t]))
         if single:
             return out[0], co[0], int(its[0])
+        return out, co, its
+
+    # -- layered schedule (opt-in mode; specification) -----------------------------------------
+    def auto_layers(self):
+        """First-fit layers (no two checks of a layer share a variable) -> list of check-index arrays."""
+        lo = np.zeros(self.mc, dtype=np.int32)
+        nl = lib().orc_auto_layers(self._p, lo.ctypes.data_as(ct.POINTER(ct.c_int)))
+        return [np.nonzero(lo == l)[0].astype(np.int32) for l in range(nl)]
+
+    @staticmethod
+    def _layer_arrays(layers):
+        ptr = np.zeros(len(layers) + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([len(l) for l in layers])
+        chk = np.ascontiguousarray(np.concatenate([np.asarray(l, dtype=np.int32) for l in layers]) if layers else np.zeros(0, np.int32), dtype=np.int32)
+        return ptr, chk
+
+    def layers_valid(self, layers):
+        ptr, chk = self._layer_arrays(layers)
+        ip = ct.POINTER(ct.c_int)
+        return bool(lib().orc_layers_valid(self._p, len(layers), ptr.ctypes.data_as(ip), chk.ctypes.data_as(ip)))
+
+    def decode_layered(self, llr_in, layers, iterations=50, early_term=True, minsum=True, ms_scale=1.0):
+        llr_in = np.ascontiguousarray(llr_in, dtype=np.float64)
+        x = llr_in.reshape(-1, self.nc)
+        out = np.empty_like(x)
+        co = np.empty(x.shape, dtype=np.uint8)
+        its = np.empty(x.shape[0], dtype=np.int32)
+        ptr, chk = self._layer_arrays(layers)
+        ip = ct.POINTER(ct.c_int)
+        for t in range(x.shape[0]):
+            its[t] = lib().orc_decode_layered(self._p, len(layers), ptr.ctypes.data_as(ip), chk.ctypes.data_as(ip), _dp(x[t]), iterations,
+                                              int(early_term), int(minsum), float(ms_scale), _dp(out[t]), _bp(co[t]))
         return out, co, its
 
     def decode_bec(self, llr_in, cw, iterations=50, early_term=True, deg1_compat=True):

@@ -533,3 +533,65 @@ def test_cli_shards_on_one_gpu_give_identical_results(built_lib, tmp_path):
             assert r.returncode == 0, r.stdout + r.stderr
             rows.append([l.split()[:5] for l in out.read_text().split("\n")[1:] if l.strip()])
         assert rows[0] == rows[1] == rows[2] and len(rows[0]) >= 1, rows
+
+
+@pytest.mark.parametrize("prec", ["f64"])
+@pytest.mark.parametrize("decoding,et,iters", [("BP_MS", True, 50), ("BP_MS", False, 7), ("BP", True, 30), ("BP", False, 3)])
+def test_layered_schedule_equals_its_specification(gpu_ctx, oracle_code, decoding, et, iters, prec):
+    """Opt-in layered schedule (legacy tree gpu/device/kernel.cpp:52-75 with the live decoder's check rules) against its
+    specification oracle.decode_layered: min-sum bit-pattern exact, sum-product within 1e-4, identical iteration counts; built-in
+    and caller-supplied layers; fused sweep counters = specification on the dumped LLRs; about half the flooding iterations."""
+    from libldpc_b200 import api
+    gpu_ctx.set_tuning(schedule=api.LAYERED, zero_codeword=1)
+    try:
+        for layers in (None, [list(map(int, l[::-1])) for l in oracle_code.auto_layers()[::-1]]):
+            gpu_ctx.set_layers(layers)
+            use = gpu_ctx.layers()
+            cw, llr = gpu_ctx.channel("AWGN", -4.4, seed=31, point=0, frame0=0, n=101)
+            llr[3, ::9] = -0.0
+            ro, rc, ri = oracle_code.decode_layered(llr, use, iters, et, decoding == "BP_MS")
+            for fpc in (0, 4):
+                gpu_ctx.set_tuning(frames_per_cta=fpc)
+                out, hard, its = gpu_ctx.decode_batch(llr, decoding, iters, et)
+                assert np.array_equal(its, ri)
+                if decoding == "BP_MS":
+                    assert np.array_equal(hard, rc) and np.array_equal(out.view(np.uint64), ro.view(np.uint64))
+                else:
+                    assert (hard == rc).mean() >= 0.9999 and _rel_err(out, ro).max() < BP_RTOL
+            gpu_ctx.set_tuning(frames_per_cta=0)
+        gpu_ctx.set_layers(None)
+        n = 500
+        g = gpu_ctx.sim_point("AWGN", -4.6, seed=5, point=1, frame0=77, nframes=n, decoding=decoding, iterations=iters, early_term=et)
+        cw, llr = gpu_ctx.channel("AWGN", -4.6, seed=5, point=1, frame0=77, n=n)
+        ro, rc, ri = oracle_code.decode_layered(llr, gpu_ctx.layers(), iters, et, decoding == "BP_MS")
+        errs = (rc[:, oracle_code.bit_pos] != 0).sum(1)
+        if decoding == "BP_MS":
+            assert g["frames"] == n and g["iters"] == int(ri.sum()) and g["fec"] == int((errs > 0).sum()) and g["bec"] == int(errs.sum())
+        if et and iters == 50 and decoding == "BP_MS":
+            fo, fc, fi = oracle_code.decode(llr, iters, et, True)
+            conv = (ri < iters) & (fi < iters)
+            assert ri[conv].mean() < 0.7 * fi[conv].mean()          # the point of the schedule
+    finally:
+        gpu_ctx.set_layers(None)
+        gpu_ctx.set_tuning(schedule=api.FLOODING, zero_codeword=0, frames_per_cta=0)
+
+
+def test_layered_schedule_on_the_bg1_shaped_code(built_lib):
+    """Layered min-sum on the quasi-cyclic BG1-shaped code (the case the schedule exists for): bit-exact against the specification."""
+    from conftest import large_code_files
+    from libldpc_b200 import api
+    from oracle import oracle as O
+    path = large_code_files()["bg1"]
+    ctx = api.Context(path, "", device=0)
+    oc = O.Code(path)
+    ctx.set_tuning(schedule=api.LAYERED)
+    layers = ctx.layers()
+    assert oc.layers_valid(layers) and len(layers) <= 46
+    cw, llr = oc.channel_frames("AWGN", -0.6, 9, 0, 0, 9)
+    for et, iters, q in ((True, 50, 0), (False, 4, 0), (True, 50, 48)):
+        ctx.set_tuning(layered_ms_scale64=q)
+        ro, rc, ri = oc.decode_layered(llr, layers, iters, et, True, ms_scale=(q or 64) / 64.0)
+        out, hard, its = ctx.decode_batch(llr, "BP_MS", iters, et)
+        assert np.array_equal(its, ri) and np.array_equal(hard, rc) and np.array_equal(out.view(np.uint64), ro.view(np.uint64))
+    assert (ri < 50).sum() >= 4      # normalised layered min-sum converges where the plain one does not (all nine frames stay at 50)
+    ctx.close()

@@ -201,3 +201,31 @@ def test_bec_slice_layout_is_bank_conflict_free(built_lib, which):
             groups.setdefault((node[e] // 32, k[e]), []).append(slot[e] % 32)
         assert all(len(b) == len(set(b)) for b in groups.values())
     ctx.close()
+
+
+def test_layers_first_fit_file_format_and_validation(built_lib, oracle_code, tmp_path):
+    """Layered schedule, host side: the built-in first-fit layering equals the oracle's and is valid (no two checks of a layer
+    share a variable); the legacy layer-file format (gpu/ldpc/ldpc.cpp:111-138) round-trips; bad layerings are refused."""
+    from libldpc_b200 import api
+    ctx = api.Context(H_FILE, "", device=-1)
+    mine = ctx.layers()
+    ref = oracle_code.auto_layers()
+    assert len(mine) == len(ref) and all(np.array_equal(a, b) for a, b in zip(mine, ref)) and oracle_code.layers_valid(mine)
+    path = tmp_path / "layers.txt"
+    perm = [list(map(int, l[::-1])) for l in mine[::-1]]           # another valid layering: layers and checks reversed
+    with open(path, "w") as f:
+        f.write("nl: %d\n" % len(perm))
+        for l in perm:
+            f.write("cn[i]: %d\n" % len(l) + "".join("%d\n" % c for c in l))
+    ctx.load_layers(path)
+    got = ctx.layers()
+    assert [sorted(map(int, l)) for l in got] == [sorted(l) for l in perm]
+    with pytest.raises(RuntimeError, match="share a variable"):
+        ctx.set_layers([list(range(ctx.mc))])
+    with pytest.raises(RuntimeError, match="no layer"):
+        ctx.set_layers([list(map(int, mine[0]))])
+    with pytest.raises(RuntimeError, match="twice"):
+        ctx.set_layers([list(map(int, l)) for l in mine] + [[0]])
+    ctx.set_layers(None)
+    assert len(ctx.layers()) == len(ref)
+    ctx.close()
