@@ -168,6 +168,16 @@ LDPC_B200_API int ldpc_b200_set_layers(ldpc_b200_ctx *ctx, int n_layers, const i
 LDPC_B200_API int ldpc_b200_load_layers(ldpc_b200_ctx *ctx, const char *layer_file);
 LDPC_B200_API int ldpc_b200_get_layers(ldpc_b200_ctx *ctx, int *layer_of /*[mc]*/);
 
+/* Higher-order modulation of the AWGN sweep (opt-in; the legacy tree's M-ASK with bit-metric decoding: constellation
+ * gpu/sim/ldpcsim.cpp:6-20, labels / bit mapper :64-140, encode_all0 + map_c_to_x :240-271, calc_llrs :273-323 =
+ * gpu/device/kernel.cpp:141-219).  M = 4, 8, ... 256 points X_j = (-M + 1 + 2j) / sqrt(mean energy), uniform; labels[M] = the
+ * log2(M)-bit label of point j (NULL: binary reflected Gray code); bit_mapper[log2 M][nct / log2 M] = the variable carrying bit
+ * level k (most significant first) of symbol i (NULL: symbol i carries transmitted positions i*bits ... i*bits + bits - 1); nct must
+ * be a multiple of log2 M.  Frames carry random scrambling bits and the LLRs are multiplied by (1 - 2c), so the decoder sees the
+ * all-zero codeword, as in the legacy tree.  M = 2 returns to BPSK (the reference's channel_awgn).  Applies to "AWGN" in
+ * ldpc_b200_channel / _sim_point* / _simulate*; flooding schedule. */
+LDPC_B200_API int ldpc_b200_set_modulation(ldpc_b200_ctx *ctx, int M, const int *labels, const int *bit_mapper);
+
 /* host-side views of the loaded code (file order; sizes from ldpc_b200_info) */
 LDPC_B200_API int ldpc_b200_get_edges(const ldpc_b200_ctx *ctx, int *rows /*[nnz]*/, int *cols /*[nnz]*/);
 LDPC_B200_API int ldpc_b200_get_bit_pos(const ldpc_b200_ctx *ctx, int *bit_pos /*[nct]*/);

@@ -47,6 +47,7 @@ namespace
         "--gpus              \tB200 only: number of GPUs to shard every round of frames over, starting at --device (Default: 1, 0 = all)\n"
         "--schedule          \tB200 only: \"flooding\" (the reference's schedule, default) or \"layered\" (opt-in; results differ by design)\n"
         "--ms-scale          \tB200 only: with --schedule layered and BP_MS: normalisation factor of the check outputs in 1/64 steps (Default: 1 = plain min-sum)\n"
+        "--modulation        \tB200 only: M-ASK with bit-metric decoding on the AWGN channel, M = 4, 8, ... (Gray labels, consecutive bit mapper; Default: 2 = BPSK)\n"
         "--layers            \tB200 only: layer file for --schedule layered (legacy format: nl: N / cn[i]: W / W check indices); default: built-in layering\n"
         "--devices           \tB200 only: explicit device list for the shards, e.g. 0,1,2,3 (an index may repeat: several shards on one GPU)\n";
 
@@ -127,6 +128,7 @@ int main(int argc, char **argv)
     int device = 0, gpus = 1;
     std::string device_list, schedule = "flooding", layer_file;
     double ms_scale = 1.0;
+    int modulation = 2;
     std::vector<std::string> pos;
     try
     {
@@ -156,6 +158,7 @@ int main(int argc, char **argv)
             else if (a == "--schedule") schedule = value();
             else if (a == "--layers") layer_file = value();
             else if (a == "--ms-scale") ms_scale = std::stod(value());
+            else if (a == "--modulation") modulation = std::stoi(value());
             else if (a.size() > 1 && a[0] == '-' && !looks_numeric(a)) throw std::runtime_error("Unknown argument: " + a);
             else pos.push_back(a);
         }
@@ -189,6 +192,11 @@ int main(int argc, char **argv)
         if (tn.schedule == LDPC_B200_LAYERED) tn.zero_codeword = 1; // the layered sweep transmits the all-zero word
         tn.layered_ms_scale64 = (int)(ms_scale * 64.0 + 0.5);
         ldpc_b200_set_tuning(ctx, &tn);
+        if (modulation != 2 && ldpc_b200_set_modulation(ctx, modulation, nullptr, nullptr) != 0)
+        {
+            std::cout << "Error: modulation: " << ldpc_b200_last_error() << std::endl;
+            return EXIT_FAILURE;
+        }
         if (!layer_file.empty() && ldpc_b200_load_layers(ctx, layer_file.c_str()) != 0)
         {
             std::cout << "Error: layers: " << ldpc_b200_last_error() << std::endl;
@@ -238,6 +246,7 @@ int main(int argc, char **argv)
                 if (!c) { std::cout << "Error: ldpc_code(): " << ldpc_b200_last_error() << std::endl; return EXIT_FAILURE; }
                 ldpc_b200_set_tuning(c, &tn);
                 if (!layer_file.empty()) ldpc_b200_load_layers(c, layer_file.c_str());
+                if (modulation != 2) ldpc_b200_set_modulation(c, modulation, nullptr, nullptr);
                 m.ctxs.push_back(c);
             }
             std::cout << "GPUs: " << devices.size() << " shards on devices ";

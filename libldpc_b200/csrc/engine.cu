@@ -133,6 +133,7 @@ namespace b200
         cudaFree(d_bit_pos_); cudaFree(d_punct_); cudaFree(d_short_); cudaFree(d_counters_); cudaFree(d_state_);
         if (ev_state_) cudaEventDestroy((cudaEvent_t)ev_state_);
         cudaFree(d_g_col_ptr_); cudaFree(d_g_row_);
+        cudaFree(d_ask_X_); cudaFree(d_ask_label_); cudaFree(d_ask_rev_); cudaFree(d_ask_bm_);
         cudaFree(d_bs_row_ptr_); cudaFree(d_bs_row_slot_); cudaFree(d_bs_col_ptr_); cudaFree(d_bs_col_slot_); cudaFree(d_bs_tx_flag_);
         for (int b = 0; b < 2; ++b)
         {
@@ -639,7 +640,8 @@ namespace b200
         for (int v : H.shorten) if (v >= 0 && v < H.nc) ++kp.n_short;
         kp.max_iter = (int)dp.iterations;
         kp.early_term = dp.earlyTerm ? 1 : 0;
-        kp.kind = src.kind;
+        kp.kind = (src.kind == SRC_AWGN && ask_M > 2) ? SRC_ASK : src.kind;
+        if (kp.kind == SRC_ASK) ask_fill(&kp.ask);
         kp.llr_in = src.d_llr; kp.llr_in_f32 = src.d_llr_f32; kp.llr_in_i8 = src.d_llr_i8; kp.i8_scale = src.i8_scale;
         if (src.kind == SRC_AWGN)
         {
@@ -668,7 +670,7 @@ namespace b200
         // transmitted codewords: random information words through G when a generator matrix is loaded (the reference's -G,
         // src/sim/ldpcsim.cpp:162-165); decoding caller-supplied LLRs has no transmitted word
         kp.tx_var = d_bit_pos_;
-        if (has_gen && !tuning.zero_codeword && src.kind != SRC_LLR)
+        if (has_gen && !tuning.zero_codeword && src.kind != SRC_LLR && kp.kind != SRC_ASK)
         {
             kp.g_col_ptr = d_g_col_ptr_; kp.g_row = d_g_row_;
             kp.g_rows = G.mc; kp.g_cols = G.nc; kp.u_words = (G.mc + 31) / 32;
@@ -900,6 +902,60 @@ namespace b200
         pair_tuned_[key] = rate[1] > 1.01 * rate[0] ? 1 : 0;
     }
 
+    void Engine::set_modulation(int M, const int *labels, const int *bit_mapper)
+    {
+        if (M == 2) { ask_M = 2; return; }
+        int bits = 0;
+        while ((1 << bits) < M) ++bits;
+        if (M < 4 || M > 256 || (1 << bits) != M) throw std::runtime_error("modulation: M must be 2 (BPSK) or a power of two 4 ... 256");
+        if (H.nct() % bits) throw std::runtime_error("modulation: the number of transmitted bits is not a multiple of log2(M)"); // gpu/sim/ldpcsim.cpp:115-118
+        const int n_sym = H.nct() / bits;
+        std::vector<int32_t> lab(M), rev(M, -1), bm((size_t)bits * n_sym);
+        for (int j = 0; j < M; ++j) lab[j] = labels ? labels[j] : (j ^ (j >> 1));
+        for (int j = 0; j < M; ++j)
+        {
+            if (lab[j] < 0 || lab[j] >= M || rev[lab[j]] >= 0) throw std::runtime_error("modulation: labels must be a permutation of 0 ... M-1");
+            rev[lab[j]] = j;
+        }
+        std::vector<char> used(H.nc, 0);
+        for (int k = 0; k < bits; ++k)
+            for (int i = 0; i < n_sym; ++i)
+            {
+                const int v = bit_mapper ? bit_mapper[(size_t)k * n_sym + i] : H.bit_pos[(size_t)i * bits + k];
+                if (v < 0 || v >= H.nc || used[v]++) throw std::runtime_error("modulation: the bit mapper must name every transmitted variable once");
+                bm[(size_t)k * n_sym + i] = v;
+            }
+        for (int v : H.bit_pos) if (!used[v]) throw std::runtime_error("modulation: the bit mapper must name every transmitted variable once");
+        std::vector<double> X(M);
+        double m = 0;
+        for (int j = 0; j < M; ++j) { X[j] = (double)-M + 1 + 2 * j; m += X[j] * X[j] * (1.0 / M); } // gpu/sim/ldpcsim.cpp:10-14
+        for (int j = 0; j < M; ++j) X[j] = X[j] / std::sqrt(m);
+        ask_M = M; ask_labels = lab; ask_rev = rev; ask_bm = bm; ask_X = X;
+        if (cuda_ready_)
+        {
+            cudaSetDevice(device);
+            cudaDeviceSynchronize();
+            cudaFree(d_ask_X_); cudaFree(d_ask_label_); cudaFree(d_ask_rev_); cudaFree(d_ask_bm_);
+            d_ask_X_ = nullptr; d_ask_label_ = d_ask_rev_ = d_ask_bm_ = nullptr;
+        }
+        ask_uploaded_ = false;
+    }
+
+    void Engine::ask_fill(void *out)
+    {
+        if (!ask_uploaded_)
+        {
+            d_ask_X_ = upload(ask_X); d_ask_label_ = upload(ask_labels); d_ask_rev_ = upload(ask_rev); d_ask_bm_ = upload(ask_bm);
+            ask_uploaded_ = true;
+        }
+        AskParams &a = *static_cast<AskParams *>(out);
+        a.M = ask_M;
+        a.bits = 0;
+        while ((1 << a.bits) < ask_M) ++a.bits;
+        a.n_sym = H.nct() / a.bits;
+        a.X = d_ask_X_; a.label = d_ask_label_; a.rev = d_ask_rev_; a.bm = d_ask_bm_;
+    }
+
     void Engine::set_layers(std::vector<std::vector<int>> layers)
     {
         if (!layers.empty()) validate_layers(H, layers);
@@ -919,6 +975,7 @@ namespace b200
     {
         cudaStream_t s = (cudaStream_t)stream;
         if (src.d_llr_f32 || src.d_llr_i8 || sink.d_hard_bits) throw std::runtime_error("layered schedule: the narrow encodings are served by the flooding path only");
+        if (src.kind == SRC_AWGN && ask_M > 2) throw std::runtime_error("layered schedule: higher-order modulation is served by the flooding path only");
         if (has_gen && !tuning.zero_codeword && src.kind != SRC_LLR)
             throw std::runtime_error("layered schedule: sweeps transmit the all-zero codeword (set tuning.zero_codeword = 1 with a generator matrix loaded)");
         const bool minsum = dp.type && std::string(dp.type) == "BP_MS";
@@ -1418,8 +1475,36 @@ namespace b200
     __global__ void channel_kernel(int kind, int nc, int nct, const int32_t *__restrict__ bit_pos, const int32_t *__restrict__ punct, int n_punct,
                                    const int32_t *__restrict__ shorten, int n_short, double sigma, double llr_scale, double delta, uint32_t thr,
                                    uint64_t seed, uint32_t point, uint64_t frame0, int64_t n_frames, uint8_t *cw, double *llr, uint8_t *llr_u8,
-                                   const int32_t *__restrict__ g_col_ptr, const int32_t *__restrict__ g_row, int g_rows, int g_cols)
+                                   const int32_t *__restrict__ g_col_ptr, const int32_t *__restrict__ g_row, int g_rows, int g_cols, AskParams ask,
+                                   double sigma2)
     {
+        if (kind == SRC_ASK)
+        { // M-ASK with bit-metric decoding: one thread per Philox block of four symbols (same arithmetic as tile4.cuh frame_pass)
+            const int nsblk = (ask.n_sym + 3) / 4;
+            const int64_t total = n_frames * (int64_t)nsblk;
+            for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x)
+            {
+                const int64_t fr = g / nsblk;
+                const int q = (int)(g % nsblk);
+                const size_t base = (size_t)fr * nc;
+                const u32x4 r = channel_block(seed, point, 0, frame0 + fr, (uint32_t)q);
+                float z[4];
+                normal_pair(r.x, r.y, z[0], z[1]);
+                normal_pair(r.z, r.w, z[2], z[3]);
+                for (int k = 0; k < 4; ++k)
+                    if (q + k * nsblk < ask.n_sym)
+                        ask_symbol(ask, seed, point, frame0 + fr, q + k * nsblk, z[k], sigma, sigma2, [&](int v, double l, uint32_t c) {
+                            llr[base + v] = l;
+                            if (cw) cw[base + v] = (uint8_t)c;
+                        });
+                if (q == 0)
+                {
+                    for (int i = 0; i < n_punct; ++i) { llr[base + punct[i]] = 0.0; if (cw) cw[base + punct[i]] = 0; }
+                    for (int i = 0; i < n_short; ++i) { llr[base + shorten[i]] = 99999.9; if (cw) cw[base + shorten[i]] = 0; }
+                }
+            }
+            return;
+        }
         // codeword bit of variable v in frame fr: parity of the Philox stream-1 information bits selected by column v of G
         // (same rule as the fused kernels); 0 without a generator matrix.
         auto cw_bit = [&](int64_t fr, int v) -> uint32_t
@@ -1506,7 +1591,9 @@ namespace b200
     {
         if (n <= 0) return;
         ensure_cuda();
-        const int kind = channel_kind(channel);
+        int kind = channel_kind(channel);
+        AskParams ask{};
+        if (kind == SRC_AWGN && ask_M > 2) { kind = SRC_ASK; ask_fill(&ask); }
         cudaStream_t s = (cudaStream_t)stream_;
         const size_t nc = H.nc;
         double *d_llr = nullptr;
@@ -1516,7 +1603,7 @@ namespace b200
         if (cw) CUDA_OK(cudaMalloc(&d_cw, n * nc));
         double sigma2 = 1, sigma = 1, delta = 0;
         uint32_t thr = 0;
-        if (kind == SRC_AWGN) { sigma2 = std::pow(10.0, -x / 10.0); sigma = std::sqrt(sigma2); }
+        if (kind == SRC_AWGN || kind == SRC_ASK) { sigma2 = std::pow(10.0, -x / 10.0); sigma = std::sqrt(sigma2); }
         else
         {
             delta = std::log((1 - x) / x);
@@ -1525,7 +1612,7 @@ namespace b200
         }
         channel_kernel<<<sm_count_ * 4, 256, 0, s>>>(kind, (int)nc, H.nct(), d_bit_pos_, d_punct_, (int)H.puncture.size(), d_short_,
                                                      (int)H.shorten.size(), sigma, 2.0 / sigma2, delta, thr, seed, point, frame0, n, d_cw, d_llr, d_u8,
-                                                     d_g_col_ptr_, d_g_row_, (has_gen && !tuning.zero_codeword) ? G.mc : 0, has_gen ? G.nc : 0);
+                                                     d_g_col_ptr_, d_g_row_, (has_gen && !tuning.zero_codeword) ? G.mc : 0, has_gen ? G.nc : 0, ask, sigma2);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess && d_llr) e = cudaMemcpyAsync(llr, d_llr, n * nc * sizeof(double), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess && d_u8) e = cudaMemcpyAsync(llr_u8, d_u8, n * nc, cudaMemcpyDeviceToHost, s);

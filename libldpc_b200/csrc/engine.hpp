@@ -88,6 +88,12 @@ namespace b200
         // frames of one full wave of the persistent grid for this decoder type under the current tuning (rounds are sized in waves)
         uint64_t wave_frames(const decoder_param &dp, const std::string &channel);
 
+        // M-ASK with bit-metric decoding for the AWGN sweep (M = 2: BPSK)
+        void set_modulation(int M, const int *labels, const int *bit_mapper);
+        int ask_M = 2;
+        std::vector<int32_t> ask_labels, ask_rev, ask_bm;
+        std::vector<double> ask_X;
+
         // layered schedule: the layering in use (empty = built-in first-fit layering, made on first use)
         void set_layers(std::vector<std::vector<int>> layers);
         const std::vector<std::vector<int>> &layers();
@@ -157,6 +163,10 @@ namespace b200
         std::unique_ptr<BecSliceLayout> bs_layout_;
         uint8_t *d_bs_tx_flag_ = nullptr;
         unsigned long long *d_counters_ = nullptr;
+        double *d_ask_X_ = nullptr;
+        int32_t *d_ask_label_ = nullptr, *d_ask_rev_ = nullptr, *d_ask_bm_ = nullptr;
+        bool ask_uploaded_ = false;
+        void ask_fill(void *ask_params); // uploads the tables on first use and fills an AskParams
         unsigned long long *d_round_[2] = {nullptr, nullptr}, *h_round_[2] = {nullptr, nullptr}; // sweep rounds in flight
         void *ev_round_[2] = {nullptr, nullptr}, *ev_round0_[2] = {nullptr, nullptr}, *ev_rdone_[2] = {nullptr, nullptr};
         unsigned char *d_state_ = nullptr;

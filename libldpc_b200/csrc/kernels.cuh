@@ -83,7 +83,48 @@ namespace b200
         z1 = __fmul_rn(r, sn);
     }
 
-    enum { SRC_LLR = 0, SRC_AWGN = 1, SRC_BSC = 2, SRC_BEC = 3 };
+    enum { SRC_LLR = 0, SRC_AWGN = 1, SRC_BSC = 2, SRC_BEC = 3, SRC_ASK = 4 }; // SRC_ASK: AWGN with M-ASK + bit-metric decoding
+
+    // M-ASK with bit-metric decoding (legacy tree gpu/device/kernel.cpp:141-219, gpu/sim/ldpcsim.cpp:240-323; specification:
+    // oracle/ldpc_oracle.c orc_channel_frame_ask).  Tables in global memory.
+    struct AskParams
+    {
+        int M, bits, n_sym;
+        const double *X;  // [M] constellation points, unit average energy
+        const int32_t *label, *rev; // [M] label of point j / point of label l
+        const int32_t *bm; // [bits][n_sym] variable id carrying bit level k of symbol i
+    };
+    // One symbol: scrambling bits of its variables -> point -> y -> bit-metric LLRs (already multiplied by 1 - 2c).  z: the
+    // symbol's standard normal.  put(variable id, LLR, scrambling bit) is called once per bit level.
+    template <typename F>
+    __device__ __forceinline__ void ask_symbol(const AskParams &a, uint64_t seed, uint32_t point, uint64_t frame, int i, float z, double sigma,
+                                               double sigma2, F &&put)
+    {
+        int tmp = 0;
+        uint32_t cbit[8];
+        for (int k = 0; k < a.bits; ++k)
+        {
+            const int v = a.bm[k * a.n_sym + i];
+            const u32x4 w = channel_block(seed, point, 2, frame, (uint32_t)v >> 7);
+            const uint32_t q4[4] = {w.x, w.y, w.z, w.w};
+            cbit[k] = (q4[(v >> 5) & 3] >> (v & 31)) & 1u;
+            tmp += (int)cbit[k] << (a.bits - 1 - k);
+        }
+        const double y = __dadd_rn(__dmul_rn((double)z, sigma), a.X[a.rev[tmp]]);
+        for (int k = 0; k < a.bits; ++k)
+        {
+            double t0 = 0, t1 = 0;
+            for (int j = 0; j < a.M; ++j)
+            {
+                const double d = y - a.X[j];
+                const double e = exp(-d * d / (2 * sigma2)) * (1.0 / a.M);
+                if (a.label[j] & (1 << (a.bits - 1 - k))) t1 += e; else t0 += e;
+            }
+            double val = log(t0 / t1);
+            if (isinf(val)) val = val > 0 ? 9999.9 : -9999.9;
+            put(a.bm[k * a.n_sym + i], cbit[k] ? -val : val, cbit[k]);
+        }
+    }
     enum { ALG_MS = 0, ALG_BP = 1 };
     constexpr uint32_t IDLE = 0xFFFFFFFFu;
 

@@ -218,6 +218,14 @@ extern "C"
         });
     }
 
+    int ldpc_b200_set_modulation(ldpc_b200_ctx *ctx, int M, const int *labels, const int *bit_mapper)
+    {
+        return guarded([&] {
+            if (!ctx) throw std::runtime_error("null argument");
+            ctx->eng->set_modulation(M, labels, bit_mapper);
+        });
+    }
+
     int ldpc_b200_set_layers(ldpc_b200_ctx *ctx, int n_layers, const int *layer_ptr, const int *layer_check)
     {
         return guarded([&] {

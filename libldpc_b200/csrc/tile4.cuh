@@ -252,6 +252,7 @@ namespace b200
         const int32_t *g_col_ptr, *g_row;
         const int32_t *tx_var;
         int g_rows, g_cols, u_words; // u_words = ceil(g_rows / 32)
+        AskParams ask; // kind == SRC_ASK
         // TMEM mirror (TM kernels): columns allocated per CTA (power of two >= 32), columns per warp window,
         // column offset of the variable-side (channel LLR) part inside a warp window
         uint32_t tm_alloc_cols, tm_cols_per_warp, tm_vn_off;
@@ -743,7 +744,7 @@ namespace b200
             };
             const bool has_g = p.g_rows > 0;
             const unsigned long long frame = p.frame0 + gf;
-            const bool gen = refill && p.kind != SRC_LLR;
+            const bool gen = refill && p.kind != SRC_LLR && p.kind != SRC_ASK;
             uint32_t nerr = 0;
 #ifdef B200_PHASE_TIMING
             const long long fp0 = clock64();
@@ -815,6 +816,22 @@ namespace b200
                     for (int i = tid; i < p.n_short; i += nthreads) put(p.short_pos[i], sv);
                 }
             }
+            else if (refill && p.kind == SRC_ASK)
+            { // M-ASK / bit-metric: thread <-> Philox block q <-> symbols q + k*nsblk; LLRs land at the positions of the mapped variables
+                const int nsblk = (p.ask.n_sym + 3) >> 2;
+                for (int q = tid; q < nsblk; q += nthreads)
+                {
+                    const u32x4 r = channel_block(p.seed, p.point, 0, frame, (uint32_t)q);
+                    float z[4];
+                    normal_pair(r.x, r.y, z[0], z[1]);
+                    normal_pair(r.z, r.w, z[2], z[3]);
+                    for (int k = 0; k < 4; ++k)
+                        if (q + k * nsblk < p.ask.n_sym)
+                            ask_symbol(p.ask, p.seed, p.point, frame, q + k * nsblk, z[k], p.sigma, p.sigma2, [&](int v, double l, uint32_t) { put((int)p.var_pos[v], (T)l); });
+                }
+                for (int i = tid; i < p.n_punct; i += nthreads) put(p.punct_pos[i], T(0));
+                for (int i = tid; i < p.n_short; i += nthreads) put(p.short_pos[i], (T)99999.9);
+            }
             else if (refill)
             {
                 if (p.llr_in_f32)
@@ -878,7 +895,7 @@ namespace b200
                 if (((mask >> g) & 1u) && (uint32_t)__popc(mask & ((1u << g) - 1u)) < n_new) gm |= 1u << g;
             auto new_frame = [&](int g) { return (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * (next_k + (unsigned long long)__popc(mask & ((1u << g) - 1u))); };
             const bool outputs = !first_fill && (p.llr_out || p.hard_out || p.hard_bits || p.iters_out);
-            const bool fused = p.kind != SRC_LLR && p.g_rows <= 0 && !outputs;
+            const bool fused = p.kind != SRC_LLR && p.kind != SRC_ASK && p.g_rows <= 0 && !outputs;
             auto bookkeeping = [&]()
             {
                 if (warp != 0) return;

@@ -636,6 +636,59 @@ void orc_channel_frame(const orc_code *c, const orc_code *g, int kind, double x,
     }
 }
 
+/* M-ASK with bit-metric decoding — the legacy tree's higher-order modulation (constellation: gpu/sim/ldpcsim.cpp:6-20; bit
+ * mapper / labels: :64-140; encode_all0 + map_c_to_x: :240-271; calc_llrs: :273-323 = gpu/device/kernel.cpp:141-219).
+ * Specification of the counter-based version: scrambling bits c[v] = bit v of Philox stream 2 (word v/32 of block v/128), symbol
+ * i carries the bits c[bm[k][i]] (level k = most significant first), y = X[x] + sigma*z with z = value i / nb of Philox block
+ * i % nb of stream 0 (nb = ceil(n_sym/4)), bit-metric LLR log(sum_{bit=0} / sum_{bit=1}) of exp(-(y-X_j)^2/(2 sigma^2)) pX_j,
+ * +-inf clipped to +-9999.9, multiplied by (1 - 2c) so that the decoder sees the all-zero codeword; punctured positions 0,
+ * shortened 99999.9 (conventions of the live channel, src/sim/channel.cpp:77,84).  cw_out receives the scrambling bits. */
+void orc_channel_frame_ask(const orc_code *c, int M, const int *labels, const int *bm, double snr, uint64_t seed, uint32_t point,
+                           uint64_t frame, uint8_t *cw_out, double *llr)
+{
+    int bits = 0;
+    while ((1 << bits) < M) ++bits;
+    const int n_sym = c->nct / bits, nb = (n_sym + 3) / 4;
+    const double sigma2 = pow(10, -snr / 10), sigma = sqrt(sigma2);
+    double *X = (double *)malloc(sizeof(double) * M);
+    int *rev = (int *)malloc(sizeof(int) * M);
+    double m = 0;
+    for (int j = 0; j < M; ++j) { X[j] = (double)-M + 1 + 2 * j; m += X[j] * X[j] * (1.0 / M); } /* ldpcsim.cpp:10-14 */
+    for (int j = 0; j < M; ++j) { X[j] = X[j] / sqrt(m); rev[labels[j]] = j; }                    /* :16-19, :80-84 */
+    memset(cw_out, 0, c->nc);
+    for (int i = 0; i < c->n_punct; ++i) llr[c->punct[i]] = 0.0;
+    for (int i = 0; i < c->n_short; ++i) llr[c->shorten[i]] = 99999.9;
+    for (int i = 0; i < n_sym; ++i)
+    {
+        int tmp = 0;
+        for (int k = 0; k < bits; ++k)
+        {
+            const int v = bm[k * n_sym + i];
+            uint32_t w[4];
+            philox_block(seed, point, 2, frame, (uint32_t)v >> 7, w);
+            cw_out[v] = (w[(v >> 5) & 3] >> (v & 31)) & 1;
+            tmp += cw_out[v] << (bits - 1 - k); /* map_c_to_x, ldpcsim.cpp:258-270 */
+        }
+        double z[4];
+        orc_normal_block(seed, point, frame, (uint32_t)(i % nb), z);
+        const double y = z[i / nb] * sigma + X[rev[tmp]];
+        for (int k = 0; k < bits; ++k)
+        {
+            double t0 = 0, t1 = 0;
+            for (int j = 0; j < M; ++j)
+            {
+                const double e = exp(-(y - X[j]) * (y - X[j]) / (2 * sigma2)) * (1.0 / M);
+                if (labels[j] & (1 << (bits - 1 - k))) t1 += e; else t0 += e;
+            }
+            double val = log(t0 / t1);
+            if (isinf(val)) val = val > 0 ? 9999.9 : -9999.9; /* ldpcsim.h:59-60 */
+            const int v = bm[k * n_sym + i];
+            llr[v] = val * (1 - 2 * (int)cw_out[v]);
+        }
+    }
+    free(X); free(rev);
+}
+
 void orc_sim_point(const orc_code *c, const orc_code *g, int kind, int minsum, int iterations, int early_term,
                    int bec_deg1_compat, double x, uint64_t seed, uint32_t point, uint64_t frame0,
                    uint64_t nframes, int threads, uint64_t counters[4])

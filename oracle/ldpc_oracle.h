@@ -99,4 +99,8 @@ int orc_decode_layered(const orc_code *c, int nl, const int *layer_ptr, const in
                        int early_term, int minsum, double ms_scale, double *llr_out, uint8_t *co);
 int orc_auto_layers(const orc_code *c, int *layer_of);
 
+/* M-ASK with bit-metric decoding (legacy tree gpu/sim/ldpcsim.cpp:6-20,240-323): labels[M], bm[log2M][nct/log2M] variable ids */
+void orc_channel_frame_ask(const orc_code *c, int M, const int *labels, const int *bm, double snr, uint64_t seed, uint32_t point,
+                           uint64_t frame, uint8_t *cw_out, double *llr);
+
 #endif

@@ -74,6 +74,7 @@ def lib():
         L.orc_decode_layered.argtypes = [P, ct.c_int, ip, ip, dp, ct.c_int, ct.c_int, ct.c_int, ct.c_double, dp, bp]
         L.orc_auto_layers.restype = ct.c_int
         L.orc_auto_layers.argtypes = [P, ip]
+        L.orc_channel_frame_ask.argtypes = [P, ct.c_int, ip, ip, ct.c_double, ct.c_uint64, ct.c_uint32, ct.c_uint64, bp, dp]
         L.orc_philox4x32_10.argtypes = [ct.POINTER(ct.c_uint32)] * 3
         L.orc_channel_frame.argtypes = [P, P, ct.c_int, ct.c_double, ct.c_uint64, ct.c_uint32, ct.c_uint64, bp, dp, bp]
         L.orc_normal_block.argtypes = [ct.c_uint64, ct.c_uint32, ct.c_uint64, ct.c_uint32, dp]
@@ -215,6 +216,26 @@ class Code:
         for t in range(nframes):
             L.orc_channel_frame(self._p, gp, k, float(x), int(seed), int(point), int(frame0 + t), _bp(cw[t]), _dp(lf[t]), _bp(lu[t]))
         return cw, (lu if k == BEC else lf)
+
+    def default_modulation(self, M):
+        """Gray labels and the consecutive bit mapper (symbol i carries transmitted positions i*bits .. i*bits+bits-1)."""
+        bits = int(M).bit_length() - 1
+        labels = np.array([j ^ (j >> 1) for j in range(M)], dtype=np.int32)
+        n_sym = self.nct // bits
+        bm = np.ascontiguousarray(self.bit_pos[:n_sym * bits].reshape(n_sym, bits).T, dtype=np.int32)
+        return labels, bm
+
+    def channel_frames_ask(self, M, labels, bm, snr, seed, point, frame0, nframes):
+        """-> (scrambling bits [n, nc] u8, llr [n, nc] f64) of the M-ASK / bit-metric channel specification"""
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        bm = np.ascontiguousarray(bm, dtype=np.int32)
+        cw = np.zeros((nframes, self.nc), dtype=np.uint8)
+        llr = np.zeros((nframes, self.nc), dtype=np.float64)
+        ip = ct.POINTER(ct.c_int)
+        for t in range(nframes):
+            lib().orc_channel_frame_ask(self._p, int(M), labels.ctypes.data_as(ip), bm.ctypes.data_as(ip), float(snr), int(seed), int(point),
+                                        int(frame0 + t), _bp(cw[t]), _dp(llr[t]))
+        return cw, llr
 
     def sim_point(self, kind, x, seed=0, point=0, frame0=0, nframes=100, decoding="BP", iterations=50,
                   early_term=True, bec_deg1_compat=True, threads=1, gen=None):

@@ -595,3 +595,35 @@ def test_layered_schedule_on_the_bg1_shaped_code(built_lib):
         assert np.array_equal(its, ri) and np.array_equal(hard, rc) and np.array_equal(out.view(np.uint64), ro.view(np.uint64))
     assert (ri < 50).sum() >= 4      # normalised layered min-sum converges where the plain one does not (all nine frames stay at 50)
     ctx.close()
+
+
+@pytest.mark.parametrize("M,snr", [(4, 1.5), (16, 10.0)])
+def test_mask_bit_metric_channel_and_sweep(gpu_ctx, oracle_code, M, snr):
+    """Higher-order modulation (legacy tree: M-ASK + bit-metric decoding, gpu/device/kernel.cpp:141-219): the GPU channel against
+    its specification (scrambling bits identical, LLRs to 1e-9 — library exp / log on both sides), default and caller-supplied
+    labels / bit mapper, and the fused sweep's counters against the oracle decoding the dumped LLRs."""
+    rng = np.random.default_rng(M)
+    lab, bm = oracle_code.default_modulation(M)
+    try:
+        for labels, mapper in ((None, None), (lab[::-1].copy(), rng.permutation(bm.reshape(-1)).reshape(bm.shape))):
+            gpu_ctx.set_modulation(M, labels, mapper)
+            l_use, m_use = (lab, bm) if labels is None else (labels, mapper)
+            cw, llr = gpu_ctx.channel("AWGN", snr, seed=12, point=2, frame0=1 << 35, n=40)
+            ocw, ollr = oracle_code.channel_frames_ask(M, l_use, m_use, snr, 12, 2, 1 << 35, 40)
+            assert np.array_equal(cw, ocw)
+            assert np.allclose(llr, ollr, rtol=1e-9, atol=1e-9)
+            assert np.all(llr[:, oracle_code.puncture] == 0.0) and 0.4 < cw[:, oracle_code.bit_pos].mean() < 0.6
+        gpu_ctx.set_modulation(M)
+        n = 400
+        g = gpu_ctx.sim_point("AWGN", snr - 1.0, seed=3, point=0, frame0=9, nframes=n, decoding="BP_MS", iterations=30, early_term=True)
+        cw, llr = gpu_ctx.channel("AWGN", snr - 1.0, seed=3, point=0, frame0=9, n=n)
+        ro, rc, ri = oracle_code.decode(llr, 30, True, True)
+        errs = (rc[:, oracle_code.bit_pos] != 0).sum(1)
+        assert g["frames"] == n and g["iters"] == int(ri.sum()) and g["fec"] == int((errs > 0).sum()) and g["bec"] == int(errs.sum())
+        assert 0 < g["iters"] < 30 * n
+    finally:
+        gpu_ctx.set_modulation(2)
+    gpu_ctx.set_tuning(zero_codeword=1)                                               # back to the reference's BPSK channel
+    cw, llr = gpu_ctx.channel("AWGN", -4.5, seed=2, point=1, frame0=5, n=4)
+    gpu_ctx.set_tuning(zero_codeword=0)
+    assert np.array_equal(llr.view(np.uint64), oracle_code.channel_frames("AWGN", -4.5, 2, 1, 5, 4)[1].view(np.uint64))

@@ -229,3 +229,16 @@ def test_layers_first_fit_file_format_and_validation(built_lib, oracle_code, tmp
     ctx.set_layers(None)
     assert len(ctx.layers()) == len(ref)
     ctx.close()
+
+
+def test_modulation_arguments_are_validated(built_lib):
+    from libldpc_b200 import api
+    ctx = api.Context(H_FILE, "", device=-1)
+    ctx.set_modulation(4)
+    ctx.set_modulation(16, labels=[j ^ (j >> 1) for j in range(16)][::-1])
+    ctx.set_modulation(2)
+    for bad, msg in ((dict(M=3), "power of two"), (dict(M=4, labels=[0, 1, 1, 2]), "permutation"), (dict(M=8), "multiple of log2"),
+                     (dict(M=4, bit_mapper=np.zeros((2, 512), np.int32)), "every transmitted variable once")):
+        with pytest.raises(RuntimeError, match=msg):
+            ctx.set_modulation(**bad)
+    ctx.close()
