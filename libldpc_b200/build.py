@@ -32,9 +32,13 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     global LIB, OBJDIR, COMMON
+    if os.environ.get("B200_VARIANT"):  # experiment builds: B200_VARIANT=name B200_DEFS="-DX=1 ..." -> libldpc_<name>.so (A/B runs via LDPC_B200_LIB)
+        LIB = os.path.join(HERE, "libldpc_%s.so" % os.environ["B200_VARIANT"])
+        OBJDIR = os.path.join("/tmp", "b200_build_%s" % os.environ["B200_VARIANT"])  # outside the tree: the gpurun snapshot stays small
+        COMMON = COMMON + os.environ.get("B200_DEFS", "").split()
     if os.environ.get("B200_PHASE_TIMING"):  # the debug build lives beside the product library (LDPC_B200_LIB selects it at load time)
         LIB = os.path.join(HERE, "libldpc_pt.so")
-        OBJDIR = os.path.join(HERE, "build_pt")
+        OBJDIR = os.path.join("/tmp", "b200_build_pt")
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     if force or _stale(LIB, deps):
@@ -60,7 +64,7 @@ def build(force=False, verbose=False):
         # exported: exactly the functions include/ldpc_b200.h declares (LDPC_B200_API); the static CUDA runtime stays internal
         subprocess.run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++", "-Xlinker", "--exclude-libs,ALL", "-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map"), "-o", LIB] + objs, check=True)
     cli_src = os.path.join(CSRC, "cli_main.cpp")
-    if not os.environ.get("B200_PHASE_TIMING") and (force or _stale(CLI, [cli_src, LIB])):
+    if not os.environ.get("B200_PHASE_TIMING") and not os.environ.get("B200_VARIANT") and (force or _stale(CLI, [cli_src, LIB])):
         cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", CLI, cli_src, LIB, "-Wl,-rpath,$ORIGIN"]  # a plain C-ABI client
         subprocess.run(cmd, check=True)
     return LIB
