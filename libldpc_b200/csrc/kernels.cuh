@@ -252,6 +252,121 @@ namespace b200
     }
 #endif
 
+    template <typename T> __device__ __forceinline__ T boxplus(T x, T y);
+
+#ifdef __CUDACC__
+    // ---- fp64 sum-product check node on E = e^-|x| -----------------------------------------------------------------------
+    // The reference evaluates a degree-d check as 3(d-2) pairwise box-plus operations (decoder.cpp:30-44 with decoder.h:12-15:
+    // two exp, a division and a log each, ~70 FP64 instructions here).  In terms of E = e^-|x| the magnitude of x [+] y is
+    //     E(x [+] y) = (Ex + Ey) / (1 + Ex Ey)                       (tanh(x/2) = (1 - Ex) / (1 + Ex) in the tanh rule)
+    // so the same function of the d inputs costs d exponentials, fraction-valued forward / backward products (E = N / D carried
+    // as the pair: folding in a raw input is two FMAs, joining a forward with a backward value four operations, no division) and
+    // d logarithms log(D / N) -- ~45 FP64 instructions per edge for any degree (d = 7: 3.2 x fewer than the pairwise chain), all
+    // of them independent chains instead of one d-deep dependent recursion.  Unlike tanh / atanh this form has no cancellation:
+    // E keeps full relative precision down to e^-708, and log(D / N) = e0 ln 2 + 2 atanh((D - N') / (D + N')) with N' = N 2^e0
+    // brought within a factor sqrt 2 of D is accurate to ~2e-16 absolute + 1e-16 relative -- the same as the reference's own
+    // double expression (tests/study_bp_edomain.py: posteriors after 50 iterations within 1.3e-7 of the oracle's, bar 1e-4).
+    // Large inputs: with m = min |x| over the check (taken from the high words), all inputs are shifted by max(0, m - 40) before
+    // the exponential and the shift is added back after the logarithm (exact: once every E <= e^-40 the denominators are 1 to
+    // 1e-34); an output whose magnitude would exceed ~665 above the shift (inputs beyond the e^-708 clamp decide it: shortened
+    // positions at 99999.9) makes the thread redo the check with the reference's pairwise recursion (`exact` below).
+    static __constant__ double BP_LOG_C[10] = {2.0, 2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19};
+    static __constant__ double BP_LOG_K[3] = {0.6931471805599453, 4503601774854144.0 /* 2^52 + 2^31 */, 40.0};
+
+    // log(D / N) + shift for 0 < N <~ D, both normal; far: beyond the range the clamp of bp_exp_neg keeps exact
+    __device__ __forceinline__ double bp_log_frac(double N, double D, double shift, bool &far)
+    {
+        const uint32_t hn = (uint32_t)__double2hiint(N), hd = (uint32_t)__double2hiint(D);
+        int e0 = (int)(hd >> 20) - (int)(hn >> 20);
+        const float fn = __uint_as_float(0x3f800000u | ((hn & 0xfffffu) << 3)), fd = __uint_as_float(0x3f800000u | ((hd & 0xfffffu) << 3));
+        e0 += (fd > 1.41421354f * fn) ? 1 : 0;
+        e0 -= (fn > 1.41421354f * fd) ? 1 : 0;
+        const double Ns = __hiloint2double((int)(hn + ((uint32_t)e0 << 20)), __double2loint(N)); // N 2^e0, within sqrt 2 of D
+        const double num = D - Ns, den = D + Ns;
+        // num / den, den in [1, 2^9): reciprocal seed (2^-23), one Newton step, quotient, one residual correction (error e^4)
+        double rc;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
+        rc = __fma_rn(rc, __fma_rn(-den, rc, 1.0), rc);
+        double w = num * rc;
+        w = __fma_rn(__fma_rn(-den, w, num), rc, w);
+        const double s = w * w;
+        double p = BP_LOG_C[9];
+#pragma unroll
+        for (int i = 8; i >= 0; --i) p = __fma_rn(p, s, BP_LOG_C[i]);
+        far = e0 > 960;
+        const double e0d = __hiloint2double(0x43300000, (int)((uint32_t)e0 ^ 0x80000000u)) - BP_LOG_K[1];
+        return __fma_rn(w, p, __fma_rn(e0d, BP_LOG_K[0], shift));
+    }
+
+    template <int D>
+    __device__ __forceinline__ void bp_check(const double (&x)[D], double (&r)[D])
+    {
+        static_assert(D >= 3, "degree-2 checks swap their inputs");
+        uint32_t sx = 0, mh = 0x7fffffffu;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+        {
+            const uint32_t h = (uint32_t)__double2hiint(x[k]);
+            sx ^= h;
+            mh = min(mh, h & 0x7fffffffu);
+        }
+        const double shift = (mh >= 0x40440000u && mh < 0x7ff00000u) ? __hiloint2double((int)mh, 0) - BP_LOG_K[2] : 0.0;
+        double E[D], FN[D - 1], FD[D - 1];
+#pragma unroll
+        for (int k = 0; k < D; ++k) E[k] = bp_exp_neg(fabs(x[k]) - shift);
+        FN[0] = E[0];
+        FD[0] = 1.0;
+#pragma unroll
+        for (int k = 1; k < D - 1; ++k)
+        {
+            FN[k] = __fma_rn(E[k], FD[k - 1], FN[k - 1]);
+            FD[k] = __fma_rn(E[k], FN[k - 1], FD[k - 1]);
+        }
+        double BN = E[D - 1], BD = 1.0;
+        bool far, anyfar;
+        r[D - 1] = bp_log_frac(FN[D - 2], FD[D - 2], shift, anyfar);
+#pragma unroll
+        for (int k = D - 2; k >= 1; --k)
+        {
+            const double N = __fma_rn(FN[k - 1], BD, BN * FD[k - 1]), Dn = __fma_rn(FN[k - 1], BN, FD[k - 1] * BD);
+            r[k] = bp_log_frac(N, Dn, shift, far);
+            anyfar |= far;
+            const double bn = __fma_rn(E[k], BD, BN), bd = __fma_rn(E[k], BN, BD);
+            BN = bn;
+            BD = bd;
+        }
+        r[0] = bp_log_frac(BN, BD, shift, far);
+        anyfar |= far;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+        {
+            const uint32_t s = (sx ^ (uint32_t)__double2hiint(x[k])) & 0x80000000u;
+            r[k] = __hiloint2double((int)(((uint32_t)__double2hiint(r[k]) & 0x7fffffffu) | s), __double2loint(r[k]));
+        }
+        if (anyfar) // rare: the reference's pairwise recursion, rolled loops over a local copy
+        {
+            double lx[D], lf[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) lx[k] = x[k];
+            lf[0] = lx[0];
+#pragma unroll 1
+            for (int k = 1; k < D; ++k) lf[k] = boxplus(lf[k - 1], lx[k]);
+            double B = lx[D - 1];
+            lf[D - 1] = lf[D - 2];
+#pragma unroll 1
+            for (int k = D - 2; k >= 1; --k)
+            {
+                const double f = lf[k - 1];
+                lf[k] = boxplus(f, B);
+                B = boxplus(B, lx[k]);
+            }
+            lf[0] = B;
+#pragma unroll
+            for (int k = 0; k < D; ++k) r[k] = lf[k];
+        }
+    }
+#endif
+
     // pairwise box-plus with the Jacobian correction, decoder.h:12-15 (same expression, same order)
     template <typename T>
     __device__ __forceinline__ T boxplus(T x, T y)

@@ -259,6 +259,9 @@ namespace b200
     };
 
     // raw value of smaller magnitude (min-sum keeps raw values; magnitude and sign are fixed at the store)
+#ifndef B200_BP_EDOMAIN
+#define B200_BP_EDOMAIN 1 // fp64 sum-product checks of degree 3..8 on E = e^-|x| (kernels.cuh bp_check); 0: the pairwise recursion (A/B builds)
+#endif
     template <typename T> __device__ __forceinline__ T min_mag(T a, T b) { return (Num<T>::abs(b) < Num<T>::abs(a)) ? b : a; }
     // |mag| with the sign bit of word s (bit 31)
     __device__ __forceinline__ double mag_sign(double m, uint32_t s)
@@ -395,6 +398,16 @@ namespace b200
 #pragma unroll
                             for (int k = 0; k < D; ++k) r[k].e[e] = mag_sign(m[k], sx ^ Num<T>::hi(v[k].e[e]));
                         }
+                    }
+                    else if constexpr (sizeof(T) == 8 && D >= 3 && B200_BP_EDOMAIN)
+                    {
+                        // sum-product in fp64: the same function of the inputs evaluated on E = e^-|x| (kernels.cuh bp_check)
+                        double x[D], y[D];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) x[k] = v[k].e[e];
+                        bp_check<D>(x, y);
+#pragma unroll
+                        for (int k = 0; k < D; ++k) r[k].e[e] = y[k];
                     }
                     else
                     {
