@@ -235,7 +235,8 @@ namespace b200
     const SegLayout &Engine::layout_for(int precision, int alg, int *residency, size_t *smem_bytes)
     {
         const int vec = precision == LDPC_B200_F32 ? 4 : 2;
-        const int max_threads = B200_TILE_MAX_THREADS; // compile-time cap of the kernels (tile4.cuh)
+        // compile-time caps of the kernels (tile4.cuh): shared-memory residency (the fp64 sum-product kernel has a lower one), global residency
+        const int max_threads = tile_thread_cap(precision != LDPC_B200_F32, alg, true), g_max_threads = B200_TILE_MAX_THREADS;
         const int threads = tuning.threads_per_cta > 0 ? std::min(tuning.threads_per_cta, max_threads) : max_threads;
         int want_lanes = 0;
         if (tuning.frames_per_cta > 0)
@@ -295,7 +296,7 @@ namespace b200
             if (tuning.residency == LDPC_B200_SMEM) throw std::runtime_error("code does not fit shared-memory residency with this tuning");
         }
         *residency = LDPC_B200_GLOBAL;
-        int g_lanes = want_lanes ? want_lanes : 1, g_threads = threads;
+        int g_lanes = want_lanes ? want_lanes : 1, g_threads = tuning.threads_per_cta > 0 ? std::min(tuning.threads_per_cta, g_max_threads) : g_max_threads;
         if (!want_lanes && tuning.threads_per_cta <= 0)
         { // global residency, nothing pinned by the caller: the autotuned (lanes, threads) of this (precision, algorithm)
             auto it = tuned_.find(std::make_pair(precision, alg));
@@ -872,7 +873,7 @@ namespace b200
                 try
                 {
                     launch(tdp, src, sink, frames / 4, s, true); // warm-up (tables, attributes)
-                    if (cand == 1 && stats.threads_per_cta != B200_TILE_MAX_THREADS / 2) break; // not eligible: the one-CTA shape ran
+                    if (cand == 1 && stats.threads_per_cta != tile_thread_cap(tuning.precision != LDPC_B200_F32, alg, true) / 2) break; // not eligible: the one-CTA shape ran
                     CUDA_OK(cudaEventRecord((cudaEvent_t)ev0_, s));
                     launch(tdp, src, sink, frames, s, true);
                     CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, s));

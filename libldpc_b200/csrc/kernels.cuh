@@ -216,29 +216,34 @@ namespace b200
     };
 
 #ifdef __CUDACC__
-    // ---- fp64 Jacobian correction log((1 + e^-a) / (1 + e^-b)), a, b >= 0, without the math library ------------------------
-    // The library exp / log spend a third of the sum-product kernel's issue slots on materialising 64-bit polynomial
-    // coefficients (two moves per constant, every call).  Here the coefficients sit in the constant bank and arrive as one
-    // uniform load each; the logarithm of the ratio is 2 atanh((u - v) / (2 + u + v)), |argument| <= 1/3, so no range
-    // reduction, no table.  Accuracy against the exact value: 3.1e-16 absolute at most over 2e7 random pairs — the same as
-    // the reference's own double expression (3.4e-16); the parity bar needs ~1e-14 (profiles/r1/bp_accuracy.md).
-    static __constant__ double BP_EXP_C[14] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
-                                               1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0}; // 1/k!
+    // ---- fp64 exponential and the Jacobian correction log((1 + e^-a) / (1 + e^-b)), a, b >= 0, without the math library -----
+    // The library exp / log spend a third of a sum-product kernel's issue slots on materialising 64-bit polynomial
+    // coefficients (two moves per constant, every call).  Here the coefficients sit in the constant bank and arrive as
+    // uniform loads; the logarithm of the ratio is 2 atanh((u - v) / (2 + u + v)), |argument| <= 1/3, so no range
+    // reduction, no table.  Accuracy of the pairwise correction against the exact value: 3.1e-16 absolute at most over 2e7
+    // random pairs -- the same as the reference's own double expression (3.4e-16); the parity bar needs ~1e-14
+    // (profiles/r1/bp_accuracy.md).  The pairwise box-plus serves the layered kernel, checks of degree > 8 and the rare exact
+    // path of bp_check below.
+    // e^r on |r| <= ln 2 / 2: minimax polynomial of degree 11 (Remez at 60 digits, profiles/gen_bp_tables.py; 1.2e-17 with the
+    // coefficients rounded to binary64; the Taylor polynomial needs degree 13 for the same error)
+    static __constant__ double BP_EXP_C[12] = {0x1.0000000000000p+0, 0x1.0000000000000p+0, 0x1.0000000000011p-1, 0x1.555555555556ap-3, 0x1.555555554f0b8p-5,
+                                               0x1.111111110c4b2p-7, 0x1.6c16c188007dap-10, 0x1.a01a01bec709ap-13, 0x1.a01991a047428p-16, 0x1.71ddd953a34f1p-19,
+                                               0x1.28b410c11893dp-22, 0x1.af8db1c459b51p-26};
     static __constant__ double BP_ATH_C[17] = {1.0, 1.0 / 3, 1.0 / 5, 1.0 / 7, 1.0 / 9, 1.0 / 11, 1.0 / 13, 1.0 / 15, 1.0 / 17, 1.0 / 19, 1.0 / 21,
                                                1.0 / 23, 1.0 / 25, 1.0 / 27, 1.0 / 29, 1.0 / 31, 1.0 / 33}; // 1/(2k+1)
-    // -log2(e), 1.5 * 2^52 (rounds to an integer in the low mantissa bits), ln 2 high and low part, argument clamp (e^-708 ~ 3e-308)
+    // -log2(e), 1.5 * 2^52 (rounds to an integer in the low mantissa bits), ln 2 high and low part, (argument clamp 708: e^-708 ~ 3e-308)
     static __constant__ double BP_K[5] = {-1.4426950408889634, 6755399441055744.0, 0.6931471803691238, 1.9082149292705877e-10, 708.0};
 
-    __device__ __forceinline__ double bp_exp_neg(double z) // e^-z, z >= 0
+    __device__ __forceinline__ double bp_exp_neg(double z) // e^-z, z >= 0 (clamped at ~708: e^-708 is still a normal number)
     {
-        const double zc = fmin(z, BP_K[4]);
+        const double zc = __hiloint2double(min(__double2hiint(z), 0x40862000), __double2loint(z)); // z >= 0: the high words order like integers
         const double t = __fma_rn(zc, BP_K[0], BP_K[1]);
         const double k = t - BP_K[1];               // round(-z log2 e)
         double r = __fma_rn(k, -BP_K[2], -zc);      // -z - k ln 2, |r| <= ln 2 / 2
         r = __fma_rn(k, -BP_K[3], r);
-        double p = BP_EXP_C[13];
+        double p = BP_EXP_C[11];
 #pragma unroll
-        for (int i = 12; i >= 0; --i) p = __fma_rn(p, r, BP_EXP_C[i]);
+        for (int i = 10; i >= 0; --i) p = __fma_rn(p, r, BP_EXP_C[i]);
         return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p)); // * 2^k (k >= -1022)
     }
     __device__ __forceinline__ double bp_log_ratio(double u, double v) // log((1 + u) / (1 + v)), u, v in [0, 1]
@@ -264,24 +269,26 @@ namespace b200
     // d logarithms log(D / N) -- ~45 FP64 instructions per edge for any degree (d = 7: 3.2 x fewer than the pairwise chain), all
     // of them independent chains instead of one d-deep dependent recursion.  Unlike tanh / atanh this form has no cancellation:
     // E keeps full relative precision down to e^-708, and log(D / N) = e0 ln 2 + 2 atanh((D - N') / (D + N')) with N' = N 2^e0
-    // brought within a factor sqrt 2 of D is accurate to ~2e-16 absolute + 1e-16 relative -- the same as the reference's own
+    // brought within a factor 2^0.59 of D is accurate to ~2e-16 absolute + 1e-16 relative -- the same as the reference's own
     // double expression (tests/study_bp_edomain.py: posteriors after 50 iterations within 1.3e-7 of the oracle's, bar 1e-4).
     // Large inputs: with m = min |x| over the check (taken from the high words), all inputs are shifted by max(0, m - 40) before
     // the exponential and the shift is added back after the logarithm (exact: once every E <= e^-40 the denominators are 1 to
     // 1e-34); an output whose magnitude would exceed ~665 above the shift (inputs beyond the e^-708 clamp decide it: shortened
-    // positions at 99999.9) makes the thread redo the check with the reference's pairwise recursion (`exact` below).
-    static __constant__ double BP_LOG_C[10] = {2.0, 2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19};
+    // positions at 99999.9) makes the thread redo the check with the reference's pairwise recursion.
+    // Per edge: exponential 16 FP64 instructions, logarithm 18 (5 of them the division), ~4 for the products.
+    // 2 atanh(w) / w as a function of s = w^2 on [0, 0.0405]: minimax polynomial of degree 7 (6e-17; profiles/gen_bp_tables.py)
+    static __constant__ double BP_LOG_C[8] = {0x1.0000000000000p+1, 0x1.55555555558bap-1, 0x1.99999998be9bbp-2, 0x1.249249cc9eae0p-2,
+                                              0x1.c71bf34d80545p-3, 0x1.7476dda759777p-3, 0x1.382eecef5e3a5p-3, 0x1.3bc09a1b49468p-3};
     static __constant__ double BP_LOG_K[3] = {0.6931471805599453, 4503601774854144.0 /* 2^52 + 2^31 */, 40.0};
 
     // log(D / N) + shift for 0 < N <~ D, both normal; far: beyond the range the clamp of bp_exp_neg keeps exact
     __device__ __forceinline__ double bp_log_frac(double N, double D, double shift, bool &far)
     {
-        const uint32_t hn = (uint32_t)__double2hiint(N), hd = (uint32_t)__double2hiint(D);
-        int e0 = (int)(hd >> 20) - (int)(hn >> 20);
-        const float fn = __uint_as_float(0x3f800000u | ((hn & 0xfffffu) << 3)), fd = __uint_as_float(0x3f800000u | ((hd & 0xfffffu) << 3));
-        e0 += (fd > 1.41421354f * fn) ? 1 : 0;
-        e0 -= (fn > 1.41421354f * fd) ? 1 : 0;
-        const double Ns = __hiloint2double((int)(hn + ((uint32_t)e0 << 20)), __double2loint(N)); // N 2^e0, within sqrt 2 of D
+        // e0 = round of the difference of the high words (a piecewise-linear log2, off by < 0.086 each): D / (N 2^e0) lies within
+        // 2^+-0.59, |w| <= 0.2003
+        const int hn = __double2hiint(N), hd = __double2hiint(D);
+        const int e0 = (hd - hn + 0x80000) >> 20;
+        const double Ns = __hiloint2double(hn + (e0 << 20), __double2loint(N));
         const double num = D - Ns, den = D + Ns;
         // num / den, den in [1, 2^9): reciprocal seed (2^-23), one Newton step, quotient, one residual correction (error e^4)
         double rc;
@@ -290,9 +297,9 @@ namespace b200
         double w = num * rc;
         w = __fma_rn(__fma_rn(-den, w, num), rc, w);
         const double s = w * w;
-        double p = BP_LOG_C[9];
+        double p = BP_LOG_C[7];
 #pragma unroll
-        for (int i = 8; i >= 0; --i) p = __fma_rn(p, s, BP_LOG_C[i]);
+        for (int i = 6; i >= 0; --i) p = __fma_rn(p, s, BP_LOG_C[i]);
         far = e0 > 960;
         const double e0d = __hiloint2double(0x43300000, (int)((uint32_t)e0 ^ 0x80000000u)) - BP_LOG_K[1];
         return __fma_rn(w, p, __fma_rn(e0d, BP_LOG_K[0], shift));

@@ -259,6 +259,12 @@ namespace b200
     };
 
     // raw value of smaller magnitude (min-sum keeps raw values; magnitude and sign are fixed at the store)
+#ifndef B200_CN_ANY_ATTR
+#define B200_CN_ANY_ATTR __noinline__
+#endif
+#ifndef B200_BP_CALL_FROM
+#define B200_BP_CALL_FROM 5 // shared-memory fp64 sum-product: check bodies of this degree and above are calls (0: all inlined)
+#endif
 #ifndef B200_BP_EDOMAIN
 #define B200_BP_EDOMAIN 1 // fp64 sum-product checks of degree 3..8 on E = e^-|x| (kernels.cuh bp_check); 0: the pairwise recursion (A/B builds)
 #endif
@@ -435,10 +441,22 @@ namespace b200
         }
     };
 
+    // Out-of-line copy of a fixed-degree body.  The fp64 sum-product bodies of degree >= B200_BP_CALL_FROM need more registers than
+    // the 128 a 512-thread CTA leaves; inlined, they make the allocator spill the decode loop's state around the whole degree
+    // switch, and with the L1 carved out for shared memory every reload is an L2 round trip -- also on codes that never execute
+    // those bodies (h.txt: check degrees 3 and 4).  Behind a call only the call site pays.
+    template <typename T, typename IdxT, bool SMEM, int LANES, int ALG, int D, int CSRC, bool TMW, bool PAR>
+    __device__ __noinline__ uint32_t cn4_call(typename PtrOf<SMEM>::type out_sub, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type ip, uint32_t tc, uint32_t fz)
+    {
+        uint32_t nx[D];
+        IdxLoad<SMEM, IdxT, LANES, D>::load(ip, nx);
+        return Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TMW, PAR>(out_sub, c2v0, nx, ip, false, tc, fz);
+    }
+
     // arbitrary degree (9..64): running min1/min2 + sign mask for min-sum, parked forward values for box-plus.
     // The index block is walked in 16-byte chunks (chunk q at ip + q*NPW*16).
     template <typename T, typename IdxT, bool SMEM, int LANES, int ALG>
-    __device__ __noinline__ uint32_t cn4_any(typename PtrOf<SMEM>::type out_sub, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type ip, int deg,
+    __device__ B200_CN_ANY_ATTR uint32_t cn4_any(typename PtrOf<SMEM>::type out_sub, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type ip, int deg,
                                              uint32_t fz)
     {
         typedef Vec<T> V;
@@ -616,8 +634,19 @@ namespace b200
     // ET: compiled with early termination support (syndrome in the check phase); ET = false serves --no-early-term runs.
     // MINB: resident CTAs per SM the kernel is compiled for (register budget 65536 / (MINB * B200_TILE_MAX_THREADS)): 1 everywhere
     // except the narrow global-residency min-sum variant (2: more warps, 64 registers), which quasi-cyclic codes prefer.
+    // The shared-memory fp64 sum-product kernel is compiled for fewer threads: its check bodies want ~170 registers, and at 128
+    // the allocator parks the decode loop's CTA-uniform state in local memory -- with the L1 carved out for shared memory every
+    // reload after a barrier is an L2 round trip with all warps waiting (ncu: 16 % of the warp time in long-scoreboard stalls).
+    // 12 warps x 168 registers beat 16 x 128 by 11 % on h.txt.
+#ifndef B200_BP64_SMEM_THREADS
+#define B200_BP64_SMEM_THREADS 384
+#endif
+    constexpr int tile_thread_cap(bool f64, int alg, bool smem)
+    {
+        return (f64 && alg == ALG_BP && smem && B200_BP64_SMEM_THREADS < B200_TILE_MAX_THREADS) ? B200_BP64_SMEM_THREADS : B200_TILE_MAX_THREADS;
+    }
     template <typename T, typename IdxT, int ALG, bool SMEM, int LANES, bool TM, bool ET, int MINB>
-    __global__ void __launch_bounds__(B200_TILE_MAX_THREADS, MINB) tile4_kernel(const K4Params p)
+    __global__ void __launch_bounds__(tile_thread_cap(sizeof(T) == 8, ALG, SMEM), MINB) tile4_kernel(const K4Params p)
     {
         static_assert(SMEM || !TM, "the TMEM mirror belongs to shared-memory residency");
         typedef typename PtrOf<SMEM>::type P;
@@ -1085,8 +1114,11 @@ namespace b200
         B200_PT_HDR                                                                                          \
         _Pragma("unroll 1") for (; nt > 0; --nt)                                                             \
         {                                                                                                    \
+            if constexpr (B200_BP_CALL_FROM > 0 && SMEM && ALG == ALG_BP && sizeof(T) == 8 && D >= B200_BP_CALL_FROM) \
+                bad |= cn4_call<T, IdxT, SMEM, LANES, ALG, D, CSRC, TM, ET>(out_sub, c2v0, ip, tc, fz) & keep; \
             ip += NPW * ST;                                                                                  \
-            bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM, ET>(out_sub, c2v0, nx, ip, nt > 1, tc, fz) & keep; \
+            if constexpr (!(B200_BP_CALL_FROM > 0 && SMEM && ALG == ALG_BP && sizeof(T) == 8 && D >= B200_BP_CALL_FROM)) \
+                bad |= Cn4<T, IdxT, SMEM, LANES, ALG, D>::template run<CSRC, TM, ET>(out_sub, c2v0, nx, ip, nt > 1, tc, fz) & keep; \
             c2v0 += D * 512;                                                                                 \
             if constexpr (TM) tc += 4 * D;                                                                   \
         }                                                                                                    \

@@ -3,13 +3,17 @@
  * reciprocal seed + Newton steps (<= 1 ulp) and this file with the correctly rounded '/'.  Included by
  * tests/study_bp_edomain.py into a copy of the C oracle. */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
-static const double ED_EXPC[14] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
-                                   1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
-static const double ED_LOGC[10] = {2.0, 2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19};
+static const double ED_EXPC[12] = {0x1.0000000000000p+0, 0x1.0000000000000p+0, 0x1.0000000000011p-1, 0x1.555555555556ap-3, 0x1.555555554f0b8p-5,
+                                   0x1.111111110c4b2p-7, 0x1.6c16c188007dap-10, 0x1.a01a01bec709ap-13, 0x1.a01991a047428p-16, 0x1.71ddd953a34f1p-19,
+                                   0x1.28b410c11893dp-22, 0x1.af8db1c459b51p-26};
+static const double ED_LOGC[8] = {0x1.0000000000000p+1, 0x1.55555555558bap-1, 0x1.99999998be9bbp-2, 0x1.249249cc9eae0p-2,
+                                  0x1.c71bf34d80545p-3, 0x1.7476dda759777p-3, 0x1.382eecef5e3a5p-3, 0x1.3bc09a1b49468p-3};
+static double ed_max_s = 0;
 
 static inline uint32_t ed_hi(double v) { uint64_t b; memcpy(&b, &v, 8); return (uint32_t)(b >> 32); }
 static inline uint32_t ed_lo(double v) { uint64_t b; memcpy(&b, &v, 8); return (uint32_t)b; }
@@ -18,27 +22,24 @@ static inline double ed_mk(uint32_t hi, uint32_t lo) { uint64_t b = ((uint64_t)h
 static double ed_exp_neg(double z) /* e^-z, z >= 0, clamped at 708 */
 {
     const double K0 = -1.4426950408889634, K1 = 6755399441055744.0, K2 = 0.6931471803691238, K3 = 1.9082149292705877e-10;
-    double zc = fmin(z, 708.0), t = fma(zc, K0, K1), k = t - K1, r = fma(k, -K2, -zc), p = ED_EXPC[13];
+    const int32_t zh = (int32_t)ed_hi(z);
+    double zc = ed_mk((uint32_t)(zh < 0x40862000 ? zh : 0x40862000), ed_lo(z)), t = fma(zc, K0, K1), k = t - K1, r = fma(k, -K2, -zc), p = ED_EXPC[11];
     r = fma(k, -K3, r);
-    for (int i = 12; i >= 0; --i) p = fma(p, r, ED_EXPC[i]);
+    for (int i = 10; i >= 0; --i) p = fma(p, r, ED_EXPC[i]);
     return ed_mk(ed_hi(p) + (ed_lo(t) << 20), ed_lo(p));
 }
 
 /* log(D / N) + shift for 0 < N <= D (both normal numbers); *far: the result is beyond the range the clamp of ed_exp_neg keeps exact */
 static double ed_log_ratio(double N, double D, double shift, int *far)
 {
-    const uint32_t hn = ed_hi(N), hd = ed_hi(D);
-    int e0 = (int)(hd >> 20) - (int)(hn >> 20);
-    float fn, fd;
-    uint32_t bn = 0x3f800000u | ((hn & 0xfffffu) << 3), bd = 0x3f800000u | ((hd & 0xfffffu) << 3);
-    memcpy(&fn, &bn, 4); memcpy(&fd, &bd, 4);
-    e0 += (fd > 1.41421354f * fn) ? 1 : 0;
-    e0 -= (fn > 1.41421354f * fd) ? 1 : 0;
-    const double Ns = ed_mk(hn + ((uint32_t)e0 << 20), ed_lo(N));
+    const int32_t hn = (int32_t)ed_hi(N), hd = (int32_t)ed_hi(D);
+    const int e0 = (hd - hn + 0x80000) >> 20;
+    const double Ns = ed_mk((uint32_t)(hn + e0 * (1 << 20)), ed_lo(N));
     const double w = (D - Ns) / (D + Ns);
     const double s = w * w;
-    double p = ED_LOGC[9];
-    for (int i = 8; i >= 0; --i) p = fma(p, s, ED_LOGC[i]);
+    double p = ED_LOGC[7];
+    for (int i = 6; i >= 0; --i) p = fma(p, s, ED_LOGC[i]);
+    if (s > ed_max_s) { ed_max_s = s; if (s > 0.0405) { fprintf(stderr, "bp_log_frac: s = %g out of range\n", s); abort(); } }
     *far = e0 > 960;
     return fma(w, p, fma((double)e0, 0.6931471805599453, shift));
 }
