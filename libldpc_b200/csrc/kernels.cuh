@@ -305,71 +305,114 @@ namespace b200
         return __fma_rn(w, p, __fma_rn(e0d, BP_LOG_K[0], shift));
     }
 
-    template <int D>
-    __device__ __forceinline__ void bp_check(const double (&x)[D], double (&r)[D])
+    // E(x [+] y) from E(x), E(y) as a plain number: (a + b) / (1 + a b), a, b in (0, 1] (the arbitrary-degree path)
+    __device__ __forceinline__ double bp_join(double a, double b)
+    {
+        const double num = a + b, den = __fma_rn(a, b, 1.0);
+        double rc;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
+        rc = __fma_rn(rc, __fma_rn(-den, rc, 1.0), rc);
+        const double q = num * rc;
+        return __fma_rn(__fma_rn(-den, q, num), rc, q);
+    }
+
+    // W frame lanes of one check at a time: the fast paths of all lanes form ONE basic block (the rare exact path is tested once,
+    // after all of them), so the scheduler interleaves W * D independent chains and every coefficient load serves W lanes.
+    template <int D, int W>
+    __device__ __forceinline__ void bp_check(const double (&x)[W][D], double (&r)[W][D])
     {
         static_assert(D >= 3, "degree-2 checks swap their inputs");
-        uint32_t sx = 0, mh = 0x7fffffffu;
+        uint32_t sx[W];
+        double shift[W], E[W][D], FN[W][D - 1], FD[W][D - 1];
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+        {
+            uint32_t mh = 0x7fffffffu;
+            sx[w] = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+            {
+                const uint32_t h = (uint32_t)__double2hiint(x[w][k]);
+                sx[w] ^= h;
+                mh = min(mh, h & 0x7fffffffu);
+            }
+            shift[w] = (mh >= 0x40440000u && mh < 0x7ff00000u) ? __hiloint2double((int)mh, 0) - BP_LOG_K[2] : 0.0;
+        }
 #pragma unroll
         for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int w = 0; w < W; ++w) E[w][k] = bp_exp_neg(fabs(x[w][k]) - shift[w]);
+        bool anyfar = false, far;
+#pragma unroll
+        for (int w = 0; w < W; ++w)
         {
-            const uint32_t h = (uint32_t)__double2hiint(x[k]);
-            sx ^= h;
-            mh = min(mh, h & 0x7fffffffu);
+            FN[w][0] = E[w][0];
+            FD[w][0] = 1.0;
+#pragma unroll
+            for (int k = 1; k < D - 1; ++k)
+            {
+                FN[w][k] = __fma_rn(E[w][k], FD[w][k - 1], FN[w][k - 1]);
+                FD[w][k] = __fma_rn(E[w][k], FN[w][k - 1], FD[w][k - 1]);
+            }
         }
-        const double shift = (mh >= 0x40440000u && mh < 0x7ff00000u) ? __hiloint2double((int)mh, 0) - BP_LOG_K[2] : 0.0;
-        double E[D], FN[D - 1], FD[D - 1];
+        double BN[W], BD[W], QN[W][D], QD[W][D]; // the fractions whose logarithms are the outputs
 #pragma unroll
-        for (int k = 0; k < D; ++k) E[k] = bp_exp_neg(fabs(x[k]) - shift);
-        FN[0] = E[0];
-        FD[0] = 1.0;
-#pragma unroll
-        for (int k = 1; k < D - 1; ++k)
+        for (int w = 0; w < W; ++w)
         {
-            FN[k] = __fma_rn(E[k], FD[k - 1], FN[k - 1]);
-            FD[k] = __fma_rn(E[k], FN[k - 1], FD[k - 1]);
-        }
-        double BN = E[D - 1], BD = 1.0;
-        bool far, anyfar;
-        r[D - 1] = bp_log_frac(FN[D - 2], FD[D - 2], shift, anyfar);
+            BN[w] = E[w][D - 1];
+            BD[w] = 1.0;
+            QN[w][D - 1] = FN[w][D - 2];
+            QD[w][D - 1] = FD[w][D - 2];
 #pragma unroll
-        for (int k = D - 2; k >= 1; --k)
-        {
-            const double N = __fma_rn(FN[k - 1], BD, BN * FD[k - 1]), Dn = __fma_rn(FN[k - 1], BN, FD[k - 1] * BD);
-            r[k] = bp_log_frac(N, Dn, shift, far);
-            anyfar |= far;
-            const double bn = __fma_rn(E[k], BD, BN), bd = __fma_rn(E[k], BN, BD);
-            BN = bn;
-            BD = bd;
-        }
-        r[0] = bp_log_frac(BN, BD, shift, far);
-        anyfar |= far;
-#pragma unroll
-        for (int k = 0; k < D; ++k)
-        {
-            const uint32_t s = (sx ^ (uint32_t)__double2hiint(x[k])) & 0x80000000u;
-            r[k] = __hiloint2double((int)(((uint32_t)__double2hiint(r[k]) & 0x7fffffffu) | s), __double2loint(r[k]));
-        }
-        if (anyfar) // rare: the reference's pairwise recursion, rolled loops over a local copy
-        {
-            double lx[D], lf[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) lx[k] = x[k];
-            lf[0] = lx[0];
-#pragma unroll 1
-            for (int k = 1; k < D; ++k) lf[k] = boxplus(lf[k - 1], lx[k]);
-            double B = lx[D - 1];
-            lf[D - 1] = lf[D - 2];
-#pragma unroll 1
             for (int k = D - 2; k >= 1; --k)
             {
-                const double f = lf[k - 1];
-                lf[k] = boxplus(f, B);
-                B = boxplus(B, lx[k]);
+                QN[w][k] = __fma_rn(FN[w][k - 1], BD[w], BN[w] * FD[w][k - 1]);
+                QD[w][k] = __fma_rn(FN[w][k - 1], BN[w], FD[w][k - 1] * BD[w]);
+                const double bn = __fma_rn(E[w][k], BD[w], BN[w]), bd = __fma_rn(E[w][k], BN[w], BD[w]);
+                BN[w] = bn;
+                BD[w] = bd;
             }
-            lf[0] = B;
+            QN[w][0] = BN[w];
+            QD[w][0] = BD[w];
+        }
 #pragma unroll
-            for (int k = 0; k < D; ++k) r[k] = lf[k];
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int w = 0; w < W; ++w)
+            {
+                const double l = bp_log_frac(QN[w][k], QD[w][k], shift[w], far);
+                anyfar |= far;
+                const uint32_t sg = (sx[w] ^ (uint32_t)__double2hiint(x[w][k])) & 0x80000000u;
+                r[w][k] = __hiloint2double((int)(((uint32_t)__double2hiint(l) & 0x7fffffffu) | sg), __double2loint(l));
+            }
+        if (anyfar) // rare: the reference's pairwise recursion for all W lanes, rolled loops over a local copy
+        {
+            double lx[W][D], lf[W][D];
+#pragma unroll
+            for (int w = 0; w < W; ++w)
+#pragma unroll
+                for (int k = 0; k < D; ++k) lx[w][k] = x[w][k];
+#pragma unroll 1
+            for (int w = 0; w < W; ++w)
+            {
+                lf[w][0] = lx[w][0];
+#pragma unroll 1
+                for (int k = 1; k < D; ++k) lf[w][k] = boxplus(lf[w][k - 1], lx[w][k]);
+                double B = lx[w][D - 1];
+                lf[w][D - 1] = lf[w][D - 2];
+#pragma unroll 1
+                for (int k = D - 2; k >= 1; --k)
+                {
+                    const double f = lf[w][k - 1];
+                    lf[w][k] = boxplus(f, B);
+                    B = boxplus(B, lx[w][k]);
+                }
+                lf[w][0] = B;
+            }
+#pragma unroll
+            for (int w = 0; w < W; ++w)
+#pragma unroll
+                for (int k = 0; k < D; ++k) r[w][k] = lf[w][k];
         }
     }
 #endif

@@ -265,6 +265,9 @@ namespace b200
 #ifndef B200_BP_CALL_FROM
 #define B200_BP_CALL_FROM 5 // shared-memory fp64 sum-product: check bodies of this degree and above are calls (0: all inlined)
 #endif
+#ifndef B200_BP_LANES_TOGETHER
+#define B200_BP_LANES_TOGETHER 1 // fp64 sum-product: both frame lanes of a vector in one basic block (1: shared-memory kernels, 2: all, 0: none)
+#endif
 #ifndef B200_BP_EDOMAIN
 #define B200_BP_EDOMAIN 1 // fp64 sum-product checks of degree 3..8 on E = e^-|x| (kernels.cuh bp_check); 0: the pairwise recursion (A/B builds)
 #endif
@@ -407,13 +410,34 @@ namespace b200
                     }
                     else if constexpr (sizeof(T) == 8 && D >= 3 && B200_BP_EDOMAIN)
                     {
-                        // sum-product in fp64: the same function of the inputs evaluated on E = e^-|x| (kernels.cuh bp_check)
-                        double x[D], y[D];
+                        // sum-product in fp64: the same function of the inputs evaluated on E = e^-|x|, both frame lanes of the
+                        // vector together (kernels.cuh bp_check)
+                        constexpr bool TOGETHER = B200_BP_LANES_TOGETHER == 2 || (B200_BP_LANES_TOGETHER == 1 && SMEM);
+                        if constexpr (TOGETHER)
+                        {
+                            if (e == 0)
+                            {
+                                double x[VEC][D], y[VEC][D];
 #pragma unroll
-                        for (int k = 0; k < D; ++k) x[k] = v[k].e[e];
-                        bp_check<D>(x, y);
+                                for (int w = 0; w < VEC; ++w)
 #pragma unroll
-                        for (int k = 0; k < D; ++k) r[k].e[e] = y[k];
+                                    for (int k = 0; k < D; ++k) x[w][k] = v[k].e[w];
+                                bp_check<D, VEC>(x, y);
+#pragma unroll
+                                for (int w = 0; w < VEC; ++w)
+#pragma unroll
+                                    for (int k = 0; k < D; ++k) r[k].e[w] = y[w][k];
+                            }
+                        }
+                        else
+                        {
+                            double x[1][D], y[1][D];
+#pragma unroll
+                            for (int k = 0; k < D; ++k) x[0][k] = v[k].e[e];
+                            bp_check<D, 1>(x, y);
+#pragma unroll
+                            for (int k = 0; k < D; ++k) r[k].e[e] = y[0][k];
+                        }
                     }
                     else
                     {
@@ -518,8 +542,11 @@ namespace b200
             // box-plus forward/backward with the forward values parked in the output slots: slot k first
             // receives F[k-1]; the backward sweep turns it into f(F[k-1], B[k+1]) (decoder.cpp:33-44).
             // v[k] is needed again by the backward sweep (out and the old c2v are gone by then).
-            V Fp, B;
             V v[64];
+            [[maybe_unused]] unsigned long long smask[VEC];
+            [[maybe_unused]] uint32_t mh[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { smask[e] = 0; mh[e] = 0x7fffffffu; }
             for (int k0 = 0; k0 < deg; k0 += EPC, ip += CSTEP)
             {
                 uint32_t eo[EPC];
@@ -536,28 +563,97 @@ namespace b200
                         for (int e = 0; e < VEC; ++e) c.e[e] = ((fz >> e) & 1u) ? T(0) : c.e[e];
                         V vk;
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) { vk.e[e] = o.e[e] - c.e[e]; par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u; }
-                        v[k] = vk;
-                        if (k == 0) Fp = vk;
-                        else
+                        for (int e = 0; e < VEC; ++e)
                         {
-                            VAcc<SMEM, T, 0>::st(c2v0 + k * CS, Fp); // F[k-1] (slot deg-1 thereby gets its final value)
-#pragma unroll
-                            for (int e = 0; e < VEC; ++e) Fp.e[e] = boxplus(Fp.e[e], vk.e[e]);
+                            vk.e[e] = o.e[e] - c.e[e];
+                            par ^= (o.e[e] <= T(0)) ? (1u << e) : 0u;
+                            if constexpr (sizeof(T) == 8)
+                            {
+                                const uint32_t h = Num<T>::hi(vk.e[e]);
+                                smask[e] |= (unsigned long long)(h >> 31) << k;
+                                mh[e] = min(mh[e], h & 0x7fffffffu);
+                            }
                         }
+                        v[k] = vk;
                     }
                 }
             }
-            B = v[deg - 1];
-            for (int k = deg - 2; k >= 1; --k)
+            bool exact = true;
+            if constexpr (sizeof(T) == 8 && B200_BP_EDOMAIN)
             {
-                const V f = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
-                V r;
+                // fp64: the check on E = e^-|x| (kernels.cuh bp_check): forward and backward values as plain numbers
+                // (one division per step), the outputs as logarithms of the joined fractions; the exponentials are
+                // recomputed in the backward sweep rather than kept in a second local array.
+                double shift[VEC];
+                V Fp, B;
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) { r.e[e] = boxplus(f.e[e], B.e[e]); B.e[e] = boxplus(B.e[e], v[k].e[e]); }
-                VAcc<SMEM, T, 0>::st(c2v0 + k * CS, r);
+                for (int e = 0; e < VEC; ++e)
+                    shift[e] = (mh[e] >= 0x40440000u && mh[e] < 0x7ff00000u) ? __hiloint2double((int)mh[e], 0) - 40.0 : 0.0;
+                for (int k = 0; k < deg; ++k)
+                {
+                    const V vk = v[k];
+                    V Ek;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) Ek.e[e] = bp_exp_neg(fabs(vk.e[e]) - shift[e]);
+                    if (k == 0) Fp = Ek;
+                    else
+                    {
+                        VAcc<SMEM, T, 0>::st(c2v0 + k * CS, Fp); // E of F[k-1]
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) Fp.e[e] = bp_join(Fp.e[e], Ek.e[e]);
+                    }
+                }
+                bool anyfar = false, far;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) B.e[e] = bp_exp_neg(fabs(v[deg - 1].e[e]) - shift[e]);
+                for (int k = deg - 1; k >= 0; --k)
+                {
+                    V f = B;
+                    if (k > 0) f = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                    const V vk = v[k];
+                    V r;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e)
+                    {
+                        double N, Dn;
+                        if (k == deg - 1) { N = f.e[e]; Dn = 1.0; }
+                        else if (k == 0) { N = B.e[e]; Dn = 1.0; }
+                        else { N = f.e[e] + B.e[e]; Dn = __fma_rn(f.e[e], B.e[e], 1.0); }
+                        const double l = bp_log_frac(N, Dn, shift[e], far);
+                        anyfar |= far;
+                        const uint32_t sg = (((uint32_t)__popcll(smask[e]) ^ (uint32_t)(smask[e] >> k)) & 1u) << 31;
+                        r.e[e] = __hiloint2double((int)(((uint32_t)__double2hiint(l) & 0x7fffffffu) | sg), __double2loint(l));
+                        if (k > 0 && k < deg - 1) B.e[e] = bp_join(B.e[e], bp_exp_neg(fabs(vk.e[e]) - shift[e]));
+                    }
+                    VAcc<SMEM, T, 0>::st(c2v0 + k * CS, r);
+                }
+                exact = anyfar; // rare: inputs beyond the clamp of the exponential decide an output
             }
-            VAcc<SMEM, T, 0>::st(c2v0, B);
+            if (exact)
+            {
+                V Fp, B;
+                for (int k = 0; k < deg; ++k)
+                {
+                    const V vk = v[k];
+                    if (k == 0) Fp = vk;
+                    else
+                    {
+                        VAcc<SMEM, T, 0>::st(c2v0 + k * CS, Fp); // F[k-1] (slot deg-1 thereby gets its final value)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) Fp.e[e] = boxplus(Fp.e[e], vk.e[e]);
+                    }
+                }
+                B = v[deg - 1];
+                for (int k = deg - 2; k >= 1; --k)
+                {
+                    const V f = VAcc<SMEM, T, 0>::ld(c2v0 + k * CS);
+                    V r;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) { r.e[e] = boxplus(f.e[e], B.e[e]); B.e[e] = boxplus(B.e[e], v[k].e[e]); }
+                    VAcc<SMEM, T, 0>::st(c2v0 + k * CS, r);
+                }
+                VAcc<SMEM, T, 0>::st(c2v0, B);
+            }
         }
         return par;
     }

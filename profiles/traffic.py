@@ -5,6 +5,7 @@ import csv
 import io
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -43,8 +44,15 @@ for n in names:
             inst = v
         kern = row[ki]
     res[n] = int(tot)
-    detail[n] = {"kernel": kern, "gpu_time_ms_under_ncu": ms, "dram_bytes": int(tot), "warp_instructions": inst, "fp64_warp_instructions": fp64}
+    m = re.findall(r"'edge_iterations': (\d+)", r.stdout)   # ctx.stats() of the measured launch, printed by traffic_cmd.py
+    detail[n] = {"kernel": kern, "gpu_time_ms_under_ncu": ms, "dram_bytes": int(tot), "warp_instructions": inst, "fp64_warp_instructions": fp64,
+                 "edge_iterations": int(m[-1]) if m else None}
     print(n, detail[n], flush=True)
+# derived: FP64 thread instructions per edge-iteration of the sum-product kernels, DRAM bytes over the algorithmic 32 B per edge-iteration
+res["_fp64_thread_instructions_per_edge_iteration"] = {n: 32.0 * d["fp64_warp_instructions"] / d["edge_iterations"] for n, d in detail.items()
+                                                       if n in ("C1_bp_fixed50", "C1_et_sweep", "C4_dvbs2_bp_noet") and d.get("edge_iterations") and d.get("fp64_warp_instructions")}
+res["_algorithmic_bytes"] = {n: 32 * d["edge_iterations"] for n, d in detail.items() if n in ("headline", "C3_bg1_ms", "C4_dvbs2_bp_noet") and d.get("edge_iterations")}
+res["_dram_over_algorithmic"] = {n: detail[n]["dram_bytes"] / b for n, b in res["_algorithmic_bytes"].items()}
 res["_source"] = "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of one launch per configuration (profiles/traffic.py -> traffic_cmd.py, same frame counts as bench.py)"
 res["_detail"] = detail
 json.dump(res, open(os.path.join(out_dir, "roofline_traffic.json"), "w"), indent=1)

@@ -21,14 +21,17 @@ CFG = {  # name: (code, channel, x, decoding, early_term, frames)
     "C2_et": ("h", "AWGN", -4.5, "BP_MS", True, 148 * 4 * 256),
     "C5_bsc": ("h", "BSC", 0.08, "BP_MS", True, 1 << 22),
     "C5_bec": ("h", "BEC", 0.70, "BP", True, 1 << 24),
-    "C3_bg1_ms": ("bg1", "AWGN", -0.5, "BP_MS", False, 4096),
-    "C4_dvbs2_bp_noet": ("dvbs2", "AWGN", 1.0, "BP", False, 2048),
+    "C3_bg1_ms": ("bg1", "AWGN", -0.5, "BP_MS", False, 148 * 32),
+    "C4_dvbs2_bp_noet": ("dvbs2", "AWGN", 1.0, "BP", False, 148 * 16),
 }
 name = sys.argv[1]
 code, ch, x, dec, et, frames = CFG[name]
 path = H if code == "h" else gen_codes.ensure()[code]
 ctx = api.Context(path, "", device=0)
+if code != "h":
+    ctx.prepare(dec, 50, et)   # the shape trial of a long sweep (kernels outside the NVTX range are not profiled)
 ctx.sim_point(ch, x, seed=1, point=0, frame0=0, nframes=min(frames, 1 << 16), decoding=dec, iterations=50, early_term=et)   # warm-up / shape trial
+ctx.stats(reset=True)
 torch.cuda.nvtx.range_push("measure")
 r = ctx.sim_point(ch, x, seed=2, point=0, frame0=0, nframes=frames, decoding=dec, iterations=50, early_term=et)
 torch.cuda.synchronize()

@@ -58,6 +58,25 @@ static void edomain_check(const double *x, int d, double *out)
     for (int j = 0; j < d; ++j) { const uint32_t h = ed_hi(x[j]); sx ^= h; mh = (h & 0x7fffffffu) < mh ? (h & 0x7fffffffu) : mh; }
     const double shift = (mh >= 0x40440000u && mh < 0x7ff00000u) ? ed_mk(mh, 0) - 40.0 : 0.0; /* min |x| (truncated) >= 40: all E <= e^-40 after the shift */
     for (int j = 0; j < d; ++j) E[j] = ed_exp_neg(fabs(x[j]) - shift);
+    if (d > 8)
+    { /* arbitrary-degree path (tile4.cuh cn4_any): forward / backward values as plain numbers, one division per step */
+        int far, anyfar = 0;
+        double B = E[d - 1];
+        FN[0] = E[0];
+        for (int j = 1; j < d - 1; ++j) FN[j] = (FN[j - 1] + E[j]) / fma(FN[j - 1], E[j], 1.0);
+        out[d - 1] = ed_log_ratio(FN[d - 2], 1.0, shift, &far); anyfar |= far;
+        for (int j = d - 2; j >= 1; --j)
+        {
+            out[j] = ed_log_ratio(FN[j - 1] + B, fma(FN[j - 1], B, 1.0), shift, &far); anyfar |= far;
+            B = (B + E[j]) / fma(B, E[j], 1.0);
+        }
+        out[0] = ed_log_ratio(B, 1.0, shift, &far); anyfar |= far;
+        if (!anyfar)
+        {
+            for (int j = 0; j < d; ++j) out[j] = copysign(out[j], ((sx ^ ed_hi(x[j])) >> 31) ? -1.0 : 1.0);
+            return;
+        }
+    }
     FN[0] = E[0]; FD[0] = 1.0;
     for (int j = 1; j < d - 1; ++j) { FN[j] = fma(E[j], FD[j - 1], FN[j - 1]); FD[j] = fma(E[j], FN[j - 1], FD[j - 1]); }
     double BN = E[d - 1], BD = 1.0;
