@@ -82,6 +82,9 @@ def test_decode_vs_oracle_seeded(gpu_ctx, oracle_code, decoding, et, iters):
     llr[4, ::7] = -0.0
     llr[5, :] = np.where(rng.random(oracle_code.nc) < 0.2, -1.5, 1.5)  # BSC-like two-valued input
     llr[6, :200] = 99999.9
+    llr[7, :] *= 300.0                         # magnitudes of several hundred: the shifted exponentials of the sum-product check node
+    llr[8, ::3] = 99999.9                      # checks whose other inputs are all beyond e^-708: its exact (pairwise) path
+    llr[9, ::2] *= 1e-9
     ro, rc, ri = oracle_code.decode(llr, iters, et, decoding == "BP_MS")
     out, hard, its = gpu_ctx.decode_batch(llr, decoding, iters, et)
     assert np.array_equal(its, ri)
