@@ -1,5 +1,5 @@
 """Short, deterministic workload for ncu captures (a few launches of the dominant kernel).
-usage: python profiles/profile_cmd.py [ms|bp|ms32|et] [frames] [frames_per_cta] [threads_per_cta] [codefile]
+usage: python profiles/profile_cmd.py [ms|bp|ms32|et|bpet] [frames] [frames_per_cta] [threads_per_cta] [codefile]
 PAIR=1 in the environment: the two-CTAs-per-SM shape (one lane, 256 threads, 16-bit index tables, 296 CTAs)."""
 import os
 import sys
@@ -17,9 +17,9 @@ ctx = api.Context(code, "", device=0)
 ctx.set_tuning(precision=api.F32 if mode == "ms32" else api.F64, frames_per_cta=fpc, threads_per_cta=threads)
 if os.environ.get("PAIR") == "1":
     ctx.set_tuning(frames_per_cta=4 if mode == "ms32" else 2, threads_per_cta=256, idx16=2, ctas=296)
-dec = "BP" if mode == "bp" else "BP_MS"
+dec = "BP" if mode in ("bp", "bpet") else "BP_MS"
 snr = float(os.environ.get("SNR", "-4.5"))   # e.g. SNR=3 with mode et: the refill-dominated regime
 for i in range(3):
-    r = ctx.sim_point("AWGN", snr, seed=0, point=0, frame0=i * frames, nframes=frames, decoding=dec, iterations=50, early_term=(mode == "et"))
+    r = ctx.sim_point("AWGN", snr, seed=0, point=0, frame0=i * frames, nframes=frames, decoding=dec, iterations=50, early_term=(mode in ("et", "bpet")))
     print(r)
 print(ctx.stats())
