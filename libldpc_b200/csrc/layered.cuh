@@ -128,6 +128,65 @@ namespace b200
             V v[64], F[64];
             uint32_t eo[64];
             for (int k = 0; k < deg; ++k) v[k] = load_v(k, eo[k]);
+            if constexpr (sizeof(T) == 8 && B200_BP_EDOMAIN)
+            {
+                // fp64: the same function of the inputs on E = e^-|x| (kernels.cuh bp_check; arbitrary degree as in tile4.cuh
+                // cn4_any): d exponentials, forward / backward values as plain numbers, d logarithms of the joined fractions.
+                // All outputs are formed before the first in-place store, so the rare exact path below can still take over.
+                if (deg >= 3)
+                {
+                    unsigned long long smask[VEC];
+                    double shift[VEC];
+                    V Ek[64], R[64];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e)
+                    {
+                        uint32_t mh = 0x7fffffffu;
+                        smask[e] = 0;
+                        for (int k = 0; k < deg; ++k)
+                        {
+                            const uint32_t h = Num<T>::hi(v[k].e[e]);
+                            smask[e] |= (unsigned long long)(h >> 31) << k;
+                            mh = min(mh, h & 0x7fffffffu);
+                        }
+                        shift[e] = (mh >= 0x40440000u && mh < 0x7ff00000u) ? __hiloint2double((int)mh, 0) - 40.0 : 0.0;
+                    }
+                    for (int k = 0; k < deg; ++k)
+                    {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) Ek[k].e[e] = bp_exp_neg(fabs(v[k].e[e]) - shift[e]);
+                        if (k == 0) F[0] = Ek[0];
+                        else if (k < deg - 1)
+                        {
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) F[k].e[e] = bp_join(F[k - 1].e[e], Ek[k].e[e]);
+                        }
+                    }
+                    bool anyfar = false, far;
+                    V B = Ek[deg - 1];
+                    for (int k = deg - 1; k >= 0; --k)
+                    {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e)
+                        {
+                            double N, Dn;
+                            if (k == deg - 1) { N = F[deg - 2].e[e]; Dn = 1.0; }
+                            else if (k == 0) { N = B.e[e]; Dn = 1.0; }
+                            else { N = F[k - 1].e[e] + B.e[e]; Dn = __fma_rn(F[k - 1].e[e], B.e[e], 1.0); }
+                            const double l = bp_log_frac(N, Dn, shift[e], far);
+                            anyfar |= far;
+                            const uint32_t sg = (((uint32_t)__popcll(smask[e]) ^ (uint32_t)(smask[e] >> k)) & 1u) << 31;
+                            R[k].e[e] = __hiloint2double((int)(((uint32_t)__double2hiint(l) & 0x7fffffffu) | sg), __double2loint(l));
+                            if (k > 0 && k < deg - 1) B.e[e] = bp_join(B.e[e], Ek[k].e[e]);
+                        }
+                    }
+                    if (!anyfar)
+                    {
+                        for (int k = deg - 1; k >= 0; --k) store(k, eo[k], v[k], R[k]);
+                        return;
+                    }
+                }
+            }
             F[0] = v[0];
             for (int k = 1; k < deg; ++k)
             {
