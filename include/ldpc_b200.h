@@ -118,7 +118,7 @@ typedef struct
     int precision;        /* LDPC_B200_F64 (bit-exact parity mode, default) | LDPC_B200_F32 */
     int residency;        /* LDPC_B200_AUTO | _SMEM | _GLOBAL */
     int frames_per_cta;   /* 0 = auto (power of two, 1..32) */
-    int threads_per_cta;  /* 0 = auto */
+    int threads_per_cta;  /* 0 = auto; capped at the kernel's build (512; 384 for the shared-memory fp64 sum-product kernel) */
     int ctas;             /* 0 = auto (148 x resident CTAs) */
     int bec_deg1_compat;  /* 1 (default) = erased degree-1 variable nodes send 0 like the reference's UB outcome */
     int tmem;             /* 0 = auto (Tensor-Memory mirror of thread-private state when it fits), 1 = off */
