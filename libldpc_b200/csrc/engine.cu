@@ -178,8 +178,6 @@ namespace b200
         device_name_ = prop.name;
         smem_optin_ = prop.sharedMemPerBlockOptin;
         smem_per_sm_ = prop.sharedMemPerMultiprocessor;
-        if (const char *g = std::getenv("LDPC_B200_L2_FETCH")) // experiment: L2 fetch granularity hint (32 / 64 / 128 bytes)
-            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
         cudaStream_t s;
         CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         stream_ = s;
