@@ -426,6 +426,29 @@ def test_full_size_counters_identical_across_kernel_variants(gpu_ctx):
     assert abs(a["fec"] - b["fec"]) <= 0.03 * b["fec"] + 5
 
 
+def test_bp_counters_identical_across_kernel_shapes(gpu_ctx):
+    """fp64 sum-product: one CTA x 384 threads, two CTAs x 192 threads with 16-bit tables (the bench shape), without the TMEM mirror,
+    and global residency (per-lane evaluation, bodies inlined) perform the same operations per frame: identical counters."""
+    from libldpc_b200 import api
+    n = 148 * 4 * 16
+    auto = dict(frames_per_cta=0, threads_per_cta=0, ctas=0)
+    res, shapes = {}, {}
+    for name, t in (("one", dict(residency=api.SMEM, tmem=0, idx16=1, **auto)),
+                    ("pair", dict(residency=api.SMEM, tmem=0, idx16=2, frames_per_cta=2, threads_per_cta=192, ctas=296)),
+                    ("no-mirror", dict(residency=api.SMEM, tmem=1, idx16=0, **auto)), ("global", dict(residency=api.GLOBAL, tmem=0, idx16=0, **auto))):
+        gpu_ctx.set_tuning(precision=api.F64, **t)
+        res[name] = {et: gpu_ctx.sim_point("AWGN", -4.6, seed=5, point=2, frame0=12345, nframes=n, decoding="BP", iterations=25, early_term=et) for et in (True, False)}
+        st = gpu_ctx.stats()
+        shapes[name] = (st["frames_per_cta"], st["threads_per_cta"], st["ctas"])
+    gpu_ctx.set_tuning(residency=api.AUTO, tmem=0, idx16=0, **auto)
+    assert shapes["one"] == (4, 384, 148) and shapes["pair"] == (2, 192, 296), shapes
+    for et in (True, False):
+        ref = {k: res["one"][et][k] for k in ("fec", "bec", "frames", "iters")}
+        assert ref["frames"] == n and ref["fec"] > 0
+        for name in ("pair", "no-mirror", "global"):
+            assert {k: res[name][et][k] for k in ("fec", "bec", "frames", "iters")} == ref, (name, et)
+
+
 @pytest.mark.parametrize("et,iters,compat", [(True, 50, 1), (False, 7, 1), (True, 20, 0), (True, 1, 1)])
 def test_bec_bit_sliced_sweep_equals_bytewise_and_oracle(gpu_ctx, oracle_code, et, iters, compat):
     """Erasure sweep: the bit-sliced kernel (32 frames per word, shared memory) against the byte-wise kernel (forced by
