@@ -259,9 +259,6 @@ namespace b200
     };
 
     // raw value of smaller magnitude (min-sum keeps raw values; magnitude and sign are fixed at the store)
-#ifndef B200_CN_ANY_ATTR
-#define B200_CN_ANY_ATTR __noinline__
-#endif
 #ifndef B200_BP_CALL_FROM
 #define B200_BP_CALL_FROM 5 // shared-memory fp64 sum-product: check bodies of this degree and above are calls (0: all inlined)
 #endif
@@ -269,7 +266,7 @@ namespace b200
 #define B200_BP_LANES_TOGETHER 1 // fp64 sum-product: both frame lanes of a vector in one basic block (1: shared-memory kernels, 2: all, 0: none)
 #endif
 #ifndef B200_BP_EDOMAIN
-#define B200_BP_EDOMAIN 1 // fp64 sum-product checks of degree 3..8 on E = e^-|x| (kernels.cuh bp_check); 0: the pairwise recursion (A/B builds)
+#define B200_BP_EDOMAIN 1 // fp64 sum-product checks on E = e^-|x| (kernels.cuh bp_check; cn4_any and layered.cuh for arbitrary degree); 0: the pairwise recursion (A/B builds)
 #endif
     template <typename T> __device__ __forceinline__ T min_mag(T a, T b) { return (Num<T>::abs(b) < Num<T>::abs(a)) ? b : a; }
     // |mag| with the sign bit of word s (bit 31)
@@ -480,7 +477,7 @@ namespace b200
     // arbitrary degree (9..64): running min1/min2 + sign mask for min-sum, parked forward values for box-plus.
     // The index block is walked in 16-byte chunks (chunk q at ip + q*NPW*16).
     template <typename T, typename IdxT, bool SMEM, int LANES, int ALG>
-    __device__ B200_CN_ANY_ATTR uint32_t cn4_any(typename PtrOf<SMEM>::type out_sub, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type ip, int deg,
+    __device__ __noinline__ uint32_t cn4_any(typename PtrOf<SMEM>::type out_sub, typename PtrOf<SMEM>::type c2v0, typename PtrOf<SMEM>::type ip, int deg,
                                              uint32_t fz)
     {
         typedef Vec<T> V;
