@@ -1365,7 +1365,10 @@ namespace b200
                 CUDA_OK(cudaEventCreateWithFlags((cudaEvent_t *)&ev_out_[b], cudaEventDisableTiming));
             }
         }
-        cudaStream_t si = (cudaStream_t)copy_in_, so = (cudaStream_t)copy_out_;
+        // a batch that is a single piece (decode() of the six-symbol ABI: one frame per call) has nothing to overlap: copies and kernel
+        // run in order on ONE stream, without the cross-stream event hand-offs (each costs microseconds of latency)
+        const bool single = pieces.size() == 1;
+        cudaStream_t si = single ? sk : (cudaStream_t)copy_in_, so = single ? sk : (cudaStream_t)copy_out_;
         auto grow = [&](void *&ptr, size_t &cap, size_t need)
         {
             if (need <= cap) return;
@@ -1395,8 +1398,11 @@ namespace b200
             const int64_t m = pieces[pi];
             if (k >= 2) CUDA_OK(cudaStreamWaitEvent(si, (cudaEvent_t)ev_k_[b], 0)); // the kernel that read this input buffer is done
             CUDA_OK(cudaMemcpyAsync(db_in_[b], (const unsigned char *)llr + (size_t)o * nc * esz, (size_t)m * nc * esz, cudaMemcpyHostToDevice, si));
-            CUDA_OK(cudaEventRecord((cudaEvent_t)ev_in_[b], si));
-            CUDA_OK(cudaStreamWaitEvent(sk, (cudaEvent_t)ev_in_[b], 0));
+            if (!single)
+            {
+                CUDA_OK(cudaEventRecord((cudaEvent_t)ev_in_[b], si));
+                CUDA_OK(cudaStreamWaitEvent(sk, (cudaEvent_t)ev_in_[b], 0));
+            }
             if (k >= 2) CUDA_OK(cudaStreamWaitEvent(sk, (cudaEvent_t)ev_out_[b], 0)); // the copy-out of this output buffer is done
             FrameSource src;
             src.kind = SRC_LLR;
@@ -1410,18 +1416,21 @@ namespace b200
             sink.hard_words = (int)hw;
             sink.d_iters = iters ? (int32_t *)db_it_[b] : nullptr;
             launch(dp, src, sink, (uint64_t)m, sk);
-            CUDA_OK(cudaEventRecord((cudaEvent_t)ev_k_[b], sk));
-            CUDA_OK(cudaStreamWaitEvent(so, (cudaEvent_t)ev_k_[b], 0));
+            if (!single)
+            {
+                CUDA_OK(cudaEventRecord((cudaEvent_t)ev_k_[b], sk));
+                CUDA_OK(cudaStreamWaitEvent(so, (cudaEvent_t)ev_k_[b], 0));
+            }
             if (llr_out) CUDA_OK(cudaMemcpyAsync(llr_out + o * nc, db_out_[b], m * nc * sizeof(double), cudaMemcpyDeviceToHost, so));
             if (hard) CUDA_OK(cudaMemcpyAsync(hard + o * nc, db_hard_[b], m * nc, cudaMemcpyDeviceToHost, so));
             if (hard_bits) CUDA_OK(cudaMemcpyAsync(hard_bits + o * hw, db_bits_[b], m * hw * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
             if (iters) CUDA_OK(cudaMemcpyAsync(iters + o, db_it_[b], m * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
-            CUDA_OK(cudaEventRecord((cudaEvent_t)ev_out_[b], so));
+            if (!single) CUDA_OK(cudaEventRecord((cudaEvent_t)ev_out_[b], so));
         }
         CUDA_OK(cudaEventRecord((cudaEvent_t)ev1_, sk));
         CUDA_OK(cudaMemcpyAsync(h, d_counters_, sizeof(h), cudaMemcpyDeviceToHost, sk));
         CUDA_OK(cudaStreamSynchronize(sk));
-        CUDA_OK(cudaStreamSynchronize(so));
+        if (!single) CUDA_OK(cudaStreamSynchronize(so));
         }
         catch (...)
         { // copies in flight still reference the caller's buffers and the cached device buffers: drain all three streams first
