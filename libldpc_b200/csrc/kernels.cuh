@@ -244,7 +244,7 @@ namespace b200
         double p = BP_EXP_C[11];
 #pragma unroll
         for (int i = 10; i >= 0; --i) p = __fma_rn(p, r, BP_EXP_C[i]);
-        return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p)); // * 2^k (k >= -1022)
+        return __hiloint2double(__double2hiint(p) + (int)((uint32_t)__double2loint(t) << 20), __double2loint(p)); // * 2^k (k >= -1022)
     }
     __device__ __forceinline__ double bp_log_ratio(double u, double v) // log((1 + u) / (1 + v)), u, v in [0, 1]
     {
@@ -288,7 +288,7 @@ namespace b200
         // 2^+-0.59, |w| <= 0.2003
         const int hn = __double2hiint(N), hd = __double2hiint(D);
         const int e0 = (hd - hn + 0x80000) >> 20;
-        const double Ns = __hiloint2double(hn + (e0 << 20), __double2loint(N));
+        const double Ns = __hiloint2double(hn + (int)((uint32_t)e0 << 20), __double2loint(N));
         const double num = D - Ns, den = D + Ns;
         // num / den, den in [1, 2^9): reciprocal seed (2^-23), one Newton step, quotient, one residual correction (error e^4)
         double rc;
